@@ -1,0 +1,488 @@
+/* ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C arithmetic restatement of the OpenCV stages the reference's CPU front-end
+ * calls.  The arithmetic lives in a third-party dependency that is NOT under
+ * /root/reference: OpenCV, pinned 3.4.16 by dynamic_vins/CMakeLists.txt:36.  The
+ * published algorithms (modules/video/src/lkpyramid.cpp, modules/imgproc/src/
+ * {pyramids,corner,featureselect,morph,drawing}.cpp) are restated here from
+ * SURVEY.md Appendix A/B and are pinned in tests/test_oracle_spec.py against the
+ * `cv2` 4.13.0 build in this image, at the reference's own call sites:
+ *   - cv::calcOpticalFlowPyrLK(img1,img2,pts1,pts2,status,err,Size(21,21),3)
+ *       dynamic_vins/src/front_end/feature_utils.cpp:43
+ *   - cv::calcOpticalFlowPyrLK(..., Size(21,21), 1, TermCriteria(COUNT+EPS,30,0.01), OPTFLOW_USE_INITIAL_FLOW)
+ *       dynamic_vins/src/front_end/feature_utils.cpp:50-53
+ *   - cv::goodFeaturesToTrack(gray, pts, n, 0.01, min_dist, mask)
+ *       dynamic_vins/src/front_end/background_tracker.cpp:85, instance_feature.cpp:381, dynamic_tracker.cpp:435
+ *   - cv::circle(mask, pt, r, 0, -1)      background_tracker.cpp:80, instance_feature.cpp:368, dynamic_tracker.cpp:430
+ *   - cv::erode(rect k x k)               feature_utils.h:142-146
+ *   - camodocal PinholeCamera::liftProjective  camera_models/src/camera_models/PinholeCamera.cc:450-510
+ *
+ * Two accumulation modes exist for the LK normal equations:
+ *   exact_int = 0 : float accumulators (what OpenCV's scalar loop does)
+ *   exact_int = 1 : exact 64-bit integer sums converted to float once (what the
+ *                   CUDA kernels do; the value OpenCV's float sums approximate)
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#define WIN 21
+#define HALF 10.0f
+#define BORDER 24          /* >= 22: patch taps reach [-21, w+20] */
+
+static inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * (n - 1) - p;
+    }
+    return p;
+}
+
+/* ---- cv::pyrDown, 8-bit: separable [1 4 6 4 1], REFLECT_101, (s+128)>>8, size ((w+1)/2,(h+1)/2) ---- */
+void spec_pyr_down(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
+    int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    int* row = (int*)malloc(sizeof(int) * (size_t)w * 5);
+    for (int y = 0; y < dh; y++) {
+        int acc_rows[5];
+        for (int k = 0; k < 5; k++) acc_rows[k] = reflect101(2 * y + k - 2, h);
+        for (int x = 0; x < dw; x++) {
+            int s = 0;
+            static const int kw[5] = {1, 4, 6, 4, 1};
+            for (int j = 0; j < 5; j++) {
+                const uint8_t* r = src + (size_t)acc_rows[j] * sstride;
+                int hs = 0;
+                for (int i = 0; i < 5; i++) hs += kw[i] * r[reflect101(2 * x + i - 2, w)];
+                s += kw[j] * hs;
+            }
+            dst[(size_t)y * dstride + x] = (uint8_t)((s + 128) >> 8);
+        }
+    }
+    free(row);
+}
+
+/* number of the last pyramid level cv::buildOpticalFlowPyramid keeps (winSize 21x21) */
+int spec_pyr_levels(int w, int h, int max_level) {
+    int lvl = 0;
+    while (lvl < max_level) {
+        int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= WIN || nh <= WIN) break;
+        w = nw; h = nh; lvl++;
+    }
+    return lvl;
+}
+
+/* ---- calcSharrDeriv: int16 (dx,dy) interleaved, REFLECT_101 inside the image ---- */
+void spec_scharr(const uint8_t* src, int w, int h, int sstride, int16_t* dst /* h*w*2 */) {
+    for (int y = 0; y < h; y++) {
+        const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * sstride;
+        const uint8_t* r1 = src + (size_t)y * sstride;
+        const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * sstride;
+        for (int x = 0; x < w; x++) {
+            int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+            int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10;
+            int t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+            int t1m = r2[xm] - r0[xm];
+            int t1c = r2[x] - r0[x];
+            int t1p = r2[xp] - r0[xp];
+            dst[((size_t)y * w + x) * 2 + 0] = (int16_t)(t0p - t0m);
+            dst[((size_t)y * w + x) * 2 + 1] = (int16_t)((t1p + t1m) * 3 + t1c * 10);
+        }
+    }
+}
+
+typedef struct {
+    int w, h;
+    int pitch;            /* of the padded u8 image */
+    uint8_t* img;         /* padded, origin at img + BORDER*pitch + BORDER */
+    int16_t* der;         /* padded (dx,dy), zero border, pitch*2 int16 per row */
+} level_t;
+
+static void make_level(level_t* L, const uint8_t* src, int w, int h, int sstride, int with_deriv) {
+    L->w = w; L->h = h; L->pitch = w + 2 * BORDER;
+    size_t rows = (size_t)h + 2 * BORDER;
+    L->img = (uint8_t*)malloc(rows * L->pitch);
+    for (int y = -BORDER; y < h + BORDER; y++) {
+        const uint8_t* r = src + (size_t)reflect101(y, h) * sstride;
+        uint8_t* d = L->img + (size_t)(y + BORDER) * L->pitch + BORDER;
+        for (int x = -BORDER; x < w + BORDER; x++) d[x] = r[reflect101(x, w)];
+    }
+    L->der = NULL;
+    if (with_deriv) {
+        L->der = (int16_t*)calloc(rows * L->pitch * 2, sizeof(int16_t));
+        int16_t* tmp = (int16_t*)malloc(sizeof(int16_t) * (size_t)w * h * 2);
+        spec_scharr(src, w, h, sstride, tmp);
+        for (int y = 0; y < h; y++)
+            memcpy(L->der + ((size_t)(y + BORDER) * L->pitch + BORDER) * 2, tmp + (size_t)y * w * 2,
+                   sizeof(int16_t) * (size_t)w * 2);
+        free(tmp);
+    }
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }   /* round-half-even (default FE mode) */
+static inline int cv_floor_f(float v) { return (int)floorf(v); }
+#define DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))
+
+/* One LK level for one point: LKTrackerInvoker::operator() body (lkpyramid.cpp). */
+static void lk_point_level(const level_t* I, const level_t* J, int level, int max_level, int use_init,
+                           const float* prev_pt_in, float* next_pt_io, uint8_t* status, int exact_int) {
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int W_BITS = 14;
+    float scale = (float)(1. / (1 << level));
+    float prevx = prev_pt_in[0] * scale, prevy = prev_pt_in[1] * scale;
+    float nextx, nexty;
+    if (level == max_level) {
+        if (use_init) { nextx = next_pt_io[0] * scale; nexty = next_pt_io[1] * scale; }
+        else { nextx = prevx; nexty = prevy; }
+    } else { nextx = next_pt_io[0] * 2.f; nexty = next_pt_io[1] * 2.f; }
+    next_pt_io[0] = nextx; next_pt_io[1] = nexty;
+
+    prevx -= HALF; prevy -= HALF;
+    int ipx = cv_floor_f(prevx), ipy = cv_floor_f(prevy);
+    if (ipx < -WIN || ipx >= I->w || ipy < -WIN || ipy >= I->h) {
+        if (level == 0) *status = 0;
+        return;
+    }
+    float a = prevx - ipx, b = prevy - ipy;
+    int iw00 = cv_round_f((1.f - a) * (1.f - b) * (1 << W_BITS));
+    int iw01 = cv_round_f(a * (1.f - b) * (1 << W_BITS));
+    int iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS));
+    int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+
+    int16_t Iw[WIN * WIN], dIx[WIN * WIN], dIy[WIN * WIN];
+    float fA11 = 0, fA12 = 0, fA22 = 0;
+    int64_t iA11 = 0, iA12 = 0, iA22 = 0;
+    int stepI = I->pitch, dstep = I->pitch * 2;
+    for (int y = 0; y < WIN; y++) {
+        const uint8_t* src = I->img + (size_t)(y + ipy + BORDER) * stepI + ipx + BORDER;
+        const int16_t* dsrc = I->der + ((size_t)(y + ipy + BORDER) * I->pitch + ipx + BORDER) * 2;
+        for (int x = 0; x < WIN; x++, dsrc += 2) {
+            int ival = DESCALE(src[x] * iw00 + src[x + 1] * iw01 + src[x + stepI] * iw10 + src[x + stepI + 1] * iw11,
+                               W_BITS - 5);
+            int ixval = DESCALE(dsrc[0] * iw00 + dsrc[2] * iw01 + dsrc[dstep] * iw10 + dsrc[dstep + 2] * iw11, W_BITS);
+            int iyval = DESCALE(dsrc[1] * iw00 + dsrc[3] * iw01 + dsrc[dstep + 1] * iw10 + dsrc[dstep + 3] * iw11,
+                                W_BITS);
+            Iw[y * WIN + x] = (int16_t)ival;
+            dIx[y * WIN + x] = (int16_t)ixval;
+            dIy[y * WIN + x] = (int16_t)iyval;
+            fA11 += (float)(ixval * ixval); fA12 += (float)(ixval * iyval); fA22 += (float)(iyval * iyval);
+            iA11 += (int64_t)ixval * ixval; iA12 += (int64_t)ixval * iyval; iA22 += (int64_t)iyval * iyval;
+        }
+    }
+    float A11, A12, A22;
+    if (exact_int) { A11 = (float)iA11 * FLT_SCALE; A12 = (float)iA12 * FLT_SCALE; A22 = (float)iA22 * FLT_SCALE; }
+    else { A11 = fA11 * FLT_SCALE; A12 = fA12 * FLT_SCALE; A22 = fA22 * FLT_SCALE; }
+    float D = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+    if ((double)minEig < 1e-4 || D < FLT_EPSILON) {
+        if (level == 0) *status = 0;
+        return;
+    }
+    D = 1.f / D;
+    nextx -= HALF; nexty -= HALF;
+    float pdx = 0, pdy = 0;
+    for (int j = 0; j < 30; j++) {
+        int inx = cv_floor_f(nextx), iny = cv_floor_f(nexty);
+        if (inx < -WIN || inx >= J->w || iny < -WIN || iny >= J->h) {
+            if (level == 0) *status = 0;
+            break;
+        }
+        a = nextx - inx; b = nexty - iny;
+        iw00 = cv_round_f((1.f - a) * (1.f - b) * (1 << W_BITS));
+        iw01 = cv_round_f(a * (1.f - b) * (1 << W_BITS));
+        iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS));
+        iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+        float fb1 = 0, fb2 = 0;
+        int64_t ib1 = 0, ib2 = 0;
+        int stepJ = J->pitch;
+        for (int y = 0; y < WIN; y++) {
+            const uint8_t* Jp = J->img + (size_t)(y + iny + BORDER) * stepJ + inx + BORDER;
+            for (int x = 0; x < WIN; x++) {
+                int diff = DESCALE(Jp[x] * iw00 + Jp[x + 1] * iw01 + Jp[x + stepJ] * iw10 + Jp[x + stepJ + 1] * iw11,
+                                   W_BITS - 5) - Iw[y * WIN + x];
+                fb1 += (float)(diff * dIx[y * WIN + x]);
+                fb2 += (float)(diff * dIy[y * WIN + x]);
+                ib1 += (int64_t)diff * dIx[y * WIN + x];
+                ib2 += (int64_t)diff * dIy[y * WIN + x];
+            }
+        }
+        float b1, b2;
+        if (exact_int) { b1 = (float)ib1 * FLT_SCALE; b2 = (float)ib2 * FLT_SCALE; }
+        else { b1 = fb1 * FLT_SCALE; b2 = fb2 * FLT_SCALE; }
+        float dx = (A12 * b2 - A22 * b1) * D;
+        float dy = (A12 * b1 - A11 * b2) * D;
+        nextx += dx; nexty += dy;
+        next_pt_io[0] = nextx + HALF; next_pt_io[1] = nexty + HALF;
+        if ((double)dx * dx + (double)dy * dy <= 0.01 * 0.01) break;
+        if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+            next_pt_io[0] -= dx * 0.5f; next_pt_io[1] -= dy * 0.5f;
+            break;
+        }
+        pdx = dx; pdy = dy;
+    }
+    if (*status && level == 0) {
+        float qx = next_pt_io[0] - HALF, qy = next_pt_io[1] - HALF;
+        int ix = cv_floor_f(qx), iy = cv_floor_f(qy);
+        if (ix < -WIN || ix >= J->w || iy < -WIN || iy >= J->h) *status = 0;
+    }
+}
+
+/* cv::calcOpticalFlowPyrLK(img1,img2,pts1,pts2,status,err,Size(21,21),max_level,(COUNT+EPS,30,0.01),flags)
+ * pts2 is in/out (initial flow when use_init).  Returns the effective max level. */
+int spec_lk(const uint8_t* img1, const uint8_t* img2, int w, int h, int stride1, int stride2,
+            const float* pts1, float* pts2, uint8_t* status, int n, int max_level, int use_init, int exact_int) {
+    int L = spec_pyr_levels(w, h, max_level);
+    level_t* P1 = (level_t*)malloc(sizeof(level_t) * (L + 1));
+    level_t* P2 = (level_t*)malloc(sizeof(level_t) * (L + 1));
+    uint8_t *c1 = NULL, *c2 = NULL;
+    const uint8_t *s1 = img1, *s2 = img2;
+    int cw = w, ch = h, st1 = stride1, st2 = stride2;
+    for (int l = 0; l <= L; l++) {
+        make_level(&P1[l], s1, cw, ch, st1, 1);
+        make_level(&P2[l], s2, cw, ch, st2, 0);
+        if (l < L) {
+            int nw = (cw + 1) / 2, nh = (ch + 1) / 2;
+            uint8_t* d1 = (uint8_t*)malloc((size_t)nw * nh);
+            uint8_t* d2 = (uint8_t*)malloc((size_t)nw * nh);
+            spec_pyr_down(s1, cw, ch, st1, d1, nw);
+            spec_pyr_down(s2, cw, ch, st2, d2, nw);
+            free(c1); free(c2);
+            c1 = d1; c2 = d2; s1 = d1; s2 = d2; cw = nw; ch = nh; st1 = st2 = nw;
+        }
+    }
+    free(c1); free(c2);
+    for (int i = 0; i < n; i++) status[i] = 1;
+    for (int l = L; l >= 0; l--)
+        for (int i = 0; i < n; i++)
+            lk_point_level(&P1[l], &P2[l], l, L, use_init, pts1 + 2 * i, pts2 + 2 * i, status + i, exact_int);
+    for (int l = 0; l <= L; l++) { free(P1[l].img); free(P1[l].der); free(P2[l].img); }
+    free(P1); free(P2);
+    return L;
+}
+
+/* FeatureTrackByLK  (dynamic_vins/src/front_end/feature_utils.cpp:35-69) */
+void spec_feature_track_by_lk(const uint8_t* img1, const uint8_t* img2, int w, int h, int stride1, int stride2,
+                              const float* pts1, float* pts2, uint8_t* status, int n, int flow_back,
+                              int max_level, int exact_int, float* rev_out /* nullable, n*2 */) {
+    spec_lk(img1, img2, w, h, stride1, stride2, pts1, pts2, status, n, max_level, 0, exact_int);
+    if (flow_back) {
+        float* rev = (float*)malloc(sizeof(float) * 2 * (size_t)n);
+        uint8_t* rst = (uint8_t*)malloc((size_t)n);
+        memcpy(rev, pts1, sizeof(float) * 2 * (size_t)n);
+        spec_lk(img2, img1, w, h, stride2, stride1, pts2, rev, rst, n, 1, 1, exact_int);
+        for (int i = 0; i < n; i++) {
+            float dx = pts1[2 * i] - rev[2 * i], dy = pts1[2 * i + 1] - rev[2 * i + 1];
+            float d = sqrtf(dx * dx + dy * dy);
+            status[i] = (status[i] && rst[i] && (double)d <= 0.5) ? 1 : 0;
+        }
+        if (rev_out) memcpy(rev_out, rev, sizeof(float) * 2 * (size_t)n);
+        free(rev); free(rst);
+    }
+    for (int i = 0; i < n; i++) {
+        if (!status[i]) continue;
+        int x = cv_round_f(pts2[2 * i]), y = cv_round_f(pts2[2 * i + 1]);
+        if (!(1 <= x && x < w - 1 && 1 <= y && y < h - 1)) status[i] = 0;      /* InBorder, feature_utils.h:68-74 */
+    }
+}
+
+/* ---- cv::cornerMinEigenVal(blockSize 3, ksize 3) ----  */
+void spec_min_eigen_val(const uint8_t* img, int w, int h, int stride, float* out /* h*w */) {
+    const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));   /* scale = 1/((1<<(ksize-1))*blockSize*255) */
+    const float s2 = s * 2.0f;
+    size_t n = (size_t)w * h;
+    float* Dx = (float*)malloc(sizeof(float) * n);
+    float* Dy = (float*)malloc(sizeof(float) * n);
+    /* Dx: row kernel [-1 0 1] (exact ints), column kernel [1 2 1]*scale : fma(s, d0+d2, s2*d1)
+     * Dy: row kernel [1 2 1]*scale: fma(s, r, fma(s2, c, s*l)), column kernel [-1 0 1] */
+    float* dxr = (float*)malloc(sizeof(float) * n);
+    float* smr = (float*)malloc(sizeof(float) * n);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* r = img + (size_t)y * stride;
+        for (int x = 0; x < w; x++) {
+            int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+            dxr[(size_t)y * w + x] = (float)((int)r[xp] - (int)r[xm]);
+            smr[(size_t)y * w + x] = fmaf(s, (float)r[xp], fmaf(s2, (float)r[x], s * (float)r[xm]));
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+        for (int x = 0; x < w; x++) {
+            float d0 = dxr[(size_t)ym * w + x], d1 = dxr[(size_t)y * w + x], d2 = dxr[(size_t)yp * w + x];
+            Dx[(size_t)y * w + x] = fmaf(s, d0 + d2, s2 * d1);
+            Dy[(size_t)y * w + x] = smr[(size_t)yp * w + x] - smr[(size_t)ym * w + x];
+        }
+    }
+    free(dxr); free(smr);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            double sxx = 0, sxy = 0, syy = 0;
+            for (int j = -1; j <= 1; j++) {
+                int yy = reflect101(y + j, h);
+                for (int i = -1; i <= 1; i++) {
+                    int xx = reflect101(x + i, w);
+                    float dx = Dx[(size_t)yy * w + xx], dy = Dy[(size_t)yy * w + xx];
+                    sxx += (double)(dx * dx); sxy += (double)(dx * dy); syy += (double)(dy * dy);
+                }
+            }
+            float a = (float)sxx * 0.5f, b = (float)sxy, c = (float)syy * 0.5f;
+            out[(size_t)y * w + x] = (a + c) - sqrtf((a - c) * (a - c) + b * b);
+        }
+    }
+    free(Dx); free(Dy);
+}
+
+typedef struct { float v; int idx; } cand_t;
+static int cand_cmp(const void* pa, const void* pb) {
+    const cand_t* a = (const cand_t*)pa; const cand_t* b = (const cand_t*)pb;
+    if (a->v > b->v) return -1;
+    if (a->v < b->v) return 1;
+    return (a->idx > b->idx) ? -1 : (a->idx < b->idx ? 1 : 0);
+}
+
+/* cv::goodFeaturesToTrack stages 2..6 on a given response map `eig` (h*w floats).
+ * Returns number of corners written to out_xy (x,y floats, acceptance order). */
+int spec_gftt_select(const float* eig, int w, int h, const uint8_t* mask, int mstride, int max_corners,
+                     double quality, double min_dist, float* out_xy, int* n_cand_out) {
+    float maxv = 0; int any = 0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (!mask || mask[(size_t)y * mstride + x]) {
+                float v = eig[(size_t)y * w + x];
+                if (!any || v > maxv) { maxv = v; any = 1; }
+            }
+    double maxVal = any ? (double)maxv : 0.0;
+    float thr = (float)(maxVal * quality);
+    size_t cap = 1024, nc = 0;
+    cand_t* c = (cand_t*)malloc(sizeof(cand_t) * cap);
+#define TZ(v) ((v) > thr ? (v) : 0.f)
+    for (int y = 1; y < h - 1; y++)
+        for (int x = 1; x < w - 1; x++) {
+            float v = TZ(eig[(size_t)y * w + x]);
+            if (v == 0) continue;
+            if (mask && !mask[(size_t)y * mstride + x]) continue;
+            float m = v;
+            for (int j = -1; j <= 1; j++)
+                for (int i = -1; i <= 1; i++) {
+                    float t = TZ(eig[(size_t)(y + j) * w + x + i]);
+                    if (t > m) m = t;
+                }
+            if (v != m) continue;
+            if (nc == cap) { cap *= 2; c = (cand_t*)realloc(c, sizeof(cand_t) * cap); }
+            c[nc].v = v; c[nc].idx = y * w + x; nc++;
+        }
+    if (n_cand_out) *n_cand_out = (int)nc;
+    qsort(c, nc, sizeof(cand_t), cand_cmp);
+    int ncorners = 0;
+    if (min_dist >= 1) {
+        int cell = (int)lrint(min_dist);
+        int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+        int* head = (int*)malloc(sizeof(int) * (size_t)gw * gh);
+        int* next = (int*)malloc(sizeof(int) * (nc + 1));
+        float* ax = (float*)malloc(sizeof(float) * (nc + 1));
+        float* ay = (float*)malloc(sizeof(float) * (nc + 1));
+        for (int i = 0; i < gw * gh; i++) head[i] = -1;
+        double md2 = min_dist * min_dist;
+        for (size_t i = 0; i < nc; i++) {
+            int y = c[i].idx / w, x = c[i].idx - y * w;
+            int xc = x / cell, yc = y / cell;
+            int x1 = xc - 1 < 0 ? 0 : xc - 1, y1 = yc - 1 < 0 ? 0 : yc - 1;
+            int x2 = xc + 1 > gw - 1 ? gw - 1 : xc + 1, y2 = yc + 1 > gh - 1 ? gh - 1 : yc + 1;
+            int good = 1;
+            for (int yy = y1; yy <= y2 && good; yy++)
+                for (int xx = x1; xx <= x2 && good; xx++)
+                    for (int k = head[yy * gw + xx]; k >= 0; k = next[k]) {
+                        float dx = x - ax[k], dy = y - ay[k];
+                        if ((double)(dx * dx + dy * dy) < md2) { good = 0; break; }
+                    }
+            if (good) {
+                ax[ncorners] = (float)x; ay[ncorners] = (float)y;
+                next[ncorners] = head[yc * gw + xc]; head[yc * gw + xc] = ncorners;
+                out_xy[2 * ncorners] = (float)x; out_xy[2 * ncorners + 1] = (float)y;
+                ncorners++;
+                if (max_corners > 0 && ncorners == max_corners) break;
+            }
+        }
+        free(head); free(next); free(ax); free(ay);
+    } else {
+        for (size_t i = 0; i < nc; i++) {
+            int y = c[i].idx / w, x = c[i].idx - y * w;
+            out_xy[2 * ncorners] = (float)x; out_xy[2 * ncorners + 1] = (float)y;
+            ncorners++;
+            if (max_corners > 0 && ncorners == max_corners) break;
+        }
+    }
+    free(c);
+    return ncorners;
+}
+
+int spec_good_features(const uint8_t* img, int w, int h, int stride, const uint8_t* mask, int mstride,
+                       int max_corners, double quality, double min_dist, float* out_xy) {
+    float* eig = (float*)malloc(sizeof(float) * (size_t)w * h);
+    spec_min_eigen_val(img, w, h, stride, eig);
+    int n = spec_gftt_select(eig, w, h, mask, mstride, max_corners, quality, min_dist, out_xy, NULL);
+    free(eig);
+    return n;
+}
+
+/* cv::circle(mask, cvRound(pt), r, 0, -1): pixel cleared  <=>  dx^2+dy^2 <= r^2 (clipped) */
+void spec_disc_mask(uint8_t* mask, int w, int h, int stride, const float* pts, int n, int r) {
+    for (int i = 0; i < n; i++) {
+        int cx = cv_round_f(pts[2 * i]), cy = cv_round_f(pts[2 * i + 1]);
+        for (int dy = -r; dy <= r; dy++) {
+            int y = cy + dy;
+            if (y < 0 || y >= h) continue;
+            for (int dx = -r; dx <= r; dx++) {
+                int x = cx + dx;
+                if (x < 0 || x >= w) continue;
+                if (dx * dx + dy * dy <= r * r) mask[(size_t)y * stride + x] = 0;
+            }
+        }
+    }
+}
+
+/* cv::erode with MORPH_RECT k x k, anchor k/2, border = +inf */
+void spec_erode_rect(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int k) {
+    int a = k / 2;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int m = 255;
+            for (int j = 0; j < k; j++) {
+                int yy = y - a + j;
+                if (yy < 0 || yy >= h) continue;
+                for (int i = 0; i < k; i++) {
+                    int xx = x - a + i;
+                    if (xx < 0 || xx >= w) continue;
+                    int v = src[(size_t)yy * sstride + xx];
+                    if (v < m) m = v;
+                }
+            }
+            dst[(size_t)y * dstride + x] = (uint8_t)m;
+        }
+}
+
+/* camodocal PinholeCamera::liftProjective + the b.x/b.z float narrowing of InstFeat::UndistortedPts */
+void spec_lift(const double* cam /* fx fy cx cy k1 k2 p1 p2 */, const float* pts, int n, float off_x, float off_y,
+               float* out) {
+    double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], k1 = cam[4], k2 = cam[5], p1 = cam[6], p2 = cam[7];
+    double iK11 = 1.0 / fx, iK13 = -cx / fx, iK22 = 1.0 / fy, iK23 = -cy / fy;
+    int nod = (k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0);
+    for (int i = 0; i < n; i++) {
+        double u = (double)(pts[2 * i] + off_x), v = (double)(pts[2 * i + 1] + off_y);
+        double mxd = iK11 * u + iK13, myd = iK22 * v + iK23, mxu = mxd, myu = myd;
+        if (!nod) {
+            for (int it = 0; it < 8; it++) {
+                double x = (it == 0) ? mxd : mxu, y = (it == 0) ? myd : myu;
+                double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2;
+                double rad = k1 * rho2 + k2 * rho2 * rho2;
+                double dux = x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2);
+                double duy = y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2);
+                mxu = mxd - dux; myu = myd - duy;
+            }
+        }
+        out[2 * i] = (float)(mxu / 1.0); out[2 * i + 1] = (float)(myu / 1.0);
+    }
+}
