@@ -1,0 +1,114 @@
+// Shared device/host definitions for the dvfe kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dvfe.h"
+
+// Padded pyramid storage.  LK reads a 22x22 window whose origin lies in [-21, w-1] x [-21, h-1]
+// (cv::calcOpticalFlowPyrLK keeps a winSize border around every level), plus one more pixel for
+// the on-the-fly Scharr taps, so every level is stored with a REFLECT_101 border of PADX/PADY
+// pixels; rows start 16-byte aligned so the LK gather can use aligned word loads.
+#define DVFE_PADX 32
+#define DVFE_PADY 24
+#define DVFE_WIN 21
+#define DVFE_HALF_WIN 10.0f
+
+struct PyrLevel {
+    int w, h;          // level size
+    int pitch;         // bytes per padded row (multiple of 16, >= w + 2*PADX)
+    unsigned offset;   // byte offset of padded row 0 inside the pyramid allocation
+};
+struct PyrDesc {
+    int n_levels;      // levels kept = effective maxLevel + 1 (cv::buildOpticalFlowPyramid truncation rule)
+    PyrLevel lv[DVFE_MAX_PYR_LEVELS];
+    unsigned bytes;    // size of one pyramid (multiple of 256)
+};
+
+__host__ __device__ __forceinline__ int reflect101(int p, int n) {
+    // cv::BORDER_REFLECT_101:  gfedcb|abcdefgh|gfedcba
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+__host__ __device__ __forceinline__ const uint8_t* pyr_px(const uint8_t* base, const PyrLevel& L) {
+    // pointer to pixel (0,0) of the level
+    return base + L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;
+}
+
+static inline PyrDesc make_pyr_desc(int w, int h, int max_level) {
+    PyrDesc d{};
+    unsigned off = 0;
+    int lw = w, lh = h, l = 0;
+    for (;;) {
+        PyrLevel& L = d.lv[l];
+        L.w = lw; L.h = lh;
+        L.pitch = ((lw + 2 * DVFE_PADX) + 15) & ~15;
+        L.offset = off;
+        off += (unsigned)(((size_t)L.pitch * (lh + 2 * DVFE_PADY) + 255) & ~(size_t)255);
+        l++;
+        if (l > max_level || l >= DVFE_MAX_PYR_LEVELS) break;
+        int nw = (lw + 1) / 2, nh = (lh + 1) / 2;
+        if (nw <= DVFE_WIN || nh <= DVFE_WIN) break;   // buildOpticalFlowPyramid: stop when next level <= winSize
+        lw = nw; lh = nh;
+    }
+    d.n_levels = l;
+    d.bytes = off;
+    return d;
+}
+
+// ---- launch accounting / error handling -------------------------------------------------
+extern unsigned long long g_dvfe_launches;
+void dvfe_set_error(const char* fmt, ...);
+
+#define DVFE_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                               \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+        ++g_dvfe_launches;                                             \
+    } while (0)
+
+#define DVFE_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            dvfe_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return DVFE_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// ---- one independent point set processed by the LK kernel --------------------------------
+// (a stream's background set, or one instance's ROI set)
+struct LkGroup {
+    const uint8_t* pyrA;     // pyramid of the template image (FeatureTrackByLK img1)
+    const uint8_t* pyrB;     // pyramid of the search image   (FeatureTrackByLK img2)
+    PyrDesc desc;            // geometry of both
+    const float2* ptsA;      // pts1
+    float2* ptsB;            // pts2 (out)
+    float2* rev;             // backward-tracked pts1 (out, nullable)
+    uint8_t* status;         // out
+    const int* n;            // number of points (device)
+    const uint8_t* mask;     // nullable: status &= mask[cvRound(pts2)] != 0
+    int mask_pitch;
+    float offx, offy;        // added to pts1 first (InstFeat::TrackRightByPad)
+};
+
+// ---- per-stream point state (struct of arrays, capacity `cap` per stream) ------------------
+struct PointSet {
+    float2* pts;             // curr_points
+    float2* last;            // last_points
+    float2* un;              // curr_un_points
+    float2* prev_un;         // prev_id_pts[id] for tracked points
+    float2* vel;             // pts_velocity
+    uint32_t* ids;
+    int32_t* track_cnt;
+    float2* rpts;            // right_points (aligned with left index; valid where rstatus)
+    float2* run;             // right_un_points
+    float2* rvel;
+    float2* rprev_un;        // right_prev_id_pts[id]
+    uint8_t* rprev_valid;
+    uint8_t* rstatus;        // right match status of this frame
+    uint8_t* status;         // temporal LK status
+    int* n;                  // [n_sets]
+};

@@ -1,0 +1,68 @@
+// Internal launch interfaces between the .cu files of libdvfe.
+#pragma once
+#include "common.cuh"
+
+// A batch of images: set 0 (left) and set 1 (right), `per_set` images each, laid out with a stride.
+struct PyrImgSet {
+    const uint8_t* src[2];
+    uint8_t* dst[2];
+    size_t src_stride;   // bytes between consecutive source images of a set
+    size_t dst_stride;   // bytes between consecutive pyramids of a set
+    int per_set;
+};
+
+// pyramid.cu
+int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st);
+int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);
+
+// lk.cu
+int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st);
+
+// gftt.cu
+struct GfttJob {                 // one detection problem (a stream's image, or one instance ROI)
+    const uint8_t* img;          // u8 image, pixel (0,0)
+    int img_pitch;
+    int w, h;
+    const uint8_t* region_mask;  // nullable (all 255)
+    int region_pitch;
+    uint8_t* mask;               // detection mask scratch (w x h, pitch mask_pitch): region minus discs
+    int mask_pitch;
+    float* eig;                  // response map scratch (w x h, dense)
+    const float* eig_in;         // nullable: externally supplied response map (seam op)
+    unsigned long long* cand;    // candidate keys scratch [cand_cap]
+    unsigned long long* cand2;   // second buffer [cand_cap]
+    int cand_cap;
+    int* cell_count;             // scratch [n_cells + 1]
+    int* counters;               // [8]: 0 n_cand, 1 masked max (ordered int), 2 overflow flag, 3 n_accepted, 4 n_new
+    uint8_t* state;              // scratch [cand_cap]
+    // point set the discs come from and new corners are appended to
+    float2* pts;
+    uint32_t* ids;               // nullable
+    int32_t* track_cnt;          // nullable
+    int* n;                      // current count (in/out)
+    uint32_t* next_id;           // id counter (in/out), nullable
+    int max_cnt;                 // capacity target: K = max_cnt - n
+    int min_needed;              // detect only if K >= min_needed (1: TrackImage, 10: DetectNewFeature)
+    int disc_radius;             // radius of the discs around existing points
+    float min_dist;              // NMS distance
+    double quality;              // 0.01
+    int id_order;                // jobs sharing next_id are serialised in this order (instances)
+};
+int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
+                cudaStream_t st);
+int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st);
+int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n, int max_pts, int radius,
+                     cudaStream_t st);
+
+// morph.cu
+int launch_erode_rect(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, uint8_t* tmp, int w, int h, int k,
+                      int n_img, size_t img_stride, const int* enable, cudaStream_t st);
+
+// points.cu
+struct CamParams {
+    double inv_K11, inv_K13, inv_K22, inv_K23;
+    double k1, k2, p1, p2;
+    int no_distortion;
+};
+CamParams make_cam(const dvfe_camera& c);
+int launch_lift(const CamParams& cam, const float2* pts, int n, float offx, float offy, float2* out, cudaStream_t st);

@@ -1,0 +1,208 @@
+// Per-point bookkeeping kernels — replace the std::vector / std::map glue of InstFeat
+// (dynamic_vins/src/front_end/instance_feature.{h,cpp}) and FeatureTracker::SetOutputFeats:
+//   ReduceVector (front_end/feature_utils.h:77-85)            -> order-preserving compaction
+//   InstFeat::UndistortedPts / RightUndistortedPts / UndistortedPointsWithAddOffset
+//     (instance_feature.cpp:94-103,123-133,137-146) -> PinholeCamera::liftProjective
+//     (/root/reference/camera_models/src/camera_models/PinholeCamera.cc:450-510, distortion :646-660), fp64
+//   InstFeat::PtsVelocity / RightPtsVelocity (instance_feature.cpp:26-85): the id->point maps are replaced by
+//     values carried with the points through the compaction (an id is in prev_id_pts iff the point existed in
+//     the previous frame)
+//   InstFeat::PostProcess (instance_feature.h:88-101): prev := curr, done in place
+//   FeatureTracker::SetOutputFeats (front_end/background_tracker.cpp:340-392): records sorted by (id, cam)
+#include "kernels.cuh"
+#include "state.cuh"
+
+CamParams make_cam(const dvfe_camera& c) {
+    CamParams p;
+    p.inv_K11 = 1.0 / c.fx;
+    p.inv_K13 = -c.cx / c.fx;
+    p.inv_K22 = 1.0 / c.fy;
+    p.inv_K23 = -c.cy / c.fy;
+    p.k1 = c.k1; p.k2 = c.k2; p.p1 = c.p1; p.p2 = c.p2;
+    p.no_distortion = (c.k1 == 0.0 && c.k2 == 0.0 && c.p1 == 0.0 && c.p2 == 0.0);
+    return p;
+}
+
+__device__ __forceinline__ float2 lift_projective(const CamParams& cam, float px, float py) {
+    const double u = (double)px, v = (double)py;
+    const double mx_d = cam.inv_K11 * u + cam.inv_K13;
+    const double my_d = cam.inv_K22 * v + cam.inv_K23;
+    double mx_u = mx_d, my_u = my_d;
+    if (!cam.no_distortion) {
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {      // n = 8 fixed-point steps, the first from (mx_d, my_d)
+            const double x = mx_u, y = my_u;
+            const double mx2 = x * x, my2 = y * y, mxy = x * y;
+            const double rho2 = mx2 + my2;
+            const double rad = cam.k1 * rho2 + cam.k2 * rho2 * rho2;
+            const double dux = x * rad + 2.0 * cam.p1 * mxy + cam.p2 * (rho2 + 2.0 * mx2);
+            const double duy = y * rad + 2.0 * cam.p2 * mxy + cam.p1 * (rho2 + 2.0 * my2);
+            mx_u = mx_d - dux;
+            my_u = my_d - duy;
+        }
+    }
+    return make_float2((float)mx_u, (float)my_u);    // b.x / b.z with b.z == 1.0
+}
+
+__global__ void k_lift(CamParams cam, const float2* __restrict__ pts, int n, float offx, float offy, float2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 p = pts[i];
+    out[i] = lift_projective(cam, p.x + offx, p.y + offy);
+}
+
+int launch_lift(const CamParams& cam, const float2* pts, int n, float offx, float offy, float2* out, cudaStream_t st) {
+    if (n <= 0) return DVFE_OK;
+    DVFE_LAUNCH(k_lift, (n + 127) / 128, 128, 0, st, cam, pts, n, offx, offy, out);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// ---- ReduceVector after the temporal LK: keep status != 0, preserve order; track_cnt++ ---------------
+// One block per point set; in-place (destination index <= source index, chunks are read before written).
+__global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int cap) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int set = blockIdx.x;
+    const size_t o = (size_t)set * cap;
+    const int n = S.n[set];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 256) {
+        const int i = c0 + tid;
+        const bool keep = (i < n) && S.status[o + i] != 0;
+        float2 p = make_float2(0, 0), un = p, rp = p;
+        uint32_t id = 0; int32_t tc = 0; uint8_t rv = 0;
+        if (keep) {
+            p = S.lk_out[o + i]; un = S.un[o + i]; id = S.ids[o + i]; tc = S.track_cnt[o + i];
+            rp = S.rprev_un[o + i]; rv = S.rprev_valid[o + i];
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        int off = s_base;
+        for (int wv = 0; wv < warp; wv++) off += s_warp[wv];
+        if (keep) {
+            const int j = off + __popc(ballot & ((1u << lane) - 1));
+            S.pts[o + j] = p; S.un[o + j] = un; S.ids[o + j] = id; S.track_cnt[o + j] = tc + 1;
+            S.rprev_un[o + j] = rp; S.rprev_valid[o + j] = rv;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int wv = 0; wv < 8; wv++) tot += s_warp[wv];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) S.n[set] = s_base;
+}
+
+int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st) {
+    if (n_sets <= 0) return DVFE_OK;
+    DVFE_LAUNCH(k_compact_tracked, n_sets, 256, 0, st, S, cap);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// ---- UndistortedPts + PtsVelocity for the left image; un[] holds prev_id_pts on entry, curr on exit ------
+__global__ void __launch_bounds__(128) k_left_post(PointSetArrays S, int cap, CamParams cam, const double* __restrict__ dt,
+                                                   const float2* __restrict__ offset /* nullable, per set */) {
+    const int set = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n[set]) return;
+    const size_t k = (size_t)set * cap + i;
+    const float2 p = S.pts[k];
+    const float2 off = offset ? offset[set] : make_float2(0.f, 0.f);
+    const float2 un = lift_projective(cam, p.x + off.x, p.y + off.y);
+    float2 vel = make_float2(0.f, 0.f);
+    if (S.track_cnt[k] > 1) {          // id is in prev_id_pts  <=>  the point was tracked from the last frame
+        const float2 prev = S.un[k];
+        const double d = dt[set];
+        vel.x = (float)((double)(un.x - prev.x) / d);
+        vel.y = (float)((double)(un.y - prev.y) / d);
+    } else {
+        S.rprev_valid[k] = 0;          // a new id has no entry in right_prev_id_pts
+    }
+    S.un[k] = un;
+    S.vel[k] = vel;
+}
+
+int launch_left_post(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam, const double* d_dt,
+                     const float2* d_offset, cudaStream_t st) {
+    if (n_sets <= 0) return DVFE_OK;
+    dim3 grid((cap + 127) / 128, n_sets);
+    DVFE_LAUNCH(k_left_post, grid, 128, 0, st, S, cap, cam, d_dt, d_offset);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// ---- right image: RightUndistortedPts + RightPtsVelocity + SetOutputFeats --------------------------------
+// One block per point set.  Emits dvfe_obs records sorted by (id, cam): the point arrays are always in
+// ascending id order (survivors keep their order, new ids are appended).
+__global__ void __launch_bounds__(256) k_right_post_pack(PointSetArrays S, int cap, CamParams cam1, const double* __restrict__ dt,
+                                                         int stereo_now, dvfe_obs* __restrict__ obs, int* __restrict__ n_obs) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int set = blockIdx.x;
+    const size_t o = (size_t)set * cap;
+    const int n = S.n[set];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    dvfe_obs* out = obs + (size_t)set * 2 * cap;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 256) {
+        const int i = c0 + tid;
+        const bool has_r = stereo_now && (i < n) && S.rstatus[o + i] != 0;
+        float2 run = make_float2(0, 0), rvel = run, rp = run;
+        if (has_r) {
+            rp = S.rpts[o + i];
+            run = lift_projective(cam1, rp.x, rp.y);
+            if (S.rprev_valid[o + i]) {
+                const float2 prev = S.rprev_un[o + i];
+                const double d = dt[set];
+                rvel.x = (float)((double)(run.x - prev.x) / d);
+                rvel.y = (float)((double)(run.y - prev.y) / d);
+            }
+        }
+        if (stereo_now && i < n) {     // right_prev_id_pts = right_curr_id_pts
+            S.rprev_valid[o + i] = has_r ? 1 : 0;
+            if (has_r) S.rprev_un[o + i] = run;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, has_r);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        int off = s_base;
+        for (int wv = 0; wv < warp; wv++) off += s_warp[wv];
+        if (i < n) {
+            const int j = i + off + __popc(ballot & ((1u << lane) - 1));
+            const float2 p = S.pts[o + i], un = S.un[o + i], vel = S.vel[o + i];
+            dvfe_obs r;
+            r.id = S.ids[o + i]; r.cam = 0;
+            r.v[0] = un.x; r.v[1] = un.y; r.v[2] = 1.0; r.v[3] = p.x; r.v[4] = p.y; r.v[5] = vel.x; r.v[6] = vel.y;
+            out[j] = r;
+            if (has_r) {
+                r.cam = 1;
+                r.v[0] = run.x; r.v[1] = run.y; r.v[3] = rp.x; r.v[4] = rp.y; r.v[5] = rvel.x; r.v[6] = rvel.y;
+                out[j + 1] = r;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int wv = 0; wv < 8; wv++) tot += s_warp[wv];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_obs[set] = n + s_base;
+}
+
+int launch_right_post_pack(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam1, const double* d_dt,
+                           int stereo_now, dvfe_obs* obs, int* n_obs, cudaStream_t st) {
+    if (n_sets <= 0) return DVFE_OK;
+    DVFE_LAUNCH(k_right_post_pack, n_sets, 256, 0, st, S, cap, cam1, d_dt, stereo_now, obs, n_obs);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}

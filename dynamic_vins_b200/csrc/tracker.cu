@@ -1,0 +1,406 @@
+// C ABI of libdvfe (include/dvfe.h): the batched, device-resident frame step that replaces
+// FeatureTracker::TrackImage / TrackSemanticImage (dynamic_vins/src/front_end/background_tracker.cpp:52-158,
+// 757-837) and the seam-level operators.  Host code only orchestrates launches; no pixel or point
+// arithmetic happens on the CPU and there is no fallback when no CUDA device is present.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+#include "state.cuh"
+#include "tracker.h"
+
+unsigned long long g_dvfe_launches = 0;
+static char g_err[512] = "";
+
+void dvfe_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define DVFE_CHECK(call)                 \
+    do {                                 \
+        int rc__ = (call);               \
+        if (rc__ != DVFE_OK) return rc__; \
+    } while (0)
+
+template <typename T>
+static int dmalloc(T** p, size_t count) {
+    DVFE_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    DVFE_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+    return DVFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int alloc_point_sets(PointSetArrays* S, int n_sets, int cap) {
+    const size_t N = (size_t)n_sets * cap;
+    DVFE_CHECK(dmalloc(&S->pts, N));
+    DVFE_CHECK(dmalloc(&S->lk_out, N));
+    DVFE_CHECK(dmalloc(&S->un, N));
+    DVFE_CHECK(dmalloc(&S->vel, N));
+    DVFE_CHECK(dmalloc(&S->ids, N));
+    DVFE_CHECK(dmalloc(&S->track_cnt, N));
+    DVFE_CHECK(dmalloc(&S->status, N));
+    DVFE_CHECK(dmalloc(&S->rpts, N));
+    DVFE_CHECK(dmalloc(&S->rstatus, N));
+    DVFE_CHECK(dmalloc(&S->rprev_un, N));
+    DVFE_CHECK(dmalloc(&S->rprev_valid, N));
+    DVFE_CHECK(dmalloc(&S->n, (size_t)n_sets));
+    return DVFE_OK;
+}
+
+void free_point_sets(PointSetArrays* S) {
+    cudaFree(S->pts); cudaFree(S->lk_out); cudaFree(S->un); cudaFree(S->vel); cudaFree(S->ids);
+    cudaFree(S->track_cnt); cudaFree(S->status); cudaFree(S->rpts); cudaFree(S->rstatus);
+    cudaFree(S->rprev_un); cudaFree(S->rprev_valid); cudaFree(S->n);
+    memset(S, 0, sizeof(*S));
+}
+
+int gftt_cells(int w, int h, float min_dist) {
+    int cell = (int)lrintf(min_dist);
+    if (cell < 1) cell = 1;
+    return ((w + cell - 1) / cell) * ((h + cell - 1) / cell);
+}
+
+int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist) {
+    sc->n_jobs = n_jobs;
+    sc->w = w; sc->h = h;
+    sc->mask_pitch = (w + 15) & ~15;
+    sc->cand_cap = (w * h) / 4 + 4096;
+    sc->n_cells = gftt_cells(w, h, min_dist);
+    DVFE_CHECK(dmalloc(&sc->mask, (size_t)n_jobs * sc->mask_pitch * h));
+    DVFE_CHECK(dmalloc(&sc->eig, (size_t)n_jobs * w * h));
+    DVFE_CHECK(dmalloc(&sc->cand, (size_t)n_jobs * sc->cand_cap));
+    DVFE_CHECK(dmalloc(&sc->cand2, (size_t)n_jobs * sc->cand_cap));
+    DVFE_CHECK(dmalloc(&sc->state, (size_t)n_jobs * sc->cand_cap));
+    DVFE_CHECK(dmalloc(&sc->cell_count, (size_t)n_jobs * 2 * (sc->n_cells + 1)));
+    DVFE_CHECK(dmalloc(&sc->counters, (size_t)n_jobs * 8));
+    return DVFE_OK;
+}
+
+void free_gftt_scratch(GfttScratch* sc) {
+    cudaFree(sc->mask); cudaFree(sc->eig); cudaFree(sc->cand); cudaFree(sc->cand2); cudaFree(sc->state);
+    cudaFree(sc->cell_count); cudaFree(sc->counters);
+    memset(sc, 0, sizeof(*sc));
+}
+
+void gftt_job_bind_scratch(GfttJob* J, const GfttScratch& sc, int j) {
+    J->mask = sc.mask + (size_t)j * sc.mask_pitch * sc.h;
+    J->mask_pitch = sc.mask_pitch;
+    J->eig = sc.eig + (size_t)j * sc.w * sc.h;
+    J->cand = sc.cand + (size_t)j * sc.cand_cap;
+    J->cand2 = sc.cand2 + (size_t)j * sc.cand_cap;
+    J->cand_cap = sc.cand_cap;
+    J->state = sc.state + (size_t)j * sc.cand_cap;
+    J->cell_count = sc.cell_count + (size_t)j * 2 * (sc.n_cells + 1);
+    J->counters = sc.counters + (size_t)j * 8;
+}
+
+static int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        dvfe_set_error("no CUDA device available (%s): libdvfe has no CPU fallback", cudaGetErrorString(e));
+        return DVFE_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        dvfe_set_error("device ordinal %d out of range (%d devices)", device, count);
+        return DVFE_ERR_NO_DEVICE;
+    }
+    DVFE_CUDA(cudaSetDevice(device));
+    return DVFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" const char* dvfe_version(void) { return "dvfe 0.1 (sm_100a)"; }
+extern "C" unsigned long long dvfe_kernel_launches(void) { return g_dvfe_launches; }
+extern "C" const char* dvfe_last_error(const dvfe_tracker* t) { (void)t; return g_err; }
+
+extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
+    if (!cfg || !out) { dvfe_set_error("dvfe_create: null argument"); return DVFE_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->width < 32 || cfg->height < 32 || cfg->n_streams < 1 || cfg->max_cnt < 1 || cfg->max_cnt > 2048 ||
+        cfg->min_dist < 1 || cfg->lk_max_level < 0 || cfg->lk_max_level >= DVFE_MAX_PYR_LEVELS) {
+        dvfe_set_error("dvfe_create: invalid config (w=%d h=%d streams=%d max_cnt=%d min_dist=%d lk_max_level=%d)",
+                       cfg->width, cfg->height, cfg->n_streams, cfg->max_cnt, cfg->min_dist, cfg->lk_max_level);
+        return DVFE_ERR_CONFIG;
+    }
+    DVFE_CHECK(check_device(cfg->device));
+    dvfe_tracker* t = new (std::nothrow) dvfe_tracker();
+    if (!t) return DVFE_ERR_CAPACITY;
+    t->cfg = *cfg;
+    t->B = cfg->n_streams; t->W = cfg->width; t->H = cfg->height; t->cap = cfg->max_cnt;
+    t->desc = make_pyr_desc(t->W, t->H, cfg->lk_max_level);
+    t->cam0 = make_cam(cfg->cam0);
+    t->cam1 = make_cam(cfg->cam1);
+    int rc = t->init();
+    if (rc != DVFE_OK) { dvfe_destroy(t); return rc; }
+    *out = t;
+    return DVFE_OK;
+}
+
+int dvfe_tracker::init() {
+    DVFE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t P = (size_t)W * H;
+    for (int s = 0; s < 3; s++) DVFE_CHECK(dmalloc(&pyr[s], (size_t)B * desc.bytes));
+    DVFE_CHECK(dmalloc(&d_in, 2 * B * P));
+    DVFE_CHECK(alloc_point_sets(&bg, B, cap));
+    DVFE_CHECK(dmalloc(&d_next_id, (size_t)B));
+    {
+        std::vector<uint32_t> ones(B, 1u);     // InstFeat::global_id_count{1}
+        DVFE_CUDA(cudaMemcpy(d_next_id, ones.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    DVFE_CHECK(dmalloc(&d_dt, (size_t)B));
+    DVFE_CUDA(cudaMallocHost((void**)&h_dt, B * sizeof(double)));
+    prev_time.assign(B, 0.0);
+    DVFE_CHECK(dmalloc(&d_obs, (size_t)B * 2 * cap));
+    DVFE_CHECK(dmalloc(&d_nobs, (size_t)B));
+    DVFE_CUDA(cudaMallocHost((void**)&h_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs)));
+    DVFE_CUDA(cudaMallocHost((void**)&h_nobs, B * sizeof(int)));
+    memset(h_nobs, 0, B * sizeof(int));
+    DVFE_CHECK(dmalloc(&d_region, (size_t)B * P));
+    DVFE_CHECK(dmalloc(&d_region_tmp, (size_t)B * P));
+    DVFE_CHECK(dmalloc(&d_inv_in, (size_t)B * P));
+    DVFE_CHECK(dmalloc(&d_exist, (size_t)B));
+    DVFE_CUDA(cudaMallocHost((void**)&h_exist, B * sizeof(int)));
+    DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
+
+    // LK groups: [parity][temporal raw | temporal semantic | stereo]
+    std::vector<LkGroup> g(B);
+    for (int par = 0; par < 2; par++) {
+        uint8_t* cur = pyr[par];
+        uint8_t* prev = pyr[1 - par];
+        for (int kind = 0; kind < 3; kind++) {
+            for (int s = 0; s < B; s++) {
+                LkGroup& G = g[s];
+                memset(&G, 0, sizeof(G));
+                G.desc = desc;
+                const size_t o = (size_t)s * cap;
+                if (kind < 2) {
+                    G.pyrA = prev + (size_t)s * desc.bytes;
+                    G.pyrB = cur + (size_t)s * desc.bytes;
+                    G.ptsA = bg.pts + o; G.ptsB = bg.lk_out + o; G.status = bg.status + o;
+                    if (kind == 1) { G.mask = d_region + (size_t)s * P; G.mask_pitch = W; }
+                } else {
+                    G.pyrA = cur + (size_t)s * desc.bytes;
+                    G.pyrB = pyr[2] + (size_t)s * desc.bytes;
+                    G.ptsA = bg.pts + o; G.ptsB = bg.rpts + o; G.status = bg.rstatus + o;
+                }
+                G.n = bg.n + s;
+            }
+            DVFE_CHECK(dmalloc(&d_groups[par][kind], (size_t)B));
+            DVFE_CUDA(cudaMemcpy(d_groups[par][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
+        }
+    }
+    // GFTT jobs: [parity][raw | semantic]
+    std::vector<GfttJob> jobs(B);
+    for (int par = 0; par < 2; par++)
+        for (int kind = 0; kind < 2; kind++) {
+            for (int s = 0; s < B; s++) {
+                GfttJob& J = jobs[s];
+                memset(&J, 0, sizeof(J));
+                const PyrLevel& L0 = desc.lv[0];
+                J.img = pyr[par] + (size_t)s * desc.bytes + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+                J.img_pitch = L0.pitch;
+                J.w = W; J.h = H;
+                if (kind == 1) { J.region_mask = d_region + (size_t)s * P; J.region_pitch = W; }
+                gftt_job_bind_scratch(&J, gsc, s);
+                const size_t o = (size_t)s * cap;
+                J.pts = bg.pts + o; J.ids = bg.ids + o; J.track_cnt = bg.track_cnt + o;
+                J.n = bg.n + s; J.next_id = d_next_id + s;
+                J.max_cnt = cfg.max_cnt;
+                J.min_needed = kind == 0 ? 1 : 10;    // TrackImage: n_max_cnt > 0; DetectNewFeature: n_max_cnt >= 10
+                J.disc_radius = cfg.min_dist;
+                J.min_dist = (float)cfg.min_dist;
+                J.quality = 0.01;
+            }
+            DVFE_CHECK(dmalloc(&d_jobs[par][kind], (size_t)B));
+            DVFE_CUDA(cudaMemcpy(d_jobs[par][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
+        }
+    DVFE_CUDA(cudaDeviceSynchronize());
+    return DVFE_OK;
+}
+
+extern "C" void dvfe_destroy(dvfe_tracker* t) {
+    if (!t) return;
+    cudaSetDevice(t->cfg.device);
+    if (t->st) cudaStreamSynchronize(t->st);
+    for (int s = 0; s < 3; s++) cudaFree(t->pyr[s]);
+    cudaFree(t->d_in);
+    free_point_sets(&t->bg);
+    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFreeHost(t->h_dt);
+    cudaFree(t->d_obs); cudaFree(t->d_nobs); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_nobs);
+    cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_inv_in); cudaFree(t->d_exist);
+    cudaFreeHost(t->h_exist);
+    free_gftt_scratch(&t->gsc);
+    for (int p = 0; p < 2; p++) {
+        for (int k = 0; k < 3; k++) cudaFree(t->d_groups[p][k]);
+        for (int k = 0; k < 2; k++) cudaFree(t->d_jobs[p][k]);
+    }
+    t->free_instances();
+    if (t->st) cudaStreamDestroy(t->st);
+    delete t;
+}
+
+// The frame step with the images already on the device (dense or pitched, strided per stream).
+int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
+                              const double* time0, bool semantic) {
+    DVFE_CUDA(cudaSetDevice(cfg.device));
+    const bool stereo_now = cfg.stereo && d_right != nullptr;
+    const int par = cur;
+    for (int s = 0; s < B; s++) h_dt[s] = time0[s] - prev_time[s];       // cur_time - prev_time
+    DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt, B * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    PyrImgSet set;
+    set.src[0] = d_left; set.src[1] = d_right;
+    set.dst[0] = pyr[par]; set.dst[1] = pyr[2];
+    set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
+    DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st));
+
+    if (frames > 0) {
+        // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points) + ReduceVector + track_cnt++
+        DVFE_CHECK(launch_lk(d_groups[par][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+        DVFE_CHECK(launch_compact(bg, B, cap, st));
+    }
+    // discs + goodFeaturesToTrack + ids
+    DVFE_CHECK(launch_gftt(d_jobs[par][semantic ? 1 : 0], nullptr, B, W, H, cap, st));
+    // UndistortedPts(cam0) + PtsVelocity
+    DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
+    if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
+        DVFE_CHECK(launch_lk(d_groups[par][2], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+    DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs, d_nobs, st));
+    DVFE_CUDA(cudaMemcpyAsync(h_nobs, d_nobs, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DVFE_CUDA(cudaMemcpyAsync(h_obs, d_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, st));
+    DVFE_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < B; s++) prev_time[s] = time0[s];
+    cur = 1 - cur;
+    frames++;
+    return DVFE_OK;
+}
+
+int dvfe_tracker::upload(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
+    const size_t P = (size_t)W * H;
+    for (int s = 0; s < B; s++) {
+        DVFE_CUDA(cudaMemcpy2DAsync(d_in + s * P, W, left + s * stream_stride, pitch, W, (size_t)H,
+                                    cudaMemcpyHostToDevice, st));
+        if (right)
+            DVFE_CUDA(cudaMemcpy2DAsync(d_in + (B + s) * P, W, right + s * stream_stride, pitch, W, (size_t)H,
+                                        cudaMemcpyHostToDevice, st));
+    }
+    return DVFE_OK;
+}
+
+static int check_step_args(dvfe_tracker* t, const uint8_t* left, int pitch, const double* time0) {
+    if (!t || !left || !time0 || pitch < t->W) {
+        dvfe_set_error("track: input wrong, received at least one empty parameter");   // feature_utils.cpp:39-41
+        return DVFE_ERR_INVALID;
+    }
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
+                                int pitch, const double* time0) {
+    DVFE_CHECK(check_step_args(t, left, pitch, time0));
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t P = (size_t)t->W * t->H;
+    // one contiguous copy when the host layout is dense
+    if (pitch == t->W && stream_stride == P) {
+        DVFE_CUDA(cudaMemcpyAsync(t->d_in, left, t->B * P, cudaMemcpyHostToDevice, t->st));
+        if (right) DVFE_CUDA(cudaMemcpyAsync(t->d_in + t->B * P, right, t->B * P, cudaMemcpyHostToDevice, t->st));
+    } else {
+        DVFE_CHECK(t->upload(left, right, stream_stride, pitch));
+    }
+    return t->step_device(t->d_in, right ? t->d_in + t->B * P : nullptr, P, t->W, time0, false);
+}
+
+extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
+                                       size_t stream_stride, int pitch, const double* time0) {
+    DVFE_CHECK(check_step_args(t, d_left, pitch, time0));
+    return t->step_device(d_left, d_right, stream_stride, pitch, time0, false);
+}
+
+extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right,
+                                         const uint8_t* inv_merge_mask, size_t stream_stride, int pitch,
+                                         const int* exist_inst, const double* time0) {
+    DVFE_CHECK(check_step_args(t, left, pitch, time0));
+    if (!exist_inst) { dvfe_set_error("track_semantic_image: exist_inst is null"); return DVFE_ERR_INVALID; }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    const size_t P = (size_t)t->W * t->H;
+    DVFE_CHECK(t->upload(left, right, stream_stride, pitch));
+    bool any = false;
+    for (int s = 0; s < t->B; s++) {
+        t->h_exist[s] = exist_inst[s] ? 1 : 0;
+        any |= exist_inst[s] != 0;
+        if (exist_inst[s]) {
+            if (!inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
+            DVFE_CUDA(cudaMemcpy2DAsync(t->d_inv_in + s * P, t->W, inv_merge_mask + s * stream_stride, pitch, t->W,
+                                        (size_t)t->H, cudaMemcpyHostToDevice, t->st));
+        }
+    }
+    (void)any;
+    DVFE_CUDA(cudaMemcpyAsync(t->d_exist, t->h_exist, t->B * sizeof(int), cudaMemcpyHostToDevice, t->st));
+    // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772)
+    const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
+    DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
+                                 t->d_exist, t->st));
+    return t->step_device(t->d_in, right ? t->d_in + t->B * P : nullptr, P, t->W, time0, true);
+}
+
+extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out) {
+    if (!t || stream < 0 || stream >= t->B || !n_out) { dvfe_set_error("get_features: bad argument"); return DVFE_ERR_INVALID; }
+    const int n = t->h_nobs[stream];
+    *n_out = n;
+    if (n > cap) { dvfe_set_error("get_features: %d records, capacity %d", n, cap); return DVFE_ERR_CAPACITY; }
+    if (n > 0 && out) memcpy(out, t->h_obs + (size_t)stream * 2 * t->cap, (size_t)n * sizeof(dvfe_obs));
+    return DVFE_OK;
+}
+
+// ---- state get/set (teacher-forced parity tests, checkpointing) ---------------------------------------
+extern "C" int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* stt, int cap) {
+    if (!t || !stt || stream < 0 || stream >= t->B) { dvfe_set_error("get_state: bad argument"); return DVFE_ERR_INVALID; }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CUDA(cudaStreamSynchronize(t->st));
+    int n = 0;
+    DVFE_CUDA(cudaMemcpy(&n, t->bg.n + stream, sizeof(int), cudaMemcpyDeviceToHost));
+    DVFE_CUDA(cudaMemcpy(&stt->next_id, t->d_next_id + stream, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    stt->n = n;
+    stt->prev_time = t->prev_time[stream];
+    if (n > cap) { dvfe_set_error("get_state: %d points, capacity %d", n, cap); return DVFE_ERR_CAPACITY; }
+    const size_t o = (size_t)stream * t->cap;
+    if (n > 0) {
+        if (stt->ids) DVFE_CUDA(cudaMemcpy(stt->ids, t->bg.ids + o, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (stt->track_cnt) DVFE_CUDA(cudaMemcpy(stt->track_cnt, t->bg.track_cnt + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (stt->last_points) DVFE_CUDA(cudaMemcpy(stt->last_points, t->bg.pts + o, n * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (stt->prev_un) DVFE_CUDA(cudaMemcpy(stt->prev_un, t->bg.un + o, n * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (stt->right_prev_un) DVFE_CUDA(cudaMemcpy(stt->right_prev_un, t->bg.rprev_un + o, n * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (stt->right_prev_valid) DVFE_CUDA(cudaMemcpy(stt->right_prev_valid, t->bg.rprev_valid + o, n, cudaMemcpyDeviceToHost));
+    }
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt) {
+    if (!t || !stt || stream < 0 || stream >= t->B || stt->n < 0 || stt->n > t->cap) {
+        dvfe_set_error("set_state: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CUDA(cudaStreamSynchronize(t->st));
+    const int n = stt->n;
+    const size_t o = (size_t)stream * t->cap;
+    DVFE_CUDA(cudaMemcpy(t->bg.n + stream, &n, sizeof(int), cudaMemcpyHostToDevice));
+    DVFE_CUDA(cudaMemcpy(t->d_next_id + stream, &stt->next_id, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    t->prev_time[stream] = stt->prev_time;
+    if (n > 0) {
+        DVFE_CUDA(cudaMemcpy(t->bg.ids + o, stt->ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        DVFE_CUDA(cudaMemcpy(t->bg.track_cnt + o, stt->track_cnt, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        DVFE_CUDA(cudaMemcpy(t->bg.pts + o, stt->last_points, n * sizeof(float2), cudaMemcpyHostToDevice));
+        DVFE_CUDA(cudaMemcpy(t->bg.un + o, stt->prev_un, n * sizeof(float2), cudaMemcpyHostToDevice));
+        DVFE_CUDA(cudaMemcpy(t->bg.rprev_un + o, stt->right_prev_un, n * sizeof(float2), cudaMemcpyHostToDevice));
+        DVFE_CUDA(cudaMemcpy(t->bg.rprev_valid + o, stt->right_prev_valid, n, cudaMemcpyHostToDevice));
+    }
+    return DVFE_OK;
+}

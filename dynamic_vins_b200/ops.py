@@ -1,0 +1,94 @@
+"""Seam-level operators (include/dvfe.h `dvfe_op_*`) on numpy arrays.  Each call goes through the C ABI into
+the CUDA kernels; nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def build_pyramid(img, max_level: int = 3):
+    """cv::buildOpticalFlowPyramid(img, Size(21,21), max_level) -> list of level images."""
+    img = _u8(img)
+    h, w = img.shape
+    outs, lw, lh = [], w, h
+    for _ in range(max_level + 1):
+        outs.append(np.zeros((lh, lw), np.uint8))
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+    arr = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+    ws = np.zeros(8, np.int32)
+    hs = np.zeros(8, np.int32)
+    n = C.c_int(0)
+    L.check(L.lib().dvfe_op_build_pyramid(L.ptr(img), w, h, img.strides[0], max_level, arr, L.ptr(ws), L.ptr(hs),
+                                          C.byref(n)))
+    return [outs[i][:hs[i], :ws[i]] for i in range(n.value)]
+
+
+def feature_track_by_lk(img1, img2, pts1, flow_back: bool = True, max_level: int = 3, mask=None,
+                        return_rev: bool = False):
+    """FeatureTrackByLK (dynamic_vins/src/front_end/feature_utils.cpp:35-69) -> (pts2, status[, rev])."""
+    img1, img2 = _u8(img1), _u8(img2)
+    h, w = img1.shape
+    p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    n = len(p1)
+    p2 = np.zeros((n, 2), np.float32)
+    rev = np.zeros((n, 2), np.float32)
+    st = np.zeros(n, np.uint8)
+    m = _u8(mask) if mask is not None else None
+    L.check(L.lib().dvfe_op_lk(L.ptr(img1), L.ptr(img2), w, h, w, L.ptr(p1), n, int(flow_back), max_level,
+                               L.ptr(m), w, L.ptr(p2), L.ptr(st), L.ptr(rev)))
+    return (p2, st, rev) if return_rev else (p2, st)
+
+
+def min_eigen_val(img):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.zeros((h, w), np.float32)
+    L.check(L.lib().dvfe_op_min_eigen_val(L.ptr(img), w, h, w, L.ptr(out)))
+    return out
+
+
+def good_features(img, max_corners: int, quality: float, min_dist: float, mask=None, eig=None,
+                  return_n_candidates: bool = False):
+    """cv::goodFeaturesToTrack(img, K, quality, min_dist, mask); `eig` overrides the response map."""
+    img = _u8(img) if img is not None else None
+    h, w = (img.shape if img is not None else eig.shape)
+    e = np.ascontiguousarray(eig, np.float32) if eig is not None else None
+    m = _u8(mask) if mask is not None else None
+    out = np.zeros((max_corners, 2), np.float32)
+    n, nc = C.c_int(0), C.c_int(0)
+    L.check(L.lib().dvfe_op_good_features(L.ptr(img), w, h, w, L.ptr(e), L.ptr(m), w, int(max_corners),
+                                          float(quality), float(min_dist), L.ptr(out), C.byref(n), C.byref(nc)))
+    res = out[:n.value].copy()
+    return (res, nc.value) if return_n_candidates else res
+
+
+def disc_mask(mask, pts, radius: int):
+    m = _u8(mask).copy()
+    h, w = m.shape
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    L.check(L.lib().dvfe_op_disc_mask(L.ptr(m), w, h, w, L.ptr(p), len(p), int(radius)))
+    return m
+
+
+def erode_rect(mask, k: int):
+    m = _u8(mask)
+    h, w = m.shape
+    out = np.zeros_like(m)
+    L.check(L.lib().dvfe_op_erode_rect(L.ptr(m), w, h, w, int(k), L.ptr(out)))
+    return out
+
+
+def lift_projective(cam: dict, pts, off=(0.0, 0.0)):
+    c = L.Camera(**{k: float(cam[k]) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")})
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(p)
+    L.check(L.lib().dvfe_op_lift_projective(C.byref(c), L.ptr(p), len(p), float(off[0]), float(off[1]), L.ptr(out)))
+    return out

@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's front-end classes over the C ABI.
+
+`FeatureTracker` keeps the reference's method names and output shape
+(dynamic_vins/src/front_end/background_tracker.h:44-49):
+    TrackImage(img)          -> FeatureBackground.points  {id: [(cam, [x,y,1,u,v,vx,vy]), ...]}
+    TrackSemanticImage(img)  -> same, with the instance region mask
+`BatchTracker` is the B-stream form the benchmark drives (one tracker object, B camera streams, one
+set of kernel launches per step).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def make_config(width: int, height: int, max_cnt: int, min_dist: int, cam0: dict, cam1: Optional[dict] = None,
+                stereo: bool = True, n_streams: int = 1, max_dynamic_cnt: int = 50, min_dynamic_dist: int = 5,
+                flow_back: int = 1, use_mask_morphology: int = 0, mask_morphology_size: int = 5,
+                lk_max_level: int = 3, max_instances: int = 0, device: int = 0, **_ignored) -> L.Config:
+    c = L.Config()
+    c.width, c.height, c.n_streams, c.stereo = width, height, n_streams, int(bool(stereo))
+    c.max_cnt, c.min_dist = max_cnt, min_dist
+    c.max_dynamic_cnt, c.min_dynamic_dist = max_dynamic_cnt, min_dynamic_dist
+    c.flow_back = flow_back
+    c.use_mask_morphology, c.mask_morphology_size = use_mask_morphology, mask_morphology_size
+    c.lk_max_level, c.max_instances, c.device = lk_max_level, max_instances, device
+    cam1 = cam1 if cam1 is not None else cam0
+    for dst, src in ((c.cam0, cam0), (c.cam1, cam1)):
+        for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2"):
+            setattr(dst, k, float(src[k]))
+    return c
+
+
+def config_from_yaml(path: str) -> L.Config:
+    c = L.Config()
+    L.check(L.lib().dvfe_config_from_yaml(path.encode(), C.byref(c)))
+    return c
+
+
+def obs_to_map(rec: np.ndarray) -> Dict[int, List[Tuple[int, np.ndarray]]]:
+    """dvfe_obs records -> the reference's std::map<id, vector<pair<cam, Vec7d>>>."""
+    out: Dict[int, List[Tuple[int, np.ndarray]]] = {}
+    for r in rec:
+        out.setdefault(int(r["id"]), []).append((int(r["cam"]), r["v"].copy()))
+    return out
+
+
+class BatchTracker:
+    """B independent camera streams of one geometry on one GPU (dvfe_tracker)."""
+
+    def __init__(self, cfg: L.Config):
+        self.cfg = cfg
+        self.B, self.W, self.H = cfg.n_streams, cfg.width, cfg.height
+        self._h = C.c_void_p()
+        L.check(L.lib().dvfe_create(C.byref(cfg), C.byref(self._h)))
+        self._obs = np.zeros(2 * cfg.max_cnt, dtype=L.OBS_DTYPE)
+        self._iobs = np.zeros(max(1, cfg.max_instances) * max(1, cfg.max_dynamic_cnt), dtype=L.INST_OBS_DTYPE)
+
+    def close(self):
+        if self._h:
+            L.lib().dvfe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- frame steps ---------------------------------------------------------------------------
+    def _times(self, time0) -> np.ndarray:
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(time0, np.float64), (self.B,)))
+        return t
+
+    @staticmethod
+    def _batch(a: Optional[np.ndarray], B: int, H: int, W: int) -> Optional[np.ndarray]:
+        if a is None:
+            return None
+        a = np.asarray(a)
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape == (B, H, W) and a.dtype == np.uint8, (a.shape, a.dtype)
+        return a if a.flags["C_CONTIGUOUS"] else np.ascontiguousarray(a)
+
+    def track_image(self, left: np.ndarray, right: Optional[np.ndarray], time0) -> None:
+        """left/right: (B,H,W) or (H,W) uint8 host arrays."""
+        l = self._batch(left, self.B, self.H, self.W)
+        r = self._batch(right, self.B, self.H, self.W)
+        t = self._times(time0)
+        L.check(L.lib().dvfe_track_image(self._h, L.ptr(l), L.ptr(r), self.H * self.W, self.W, L.ptr(t)))
+
+    def track_image_device(self, d_left: int, d_right: int, stream_stride: int, pitch: int, time0) -> None:
+        """d_left/d_right: device pointers (ints), e.g. torch tensor .data_ptr()."""
+        t = self._times(time0)
+        L.check(L.lib().dvfe_track_image_device(self._h, C.c_void_p(d_left), C.c_void_p(d_right) if d_right else None,
+                                                stream_stride, pitch, L.ptr(t)))
+
+    def track_semantic_image(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
+        l = self._batch(left, self.B, self.H, self.W)
+        r = self._batch(right, self.B, self.H, self.W)
+        m = self._batch(inv_merge_mask, self.B, self.H, self.W)
+        e = np.ascontiguousarray(np.broadcast_to(np.asarray(exist_inst, np.int32), (self.B,)))
+        t = self._times(time0)
+        L.check(L.lib().dvfe_track_semantic_image(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W, self.W,
+                                                  L.ptr(e), L.ptr(t)))
+
+    def insts_track(self, stream: int, boxes: Sequence[dict], time0: float) -> None:
+        """boxes: [{track_id, rect=(x,y,w,h), mask (h,w) uint8}] (SemanticImage::boxes2d)."""
+        arr = (L.InstIn * max(1, len(boxes)))()
+        keep = []
+        for i, b in enumerate(boxes):
+            m = np.ascontiguousarray(b["mask"], np.uint8)
+            keep.append(m)
+            x, y, w, h = b["rect"]
+            arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
+            arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
+        L.check(L.lib().dvfe_insts_track(self._h, stream, arr, len(boxes), float(time0)))
+
+    # ---- outputs -------------------------------------------------------------------------------
+    def features(self, stream: int = 0) -> np.ndarray:
+        """dvfe_obs records (structured array: id, cam, v[7]) sorted by (id, cam)."""
+        n = C.c_int(0)
+        L.check(L.lib().dvfe_get_features(self._h, stream, L.ptr(self._obs), len(self._obs), C.byref(n)))
+        return self._obs[:n.value].copy()
+
+    def insts_output(self, stream: int = 0) -> np.ndarray:
+        n = C.c_int(0)
+        L.check(L.lib().dvfe_insts_output(self._h, stream, L.ptr(self._iobs), len(self._iobs), C.byref(n)))
+        return self._iobs[:n.value].copy()
+
+    # ---- state ---------------------------------------------------------------------------------
+    def get_state(self, stream: int = 0) -> dict:
+        cap = self.cfg.max_cnt
+        a = dict(ids=np.zeros(cap, np.uint32), track_cnt=np.zeros(cap, np.int32),
+                 last_points=np.zeros((cap, 2), np.float32), prev_un=np.zeros((cap, 2), np.float32),
+                 right_prev_un=np.zeros((cap, 2), np.float32), right_prev_valid=np.zeros(cap, np.uint8))
+        st = L.State()
+        for k, v in a.items():
+            setattr(st, k, v.ctypes.data)
+        L.check(L.lib().dvfe_get_state(self._h, stream, C.byref(st), cap))
+        out = {k: v[:st.n].copy() for k, v in a.items()}
+        out.update(n=st.n, next_id=st.next_id, prev_time=st.prev_time)
+        return out
+
+    def set_state(self, stream: int, state: dict) -> None:
+        n = int(state["n"])
+        a = dict(ids=np.ascontiguousarray(state["ids"], np.uint32),
+                 track_cnt=np.ascontiguousarray(state["track_cnt"], np.int32),
+                 last_points=np.ascontiguousarray(state["last_points"], np.float32),
+                 prev_un=np.ascontiguousarray(state["prev_un"], np.float32),
+                 right_prev_un=np.ascontiguousarray(state["right_prev_un"], np.float32),
+                 right_prev_valid=np.ascontiguousarray(state["right_prev_valid"], np.uint8))
+        st = L.State()
+        st.n, st.next_id, st.prev_time = n, int(state["next_id"]), float(state["prev_time"])
+        for k, v in a.items():
+            assert len(v) >= n
+            setattr(st, k, v.ctypes.data)
+        L.check(L.lib().dvfe_set_state(self._h, stream, C.byref(st)))
+
+
+class FeatureTracker:
+    """Single-stream tracker with the reference's method names (front_end/background_tracker.h:44-49).
+    `img` is any object with the SemanticImage fields the path reads: gray0, gray1 (or None), time0 and, for
+    TrackSemanticImage, inv_merge_mask + exist_inst (basic/semantic_image.h:30-65)."""
+
+    def __init__(self, config):
+        cfg = config_from_yaml(config) if isinstance(config, str) else config
+        if cfg.n_streams != 1:
+            raise ValueError("FeatureTracker is the single-stream API; use BatchTracker for B > 1")
+        self.batch = BatchTracker(cfg)
+
+    def TrackImage(self, img) -> Dict[int, List[Tuple[int, np.ndarray]]]:
+        self.batch.track_image(img.gray0, img.gray1, img.time0)
+        return obs_to_map(self.batch.features(0))
+
+    def TrackSemanticImage(self, img) -> Dict[int, List[Tuple[int, np.ndarray]]]:
+        self.batch.track_semantic_image(img.gray0, img.gray1, img.inv_merge_mask, int(bool(img.exist_inst)), img.time0)
+        return obs_to_map(self.batch.features(0))
+
+
+def serialize_point_features(points: Dict[int, List[Tuple[int, np.ndarray]]]) -> str:
+    """SerializePointFeature text format (dynamic_vins/src/utils/io/feature_serialization.cpp:26-38)."""
+    lines = []
+    for fid in sorted(points):
+        obs = points[fid]
+        vals = " ".join(repr(float(x)) for x in obs[0][1])
+        if len(obs) == 1:
+            lines.append(f"0 {fid} {vals}")
+        else:
+            lines.append(f"1 {fid} {vals} " + " ".join(repr(float(x)) for x in obs[1][1]))
+    return "\n".join(lines) + ("\n" if lines else "")

@@ -1,0 +1,197 @@
+/* dvfe.h — C ABI of the B200-native Dynamic-VINS feature-tracking front-end.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json `north_star`.
+ * The reference has no FFI layer: the seam is a C++ class API inside one binary
+ * (SURVEY.md §8b).  Every entry point below names the reference interface it
+ * replaces (paths under /root/reference/dynamic_vins/src/).  Plain pointers and
+ * sizes only; no C++/torch types cross this boundary; nothing throws — the
+ * reference's exception cases come back as negative codes.
+ *
+ * One `dvfe_tracker` owns B independent camera streams of identical geometry on
+ * one GPU ("stream-sharded replicas").  B = 1 is the reference's
+ * single `FeatureTracker` + `InstsFeatManager` pair.  All device state (pyramids,
+ * point sets, ids, velocities) stays resident in HBM between calls.
+ */
+#ifndef DVFE_H_
+#define DVFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVFE_OK 0
+#define DVFE_ERR_INVALID (-1)   /* bad argument / empty input: std::runtime_error, front_end/feature_utils.cpp:39-41 */
+#define DVFE_ERR_CUDA (-2)      /* CUDA runtime failure (see dvfe_last_error) */
+#define DVFE_ERR_CONFIG (-3)    /* bad settings path or key: front_end/front_end_parameters.cpp:20-22 */
+#define DVFE_ERR_CAPACITY (-4)  /* a caller-provided buffer or a configured capacity is too small */
+#define DVFE_ERR_NO_DEVICE (-5) /* no sm_100 device: the library has no CPU fallback */
+
+#define DVFE_MAX_PYR_LEVELS 5
+
+/* camodocal PinholeCamera parameters (model_type: PINHOLE — the only model any shipped config uses;
+ * /root/reference/camera_models/src/camera_models/PinholeCamera.cc:187-205) */
+typedef struct dvfe_camera {
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2;
+} dvfe_camera;
+
+/* fe_para / cfg keys the path reads (front_end/front_end_parameters.cpp:24-37, utils/parameters.cpp) */
+typedef struct dvfe_config {
+    int width, height;          /* image_width, image_height */
+    int n_streams;              /* B independent streams held by this tracker (reference: 1) */
+    int stereo;                 /* cfg::is_stereo (num_of_cam == 2) */
+    int max_cnt;                /* max_cnt */
+    int min_dist;               /* min_dist */
+    int max_dynamic_cnt;        /* max_dynamic_cnt */
+    int min_dynamic_dist;       /* min_dynamic_dist */
+    int flow_back;              /* flow_back (fe_para::is_flow_back) */
+    int use_mask_morphology;    /* use_mask_morphology */
+    int mask_morphology_size;   /* mask_morphology_size */
+    int lk_max_level;           /* 3: cv::calcOpticalFlowPyrLK(..., Size(21,21), 3), front_end/feature_utils.cpp:43 */
+    int max_instances;          /* per-stream instance slots for dynamic mode (0 = raw mode only) */
+    int device;                 /* CUDA device ordinal */
+    dvfe_camera cam0, cam1;     /* cam_t.cam0 / cam_t.cam1, utils/camera_model.h:52-54 */
+} dvfe_config;
+
+/* One observation of FeatureBackground::points — map<id, vector<pair<cam, Vec7d>>>
+ * (basic/frontend_feature.h:34-47; packed by FeatureTracker::SetOutputFeats,
+ * front_end/background_tracker.cpp:340-392).  v = [x, y, 1, u, v, vx, vy]. Records come
+ * sorted by (id, cam), i.e. in the iteration order of the reference's std::map. */
+typedef struct dvfe_obs {
+    uint32_t id;
+    int32_t cam;
+    double v[7];
+} dvfe_obs;
+
+/* One feature of FeatureInstance::features (basic/frontend_feature.h:49-58, basic/point_feature.h:22-100;
+ * packed by InstsFeatManager::Output, front_end/dynamic_tracker.cpp:521-577). */
+typedef struct dvfe_inst_obs {
+    uint32_t inst_id;           /* instance (track) id */
+    uint32_t id;                /* feature id */
+    int32_t is_stereo;
+    int32_t reserved;
+    double point[3];            /* (un.x, un.y, 1) */
+    double vel[2];
+    double point_right[3];
+    double vel_right[2];
+    double uv[2];               /* ROI-local pixel position (curr_points) */
+    double disp;                /* 0: no disparity map on this path (reference quirk Q8) */
+} dvfe_inst_obs;
+
+/* One detected instance of a frame: Box2D + InstRoi (basic/box2d.h:24-56), as produced by
+ * SemanticImage::SetMaskAndRoi (basic/semantic_image.cpp:20-63) and consumed by
+ * InstsFeatManager::AddViodeInstances (front_end/dynamic_tracker.cpp:585-605). */
+typedef struct dvfe_inst_in {
+    uint32_t track_id;
+    int32_t x, y, w, h;         /* Box2D::rect (integer valued) */
+    const uint8_t* mask;        /* HOST pointer, h rows x w cols, 255 = object (InstRoi::mask_cv) */
+    int32_t mask_pitch;
+} dvfe_inst_in;
+
+typedef struct dvfe_tracker dvfe_tracker;
+
+/* ---- lifetime --------------------------------------------------------------------- */
+
+/* FeatureTracker::FeatureTracker(config_path) + InstsFeatManager::InstsFeatManager(config_path)
+ * (front_end/background_tracker.cpp:30-43, front_end/dynamic_tracker.cpp:33) with the yaml already parsed. */
+int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out);
+void dvfe_destroy(dvfe_tracker* t);
+
+/* fe_para::SetParameters(config_path) + the cfg keys of utils/parameters.cpp + the two camodocal yaml files
+ * named by cam0_calib / cam1_calib (front_end/front_end_parameters.cpp:17-40).  Fills *cfg; n_streams = 1. */
+int dvfe_config_from_yaml(const char* config_path, dvfe_config* cfg);
+
+const char* dvfe_last_error(const dvfe_tracker* t);   /* t may be NULL: last error of dvfe_create / ops */
+const char* dvfe_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py `gpu_launches`). */
+unsigned long long dvfe_kernel_launches(void);
+
+/* ---- the frame step ----------------------------------------------------------------- */
+
+/* FeatureTracker::TrackImage(SemanticImage&) for all B streams (front_end/background_tracker.cpp:52-158).
+ * left/right: HOST pointers (pinned or pageable) to stream 0's gray0/gray1 (CV_8UC1, `pitch` bytes per row);
+ * stream s is at + s*stream_stride.  right may be NULL (mono frame).  time0[s] = SemanticImage::time0.
+ * The call uploads the images, runs the whole step on the device and returns when the outputs are on
+ * the host (read them with dvfe_get_features). */
+int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch,
+                     const double* time0);
+
+/* Same step with the images already resident in device memory (no H2D inside). */
+int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride,
+                            int pitch, const double* time0);
+
+/* FeatureTracker::TrackSemanticImage(SemanticImage&) (front_end/background_tracker.cpp:757-837).
+ * inv_merge_mask: HOST, same layout as left (0 = object, 255 = background), may be NULL when no stream has
+ * instances; exist_inst[s] = SemanticImage::exist_inst. */
+int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right,
+                              const uint8_t* inv_merge_mask, size_t stream_stride, int pitch,
+                              const int* exist_inst, const double* time0);
+
+/* InstsFeatManager::InstsTrack(SemanticImage) preceded by the caller's per-frame instance reset and
+ * AddViodeInstances (system/main.cpp:198-210, front_end/dynamic_tracker.cpp:348-493,585-605), for ONE stream.
+ * Uses the gray0/gray1 uploaded by the last dvfe_track_semantic_image call of that stream. */
+int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* insts, int n_insts, double time0);
+
+/* FeatureBackground of stream s of the last step: n_out records, sorted by (id, cam). */
+int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out);
+/* InstsFeatManager::Output() (front_end/dynamic_tracker.cpp:521-577), sorted by (inst_id, id). */
+int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out);
+
+/* ---- tracker state (InstFeat bg members, front_end/instance_feature.h:103-137) --------------- */
+typedef struct dvfe_state {
+    int n;                      /* bg.ids.size() */
+    uint32_t next_id;           /* InstFeat::global_id_count */
+    double prev_time;
+    uint32_t* ids;              /* [cap] bg.ids */
+    int32_t* track_cnt;         /* [cap] bg.track_cnt */
+    float* last_points;         /* [cap*2] bg.last_points (= curr_points of the last frame) */
+    float* prev_un;             /* [cap*2] bg.prev_id_pts values, in ids order */
+    float* right_prev_un;       /* [cap*2] bg.right_prev_id_pts values (valid where right_prev_valid) */
+    uint8_t* right_prev_valid;  /* [cap] */
+} dvfe_state;
+int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* st, int cap);
+int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* st);
+
+/* ---- seam-level operators (unit parity; each replaces one OpenCV/camodocal call of the path) ---- */
+
+/* cv::buildOpticalFlowPyramid(img, pyr, Size(21,21), max_level) as used inside calcOpticalFlowPyrLK.
+ * Writes level l (l = 0..*n_levels-1) unpadded into out_levels[l] (size ((w+1)/2.., (h+1)/2..)). */
+int dvfe_op_build_pyramid(const uint8_t* img, int w, int h, int pitch, int max_level, uint8_t* const* out_levels,
+                          int* level_w, int* level_h, int* n_levels);
+
+/* FeatureTrackByLK(img1,img2,pts1,pts2,flow_back) (front_end/feature_utils.cpp:35-69):
+ * forward LK (max_level) + backward LK (max level 1, initial flow) + 0.5 px check + InBorder.
+ * mask (nullable, same size as the images): status also cleared where mask[cvRound(pt2)] == 0
+ * (InstFeat::TrackLeft, front_end/instance_feature.cpp:166-171).  pts are (x,y) float pairs.
+ * rev_out (nullable): backward-tracked points. */
+int dvfe_op_lk(const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch, const float* pts1, int n,
+               int flow_back, int max_level, const uint8_t* mask, int mask_pitch, float* pts2_out,
+               uint8_t* status_out, float* rev_out);
+
+/* cv::cornerMinEigenVal(img, eig, 3, 3) — the response map of goodFeaturesToTrack. */
+int dvfe_op_min_eigen_val(const uint8_t* img, int w, int h, int pitch, float* eig_out);
+
+/* cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_dist, mask)
+ * (front_end/background_tracker.cpp:85, front_end/instance_feature.cpp:381, front_end/dynamic_tracker.cpp:435).
+ * eig (nullable): use this response map instead of computing it (NMS parity "given equal response maps"). */
+int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
+                          int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
+                          int* n_out, int* n_candidates_out);
+
+/* for each pt: cv::circle(mask, pt, radius, 0, -1) (front_end/background_tracker.cpp:79-80). In place. */
+int dvfe_op_disc_mask(uint8_t* mask, int w, int h, int pitch, const float* pts, int n, int radius);
+
+/* ErodeMask(in,out,k): cv::erode with a k x k MORPH_RECT element (front_end/feature_utils.h:142-146). */
+int dvfe_op_erode_rect(const uint8_t* src, int w, int h, int pitch, int k, uint8_t* dst);
+
+/* InstFeat::UndistortedPts / UndistortedPointsWithAddOffset: PinholeCamera::liftProjective then (x/z, y/z)
+ * narrowed to float (front_end/instance_feature.cpp:94-103,123-133). */
+int dvfe_op_lift_projective(const dvfe_camera* cam, const float* pts, int n, float off_x, float off_y, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVFE_H_ */
