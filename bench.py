@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — front-end frames/s of the feature-tracking hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libdvfe.so)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Workload (`config.workload`): BASELINE.json configs[4] — 64 independent synthetic 1280x720 stereo camera
+streams per GPU, raw mode (TrackImage: temporal LK with forward-backward check, Shi-Tomasi top-up to 400
+points with min-distance 25, left->right LK, undistortion, velocity).  A "step" advances every stream of the
+rank by one frame.  Streams are independent, so N GPUs run N x 64 streams with no collective ("scaling": weak).
+
+  value  frames/s with the frames already resident in HBM (dvfe_track_image_device), outputs read back;
+  e2e    frames/s through the host-buffer C-ABI call (dvfe_track_image): pinned host images are copied to the
+         device and the FeatureFrame records are copied back inside the timed region.
+Timing: CUDA events on the stream the kernels run on, barrier + synchronize on both sides, max over ranks.
+Each step reads a different 118 MB set of frames plus its pyramids (working set >> the 126 MB L2), so no
+explicit L2 flush is needed ("l2": "inputs_larger_than_L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "front-end frames/s (stereo KLT+corners)"
+UNIT = "frames/s"
+WORKLOAD = "c5_zed_streams"
+
+
+# ----------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dvfe", choices=["dvfe", "reference"])
+    ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU")
+    ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gpu_frames(stream, T: int, device):
+    """The `T` unique stereo frames of one synthetic stream, rendered on the GPU with the same formulas as
+    dynamic_vins_b200.synth.SynthStream._view (float64).  Returns uint8 tensor [T][2][H][W]."""
+    import torch
+    H, W = stream.h, stream.w
+    canvas = torch.from_numpy(stream.canvas).to(device)
+    ch, cw = canvas.shape
+    yy, xx = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float64),
+                            torch.arange(W, device=device, dtype=torch.float64), indexing="ij")
+    out = torch.empty((T, 2, H, W), dtype=torch.uint8, device=device)
+    cx, cy = W / 2.0, H / 2.0
+    for k in range(T):
+        th = stream.omega * k
+        sc = 1.0 + stream.dscale * k
+        c, s = np.cos(th) * sc, np.sin(th) * sc
+        dx, dy = xx - cx, yy - cy
+        xs0 = c * dx - s * dy + cx + stream.margin + 32 + stream.vx * k
+        ys0 = s * dx + c * dy + cy + stream.margin + stream.vy * k
+        for cam in range(2):
+            xs = xs0 + (stream.d_top + (stream.d_bot - stream.d_top) * (yy / max(H - 1, 1))) if cam == 1 else xs0
+            xs = xs.clamp(0.0, cw - 1.001)
+            ys = ys0.clamp(0.0, ch - 1.001)
+            x0 = xs.floor().long(); y0 = ys.floor().long()
+            ax = xs - x0; ay = ys - y0
+            v = ((1 - ax) * (1 - ay) * canvas[y0, x0] + ax * (1 - ay) * canvas[y0, x0 + 1]
+                 + (1 - ax) * ay * canvas[y0 + 1, x0] + ax * ay * canvas[y0 + 1, x0 + 1])
+            out[k, cam] = v.round().clamp(0, 255).to(torch.uint8)
+    return out
+
+
+def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_levels: int) -> float:
+    """Compulsory HBM bytes of one launch group, SURVEY.md §8(d) (P = W*H pixels per image):
+       pyramid     read P + write the padded level 0 (P) + levels 1..3 (0.328 P), per image, 2 images per stream
+       lk_*        both pyramids of the pair read once (2 * 1.328 P) + 17 B per point (8 in, 8 out, 1 status)
+       gftt        read P (image) + mask P written and read + response map 4P written and read
+    """
+    P = float(W * H)
+    pyr = sum(1.0 / 4 ** l for l in range(n_levels))
+    if stage == "pyramid":
+        return S * 2 * (P + P * pyr)
+    if stage in ("lk_temporal", "lk_stereo"):
+        return S * 2 * P * pyr + 17.0 * n_pts_total
+    if stage == "gftt":
+        return S * (P + 2 * P + 8 * P)
+    return 0.0
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_dvfe(args):
+    import torch
+    import torch.distributed as dist
+    from dynamic_vins_b200 import BatchTracker, lib, make_config, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    c = synth.CONFIGS[WORKLOAD]
+    S, T, W, H = args.streams, args.frames, c["width"], c["height"]
+    # ---- synthetic frames: S independent streams (distinct seeds per stream and rank), T unique frames each
+    frames = torch.empty((T, 2, S, H, W), dtype=torch.uint8, device=dev)
+    for s in range(S):
+        st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + rank * S + s, stereo=True)
+        frames[:, :, s] = gpu_frames(st, T, dev)
+    torch.cuda.synchronize()
+    order = synth.pingpong_positions(T, args.warmup + args.steps)
+    times = [np.full(S, 0.05 * (i + 1)) for i in range(len(order))]
+
+    cfg = make_config(W, H, c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    P = W * H
+
+    def make_tracker():
+        t = BatchTracker(cfg)
+        t.set_stream(stream.cuda_stream)
+        return t
+
+    # ------------------------------------------------------------------ value: device-resident frames
+    trk = make_tracker()
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            f = frames[order[i]]
+            trk.track_image_device(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+        trk.profile(True)
+        launches0 = lib().dvfe_kernel_launches()
+        clocks = ClockSampler(local)
+        barrier()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_pts = 0
+        for i in range(args.warmup, args.warmup + args.steps):
+            f = frames[order[i]]
+            trk.track_image_device(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+        e1.record(stream)
+        barrier()
+        clock_info = clocks.stop()
+        launches = lib().dvfe_kernel_launches() - launches0
+        ms_value = e0.elapsed_time(e1)
+        prof, prof_steps = trk.profile_read()
+        trk.profile(False)
+        n_obs = sum(len(trk.features(s)) for s in range(S))
+        n_left = sum(int((trk.features(s)["cam"] == 0).sum()) for s in range(S))
+    trk.close()
+
+    # ------------------------------------------------------------------ e2e: host buffers through dvfe_track_image
+    host = torch.empty((T, 2, S, H, W), dtype=torch.uint8, pin_memory=True)
+    host.copy_(frames)
+    host_np = host.numpy()
+    trk = make_tracker()
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            trk.track_image(host_np[order[i], 0], host_np[order[i], 1], times[i])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, args.warmup + args.steps):
+            trk.track_image(host_np[order[i], 0], host_np[order[i], 1], times[i])
+        e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    trk.close()
+
+    t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_value, ms_e2e = float(t[0]), float(t[1])
+    total_frames = world * S * args.steps
+    value = total_frames / (ms_value * 1e-3)
+    e2e = total_frames / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        stage_ms = {k: v / max(prof_steps, 1) for k, v in prof.items()}
+        dom = max(stage_ms, key=stage_ms.get)
+        n_levels = 4
+        ab = algorithmic_bytes(dom, S, W, H, n_left, n_levels)
+        achieved = ab / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 images, int32/int64 patch sums, fp32 2x2 solve, fp64 undistortion", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": W, "height": H, "stereo": True,
+                       "max_cnt": c["max_cnt"], "min_dist": c["min_dist"], "lk": "21x21, maxLevel 3, fwd+bwd",
+                       "unique_frames_per_stream": T, "l2": "inputs_larger_than_L2",
+                       "tracked_points_per_step": n_left, "observations_per_step": n_obs},
+            "clocks": clock_info,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(2 * S * P), "d2h_bytes_per_step": int(S * (2 * c["max_cnt"] * 64 + 4))},
+            "gpu_launches": int(launches),
+            "stage_ms": stage_ms,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+def _oracle_frontend(stream_id: int):
+    from dynamic_vins_b200 import synth
+    from oracle import cv_front_end as cvfe
+    c = synth.CONFIGS[WORKLOAD]
+    st = synth.SynthStream(c["width"], c["height"], seed=1000 * c["config_id"] + stream_id, stereo=True)
+    fe = cvfe.FrontEnd(cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"], is_stereo=True),
+                       c["cam0"], c["cam1"], "raw")
+    return st, fe
+
+
+def cpu_baseline(budget_s: float) -> dict:
+    """The oracle (cv2 restatement of the reference's CPU FeatureTracker::TrackImage) timed on this box's host
+    cores on a bounded sample of the same workload: one stream, as many frames as fit the budget."""
+    import cv2
+    st, fe = _oracle_frontend(0)
+    T = 6
+    frames = [st.frame(k) for k in range(T)]
+    from dynamic_vins_b200.synth import pingpong_positions
+    order = pingpong_positions(T, 100000)
+    # warm-up
+    for i in range(3):
+        fr = frames[order[i]]
+        fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and n < 2000:
+        fr = frames[order[3 + n]]
+        fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (4 + n))
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "port",
+            "sample": f"1 stream x {n} frames of {WORKLOAD} (1280x720 stereo, 400 pts), cv2 {cv2.__version__} "
+                      f"with {cv2.getNumThreads()} threads, single process"}
+
+
+def _ref_worker(wid: int, T: int, conn):
+    import cv2
+    cv2.setNumThreads(1)
+    st, fe = _oracle_frontend(wid)
+    frames = [st.frame(k) for k in range(T)]
+    from dynamic_vins_b200.synth import pingpong_positions
+    i = 0
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg == "stop":
+            break
+        order = pingpong_positions(T, i + msg + 1)
+        for _ in range(msg):
+            fr = frames[order[i]]
+            fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
+            i += 1
+        conn.send(i)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on all host cores: one process per core, each running
+    the cv2-backed FeatureTracker::TrackImage restatement on its own stream (cv2 threads = 1 per process).  A
+    step = every worker advances its stream by one frame."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import cv2
+    ctx = mp.get_context("spawn")
+    n_workers = max(1, min(len(os.sched_getaffinity(0)), 64))
+    pipes, procs = [], []
+    for w in range(n_workers):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(w, args.frames, b), daemon=True)
+        p.start()
+        pipes.append(a); procs.append(p)
+    for a in pipes:
+        a.recv()
+
+    def step(n):
+        for a in pipes:
+            a.send(n)
+        for a in pipes:
+            a.recv()
+
+    step(args.warmup)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(1)
+    dt = time.perf_counter() - t0
+    for a in pipes:
+        a.send("stop")
+    for p in procs:
+        p.join(timeout=5)
+    value = n_workers * args.steps / dt
+    c = __import__("dynamic_vins_b200").synth.CONFIGS[WORKLOAD]
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u8 images, int16 patches, fp32 (OpenCV CPU)", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "width": c["width"], "height": c["height"],
+                      "stereo": True, "max_cnt": c["max_cnt"], "min_dist": c["min_dist"],
+                      "lk": "21x21, maxLevel 3, fwd+bwd", "unique_frames_per_stream": args.frames},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "port",
+                            "sample": f"{n_workers} processes x {args.steps} frames, one {WORKLOAD} stream each "
+                                      f"(cv2 {cv2.__version__}, 1 thread per process)"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_dvfe(a)

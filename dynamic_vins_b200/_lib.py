@@ -68,7 +68,7 @@ class State(C.Structure):
 # every symbol include/dvfe.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "dvfe_create", "dvfe_destroy", "dvfe_config_from_yaml", "dvfe_last_error", "dvfe_version",
-    "dvfe_kernel_launches", "dvfe_track_image", "dvfe_track_image_device", "dvfe_track_semantic_image",
+    "dvfe_kernel_launches", "dvfe_set_stream", "dvfe_profile", "dvfe_profile_read", "dvfe_track_image", "dvfe_track_image_device", "dvfe_track_semantic_image",
     "dvfe_insts_track", "dvfe_get_features", "dvfe_insts_output", "dvfe_get_state", "dvfe_set_state",
     "dvfe_op_build_pyramid", "dvfe_op_lk", "dvfe_op_min_eigen_val", "dvfe_op_good_features",
     "dvfe_op_disc_mask", "dvfe_op_erode_rect", "dvfe_op_lift_projective",
@@ -93,6 +93,9 @@ def lib() -> C.CDLL:
         L.dvfe_destroy.argtypes = [C.c_void_p]
         L.dvfe_destroy.restype = None
         L.dvfe_config_from_yaml.argtypes = [C.c_char_p, C.POINTER(Config)]
+        L.dvfe_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.dvfe_profile.argtypes = [C.c_void_p, C.c_int]
+        L.dvfe_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]
         L.dvfe_track_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.dvfe_track_image_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.dvfe_track_semantic_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,

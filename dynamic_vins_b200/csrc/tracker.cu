@@ -145,6 +145,7 @@ extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
 
 int dvfe_tracker::init() {
     DVFE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[i]));
     const size_t P = (size_t)W * H;
     for (int s = 0; s < 3; s++) DVFE_CHECK(dmalloc(&pyr[s], (size_t)B * desc.bytes));
     DVFE_CHECK(dmalloc(&d_in, 2 * B * P));
@@ -242,7 +243,8 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
         for (int k = 0; k < 2; k++) cudaFree(t->d_jobs[p][k]);
     }
     t->free_instances();
-    if (t->st) cudaStreamDestroy(t->st);
+    for (int i = 0; i <= dvfe_tracker::ST_COUNT; i++) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->st && t->own_stream) cudaStreamDestroy(t->st);
     delete t;
 }
 
@@ -255,27 +257,41 @@ int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, siz
     for (int s = 0; s < B; s++) h_dt[s] = time0[s] - prev_time[s];       // cur_time - prev_time
     DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt, B * sizeof(double), cudaMemcpyHostToDevice, st));
 
+    mark(0);
     PyrImgSet set;
     set.src[0] = d_left; set.src[1] = d_right;
     set.dst[0] = pyr[par]; set.dst[1] = pyr[2];
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
     DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st));
-
-    if (frames > 0) {
-        // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points) + ReduceVector + track_cnt++
+    mark(ST_PYRAMID + 1);
+    if (frames > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
         DVFE_CHECK(launch_lk(d_groups[par][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+    mark(ST_LK_TEMPORAL + 1);
+    if (frames > 0)   // ReduceVector x4 + track_cnt++
         DVFE_CHECK(launch_compact(bg, B, cap, st));
-    }
+    mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
     DVFE_CHECK(launch_gftt(d_jobs[par][semantic ? 1 : 0], nullptr, B, W, H, cap, st));
+    mark(ST_GFTT + 1);
     // UndistortedPts(cam0) + PtsVelocity
     DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
+    mark(ST_LEFT_POST + 1);
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
         DVFE_CHECK(launch_lk(d_groups[par][2], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+    mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs, d_nobs, st));
+    mark(ST_PACK + 1);
     DVFE_CUDA(cudaMemcpyAsync(h_nobs, d_nobs, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     DVFE_CUDA(cudaMemcpyAsync(h_obs, d_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, st));
+    mark(ST_D2H + 1);
     DVFE_CUDA(cudaStreamSynchronize(st));
+    if (prof) {
+        for (int i = 0; i < ST_COUNT; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) prof_ms[i] += ms;
+        }
+        prof_steps++;
+    }
     for (int s = 0; s < B; s++) prev_time[s] = time0[s];
     cur = 1 - cur;
     frames++;
@@ -403,4 +419,36 @@ extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt
         DVFE_CUDA(cudaMemcpy(t->bg.rprev_valid + o, stt->right_prev_valid, n, cudaMemcpyHostToDevice));
     }
     return DVFE_OK;
+}
+
+extern "C" int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream) {
+    if (!t) { dvfe_set_error("set_stream: null tracker"); return DVFE_ERR_INVALID; }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CUDA(cudaStreamSynchronize(t->st));
+    if (t->own_stream && t->st) cudaStreamDestroy(t->st);
+    t->st = (cudaStream_t)cuda_stream;
+    t->own_stream = false;
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_profile(dvfe_tracker* t, int enable) {
+    if (!t) { dvfe_set_error("profile: null tracker"); return DVFE_ERR_INVALID; }
+    t->prof = enable != 0;
+    if (enable) {
+        for (int i = 0; i < dvfe_tracker::ST_COUNT; i++) t->prof_ms[i] = 0.0;
+        t->prof_steps = 0;
+    }
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps) {
+    static const char* kNames[dvfe_tracker::ST_COUNT] = {"pyramid", "lk_temporal", "compact", "gftt",
+                                                         "left_post", "lk_stereo", "pack", "d2h"};
+    if (!t) { dvfe_set_error("profile_read: null tracker"); return DVFE_ERR_INVALID; }
+    for (int i = 0; i < dvfe_tracker::ST_COUNT; i++) {
+        if (names) names[i] = kNames[i];
+        if (total_ms) total_ms[i] = t->prof_ms[i];
+    }
+    if (steps) *steps = t->prof_steps;
+    return dvfe_tracker::ST_COUNT;
 }

@@ -50,6 +50,15 @@ struct dvfe_tracker {
     LkGroup* d_groups[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     GfttJob* d_jobs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     InstanceState* inst = nullptr;
+    bool own_stream = true;
+
+    // per-stage device timers
+    enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT, ST_LEFT_POST, ST_LK_STEREO, ST_PACK, ST_D2H, ST_COUNT };
+    bool prof = false;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    double prof_ms[ST_COUNT] = {};
+    long prof_steps = 0;
+    void mark(int i) { if (prof) cudaEventRecord(ev[i], st); }
 
     int init();
     int upload(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);

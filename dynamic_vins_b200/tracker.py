@@ -71,6 +71,23 @@ class BatchTracker:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream: int) -> None:
+        """run on a caller-owned CUDA stream (e.g. torch.cuda.Stream().cuda_stream)"""
+        L.check(L.lib().dvfe_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def profile(self, enable: bool) -> None:
+        L.check(L.lib().dvfe_profile(self._h, int(enable)))
+
+    def profile_read(self) -> Tuple[Dict[str, float], int]:
+        """{stage: summed device ms}, steps"""
+        names = (C.c_char_p * 16)()
+        ms = (C.c_double * 16)()
+        steps = C.c_long(0)
+        n = L.lib().dvfe_profile_read(self._h, names, ms, C.byref(steps))
+        if n < 0:
+            L.check(n)
+        return {names[i].decode(): ms[i] for i in range(n)}, steps.value
+
     # ---- frame steps ---------------------------------------------------------------------------
     def _times(self, time0) -> np.ndarray:
         t = np.ascontiguousarray(np.broadcast_to(np.asarray(time0, np.float64), (self.B,)))

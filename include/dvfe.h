@@ -109,6 +109,18 @@ const char* dvfe_version(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py `gpu_launches`). */
 unsigned long long dvfe_kernel_launches(void);
 
+/* Run this tracker's work on a caller-owned CUDA stream (a cudaStream_t passed as void*), so the caller can
+ * bracket steps with its own events.  Default: a private non-blocking stream. */
+int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream);
+
+/* Per-stage device timers (CUDA events on the tracker's stream around each stage of the frame step; the
+ * reference logs the same split with TicToc, front_end/background_tracker.cpp:72,98,105,138).
+ * dvfe_profile(t, 1) resets and enables, dvfe_profile(t, 0) disables.  dvfe_profile_read returns the number of
+ * stages; names[i] / total_ms[i] (caller arrays of >= 16 entries) get the stage names and the summed device
+ * time, *steps the number of steps accumulated. */
+int dvfe_profile(dvfe_tracker* t, int enable);
+int dvfe_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps);
+
 /* ---- the frame step ----------------------------------------------------------------- */
 
 /* FeatureTracker::TrackImage(SemanticImage&) for all B streams (front_end/background_tracker.cpp:52-158).

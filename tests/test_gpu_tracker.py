@@ -1,0 +1,195 @@
+"""GPU parity tests of the frame step (TrackImage / TrackSemanticImage) through the C ABI, against the committed
+golden fixtures and the cv2 oracle run live on the same seeded frames (SURVEY.md Appendix D protocol)."""
+import numpy as np
+import pytest
+
+from conftest import crc, feature_map_arrays, load_golden
+import dynamic_vins_b200 as dv
+from dynamic_vins_b200 import BatchTracker, FeatureTracker, make_config, obs_to_map, synth
+from oracle import cv_front_end as cvfe
+
+pytestmark = pytest.mark.gpu
+POS_TOL = 0.02        # px  (north_star)
+
+
+def cfg_of(name, n_streams=1, **kw):
+    c = dict(synth.CONFIGS[name])
+    c.update(kw)
+    return make_config(n_streams=n_streams, **{k: v for k, v in c.items() if k not in ("n_objects", "config_id")})
+
+
+def params_of(name):
+    c = synth.CONFIGS[name]
+    return cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"],
+                               max_dynamic_cnt=c.get("max_dynamic_cnt", 50), min_dynamic_dist=c.get("min_dynamic_dist", 5),
+                               use_mask_morphology=c.get("use_mask_morphology", 0),
+                               mask_morphology_size=c.get("mask_morphology_size", 5), is_stereo=c["stereo"])
+
+
+def compare_records(rec, ids, cams, v, cam0, dt_min=0.05):
+    """integer outputs bit-exact; pixel positions within 0.02 px; normalised coordinates and velocities within the
+    bound 0.02 px implies through the camera model and dt"""
+    assert np.array_equal(rec["id"], ids), "feature-id assignment differs"
+    assert np.array_equal(rec["cam"], cams), "camera lists differ (stereo status bits)"
+    if len(ids) == 0:
+        return 0.0
+    gv = rec["v"]
+    err_px = np.abs(gv[:, 3:5] - v[:, 3:5]).max()
+    assert err_px <= POS_TOL
+    un_tol = 1.5 * POS_TOL / min(cam0["fx"], cam0["fy"])
+    assert np.abs(gv[:, 0:2] - v[:, 0:2]).max() <= un_tol
+    assert np.array_equal(gv[:, 2], v[:, 2])
+    assert np.abs(gv[:, 5:7] - v[:, 5:7]).max() <= 2 * un_tol / dt_min
+    return err_px
+
+
+@pytest.mark.parametrize("name", ["c1_euroc_mono", "c2_kitti_stereo"])
+def test_free_running_vs_golden(name):
+    g = load_golden(f"tracker_{name}_raw.npz")
+    st = synth.make_stream(name, 0)
+    trk = FeatureTracker(cfg_of(name))
+    worst = 0.0
+    for k in range(int(g["n_frames"])):
+        fr = st.frame(k)
+        assert crc(fr.gray0) == int(g[f"f{k}_crc0"]), "synthetic generator drifted; regenerate tests/golden"
+        trk.batch.track_image(fr.gray0, fr.gray1, fr.time0)
+        worst = max(worst, compare_records(trk.batch.features(0), g[f"f{k}_ids"], g[f"f{k}_cams"], g[f"f{k}_v"],
+                                           synth.CONFIGS[name]["cam0"]))
+    print(f"{name}: worst pixel error vs golden {worst:.2e} px")
+
+
+def oracle_state(fe: cvfe.FrontEnd):
+    bg = fe.tracker.bg
+    n = len(bg.ids)
+    rp = np.zeros((n, 2), np.float32)
+    rv = np.zeros(n, np.uint8)
+    pu = np.zeros((n, 2), np.float32)
+    for i, fid in enumerate(bg.ids):
+        pu[i] = bg.prev_id_pts[fid]
+        if fid in bg.right_prev_id_pts:
+            rp[i] = bg.right_prev_id_pts[fid]
+            rv[i] = 1
+    return dict(n=n, next_id=fe.idc.next, prev_time=fe.tracker.prev_time, ids=np.asarray(bg.ids, np.uint32),
+                track_cnt=np.asarray(bg.track_cnt, np.int32), last_points=bg.last_points.copy(), prev_un=pu,
+                right_prev_un=rp, right_prev_valid=rv)
+
+
+@pytest.mark.parametrize("name,n_frames", [("c2_kitti_stereo", 10), ("c4_hd_stereo", 4)])
+def test_teacher_forced_vs_oracle(name, n_frames):
+    """every frame starts from the ORACLE's state (ids, track_cnt, points, velocity maps, id counter) and must
+    reproduce that frame's outputs: integer outputs bit-exact, positions within 0.02 px"""
+    c = synth.CONFIGS[name]
+    st = synth.make_stream(name, 1)
+    fe = cvfe.FrontEnd(params_of(name), c["cam0"], c["cam1"], "raw")
+    trk = BatchTracker(cfg_of(name))
+    for k in range(n_frames):
+        fr = st.frame(k)
+        if k > 0:
+            trk.set_state(0, oracle_state(fe))
+        want = fe.step(fr)["features"]
+        trk.track_image(fr.gray0, fr.gray1, fr.time0)
+        ids, cams, v = feature_map_arrays(want)
+        compare_records(trk.features(0), ids, cams, v, c["cam0"])
+        # state after the frame agrees as well (bit-exact integers)
+        s_gpu, s_ref = trk.get_state(0), oracle_state(fe)
+        assert s_gpu["n"] == s_ref["n"] and s_gpu["next_id"] == s_ref["next_id"]
+        assert np.array_equal(s_gpu["ids"], s_ref["ids"]) and np.array_equal(s_gpu["track_cnt"], s_ref["track_cnt"])
+        assert np.array_equal(s_gpu["right_prev_valid"], s_ref["right_prev_valid"])
+    trk.close()
+
+
+def test_batch_equals_single_streams():
+    """B streams in one tracker == B single-stream trackers, bit for bit (streams are independent)"""
+    name, B, T = "c2_kitti_stereo", 3, 4
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    batch = BatchTracker(cfg_of(name, n_streams=B))
+    singles = [BatchTracker(cfg_of(name)) for _ in range(B)]
+    for k in range(T):
+        frs = [s.frame(k) for s in streams]
+        L = np.stack([f.gray0 for f in frs])
+        R = np.stack([f.gray1 for f in frs])
+        batch.track_image(L, R, [f.time0 for f in frs])
+        for s in range(B):
+            singles[s].track_image(frs[s].gray0, frs[s].gray1, frs[s].time0)
+            a, b = batch.features(s), singles[s].features(0)
+            assert a.tobytes() == b.tobytes()
+    batch.close()
+    [s.close() for s in singles]
+
+
+def test_state_roundtrip_and_determinism():
+    name = "c1_euroc_mono"
+    st = synth.make_stream(name, 2)
+    a, b = BatchTracker(cfg_of(name)), BatchTracker(cfg_of(name))
+    for k in range(3):
+        fr = st.frame(k)
+        a.track_image(fr.gray0, None, fr.time0)
+        b.track_image(fr.gray0, None, fr.time0)
+    assert a.features(0).tobytes() == b.features(0).tobytes()
+    s = a.get_state(0)
+    assert s["n"] == len(a.features(0)) and s["next_id"] == s["ids"].max() + 1 and (s["track_cnt"] >= 1).all()
+    b.set_state(0, s)
+    fr = st.frame(3)
+    a.track_image(fr.gray0, None, fr.time0)
+    b.track_image(fr.gray0, None, fr.time0)
+    assert a.features(0).tobytes() == b.features(0).tobytes()
+    a.close(); b.close()
+
+
+def test_mono_frame_in_stereo_config_and_first_frame_velocity():
+    name = "c2_kitti_stereo"
+    c = synth.CONFIGS[name]
+    st = synth.make_stream(name, 3)
+    fe = cvfe.FrontEnd(params_of(name), c["cam0"], c["cam1"], "raw")
+    trk = BatchTracker(cfg_of(name))
+    for k in range(4):
+        fr = st.frame(k)
+        right = None if k == 2 else fr.gray1      # a dropped right image: the stereo block is skipped (:107)
+        fr.gray1 = right
+        want = fe.step(fr)["features"]
+        trk.track_image(fr.gray0, right, fr.time0)
+        ids, cams, v = feature_map_arrays(want)
+        rec = trk.features(0)
+        compare_records(rec, ids, cams, v, c["cam0"])
+        if k == 0:
+            assert (rec["v"][:, 5:7] == 0).all()      # first frame: all velocities are zero
+        if k == 2:
+            assert (rec["cam"] == 0).all()
+    trk.close()
+
+
+def test_semantic_background_vs_oracle():
+    """TrackSemanticImage: eroded inverse instance mask gates tracking and detection (C3, background part)"""
+    name = "c3_zed_dynamic"
+    c = synth.CONFIGS[name]
+    st = synth.make_stream(name, 0)
+    P = params_of(name)
+    ref = cvfe.FeatureTracker(P, cvfe.PinholeCamera(**c["cam0"]), cvfe.PinholeCamera(**c["cam1"]))
+    trk = FeatureTracker(cfg_of(name))
+    for k in range(5):
+        fr = st.frame(k)
+        if k == 3:                      # a frame without detections: the mask is all 255
+            fr.exist_inst, fr.boxes = False, []
+        want = ref.track_semantic_image(fr.gray0, fr.gray1, fr.time0, fr.inv_merge_mask, fr.exist_inst)
+        trk.batch.track_semantic_image(fr.gray0, fr.gray1, fr.inv_merge_mask, fr.exist_inst, fr.time0)
+        ids, cams, v = feature_map_arrays(want)
+        rec = trk.batch.features(0)
+        compare_records(rec, ids, cams, v, c["cam0"])
+        if fr.exist_inst:
+            # no background feature sits on an (un-eroded) object pixel of the eroded region mask
+            region = cvfe.erode_mask(fr.inv_merge_mask, P.mask_morphology_size)
+            left = rec[rec["cam"] == 0]
+            new = left  # tracked points were filtered, new points were detected inside the region
+            px = np.rint(new["v"][:, 3:5]).astype(int)
+            assert (region[px[:, 1], px[:, 0]] != 0).all()
+
+
+def test_reference_api_names():
+    name = "c1_euroc_mono"
+    trk = FeatureTracker(cfg_of(name))
+    fr = synth.make_stream(name, 0).frame(0)
+    out = trk.TrackImage(fr)
+    assert len(out) == 150 and all(len(v) == 1 and v[0][0] == 0 and v[0][1].shape == (7,) for v in out.values())
+    assert sorted(out) == list(range(1, 151))       # global_id_count starts at 1
+    txt = dv.tracker.serialize_point_features(out)
+    assert txt.count("\n") == 150 and txt.startswith("0 1 ")
