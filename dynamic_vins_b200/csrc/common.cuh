@@ -55,7 +55,10 @@ static inline PyrDesc make_pyr_desc(int w, int h, int max_level) {
         lw = nw; lh = nh;
     }
     d.n_levels = l;
-    d.bytes = off;
+    // one pyramid = a whole number of level-0 rows, so a batch of pyramids is a pitched 3-D array whose slices
+    // can be filled by a single cudaMemcpy3D straight from the caller's images
+    const unsigned unit = (unsigned)d.lv[0].pitch * 16u;
+    d.bytes = ((off + unit - 1) / unit) * unit;
     return d;
 }
 

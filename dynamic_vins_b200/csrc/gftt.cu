@@ -22,8 +22,6 @@
 
 #include "kernels.cuh"
 
-#define RESP_TW 32
-#define RESP_TH 16
 #define NMS_THREADS 1024
 #define NMS_MAX_K 2048
 
@@ -91,142 +89,198 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
     }
 }
 
-// ---- response map (cv::cornerMinEigenVal, blockSize 3, ksize 3) + masked max -----------------------
-__device__ __forceinline__ void resp_tile(const uint8_t* __restrict__ img, int pitch, int w, int h, int tx0, int ty0,
+// ---- response map (cv::cornerMinEigenVal, blockSize 3, ksize 3), masked max, local maxima ------------------
+// One block owns a 30x14 tile of pixels and computes lambda on the 32x16 region around it (1-pixel ring for the
+// 3x3 local-maximum test), from Sobel derivatives on 34x18 and image pixels on 36x20, all staged in shared
+// memory.  Nothing but the pre-candidates (local maxima with mask != 0) and the masked maximum leaves the chip;
+// the quality threshold needs the global maximum and is applied by the selection kernel.
+#define RT_OW 62
+#define RT_OH 14
+#define RT_LW 64
+#define RT_LH 16
+#define RT_DW 66
+#define RT_DH 18
+#define RT_IW 68
+#define RT_IH 20
+
+template <bool WRITE_EIG, bool EMIT>
+__device__ __forceinline__ void resp_tile(const uint8_t* __restrict__ img, int pitch, int w, int h, int ox0, int oy0,
                                           float* __restrict__ eig, const uint8_t* __restrict__ mask, int mask_pitch,
-                                          int* max_out) {
-    __shared__ uint8_t s_img[RESP_TH + 4][RESP_TW + 4];
-    __shared__ float s_dx[RESP_TH + 2][RESP_TW + 2];
-    __shared__ float s_dy[RESP_TH + 2][RESP_TW + 2];
+                                          int* __restrict__ counters, unsigned long long* __restrict__ cand, int cand_cap) {
+    __shared__ uint8_t s_img[RT_IH][RT_IW + 4];
+    __shared__ float s_p[3][RT_DH][RT_DW + 1];       // derivative products xx, xy, yy (the CV_32F cov image)
+    __shared__ double s_h[3][RT_DH][RT_LW];          // horizontal 3-sums
+    __shared__ float s_lam[RT_LH][RT_LW + 1];
     __shared__ int s_max[8];
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int nthr = blockDim.x * blockDim.y;
+    const int tid = threadIdx.x;
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = s * 2.0f;
+    const int lx0 = ox0 - 1, ly0 = oy0 - 1;      // lambda region origin
+    const int dx0 = lx0 - 1, dy0 = ly0 - 1;      // derivative region origin
+    const int ix0 = dx0 - 1, iy0 = dy0 - 1;      // image region origin
 
-    for (int i = tid; i < (RESP_TH + 4) * (RESP_TW + 4); i += nthr) {
-        const int r = i / (RESP_TW + 4), c = i - r * (RESP_TW + 4);
-        const int gx = reflect101(tx0 - 2 + c, w), gy = reflect101(ty0 - 2 + r, h);
-        s_img[r][c] = __ldg(img + (size_t)gy * pitch + gx);
+    if (EMIT) {
+        // a tile whose owned pixels are all masked out contributes neither candidates nor the maximum
+        int any = 0;
+        for (int i = tid; i < RT_OW * RT_OH; i += 256) {
+            const int r = i / RT_OW, c = i - r * RT_OW;
+            const int gx = ox0 + c, gy = oy0 + r;
+            if (gx < w && gy < h) any |= mask[(size_t)gy * mask_pitch + gx];
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+    // P0: image region, REFLECT_101
+    for (int i = tid; i < RT_IH * RT_IW; i += 256) {
+        const int r = i / RT_IW, c = i - r * RT_IW;
+        s_img[r][c] = __ldg(img + (size_t)reflect101(iy0 + r, h) * pitch + reflect101(ix0 + c, w));
     }
     __syncthreads();
-    // Sobel at in-image positions of the tile + 1 halo
-    for (int i = tid; i < (RESP_TH + 2) * (RESP_TW + 2); i += nthr) {
-        const int r = i / (RESP_TW + 2), c = i - r * (RESP_TW + 2);
-        const int gx = tx0 - 1 + c, gy = ty0 - 1 + r;
+    // P1: Sobel at the in-image positions of the derivative region, products rounded to float
+    for (int i = tid; i < RT_DH * RT_DW; i += 256) {
+        const int r = i / RT_DW, c = i - r * RT_DW;
+        const int gx = dx0 + c, gy = dy0 + r;
         if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-            // image taps: s_img[r + dy + 1][c + dx + 1], dy,dx in {-1,0,1} -> rows r..r+2, cols c..c+2
             const float a00 = s_img[r][c], a01 = s_img[r][c + 1], a02 = s_img[r][c + 2];
-            const float a10 = s_img[r + 1][c], a11 = s_img[r + 1][c + 1], a12 = s_img[r + 1][c + 2];
+            const float a10 = s_img[r + 1][c], a12 = s_img[r + 1][c + 2];
             const float a20 = s_img[r + 2][c], a21 = s_img[r + 2][c + 1], a22 = s_img[r + 2][c + 2];
             // Dx: row kernel [-1 0 1] exact, column kernel [1 2 1]*scale -> fma(s, d0 + d2, (2s)*d1)
             const float d0 = a02 - a00, d1 = a12 - a10, d2 = a22 - a20;
-            s_dx[r][c] = __fmaf_rn(s, __fadd_rn(d0, d2), __fmul_rn(s2, d1));
+            const float dx = __fmaf_rn(s, __fadd_rn(d0, d2), __fmul_rn(s2, d1));
             // Dy: row kernel [1 2 1]*scale -> fma(s, r, fma(2s, c, s*l)); column kernel [-1 0 1]
             const float top = __fmaf_rn(s, a02, __fmaf_rn(s2, a01, __fmul_rn(s, a00)));
             const float bot = __fmaf_rn(s, a22, __fmaf_rn(s2, a21, __fmul_rn(s, a20)));
-            s_dy[r][c] = __fsub_rn(bot, top);
-            (void)a11;
+            const float dy = __fsub_rn(bot, top);
+            s_p[0][r][c] = __fmul_rn(dx, dx);
+            s_p[1][r][c] = __fmul_rn(dx, dy);
+            s_p[2][r][c] = __fmul_rn(dy, dy);
         }
     }
     __syncthreads();
-    // positions outside the image take the derivative of their REFLECT_101 position (box filter border)
-    for (int i = tid; i < (RESP_TH + 2) * (RESP_TW + 2); i += nthr) {
-        const int r = i / (RESP_TW + 2), c = i - r * (RESP_TW + 2);
-        const int gx = tx0 - 1 + c, gy = ty0 - 1 + r;
-        if (!(gx >= 0 && gx < w && gy >= 0 && gy < h)) {
-            const int rx = reflect101(gx, w), ry = reflect101(gy, h);
-            const int rr = ry - (ty0 - 1), rc = rx - (tx0 - 1);
-            if (rr >= 0 && rr < RESP_TH + 2 && rc >= 0 && rc < RESP_TW + 2) {
-                s_dx[r][c] = s_dx[rr][rc];
-                s_dy[r][c] = s_dy[rr][rc];
-            } else {   // only reachable for positions that no in-image output pixel of this tile uses
-                s_dx[r][c] = 0.f;
-                s_dy[r][c] = 0.f;
+    // P2: positions one step outside the image take the products of their REFLECT_101 position (the box
+    // filter's border rule applies to the cov image, not to the input image)
+    if (dx0 < 0 || dy0 < 0 || dx0 + RT_DW > w || dy0 + RT_DH > h) {
+        for (int i = tid; i < RT_DH * RT_DW; i += 256) {
+            const int r = i / RT_DW, c = i - r * RT_DW;
+            const int gx = dx0 + c, gy = dy0 + r;
+            if (!(gx >= 0 && gx < w && gy >= 0 && gy < h)) {
+                const int rr = reflect101(gy, h) - dy0, rc = reflect101(gx, w) - dx0;
+                const bool ok = gx >= -1 && gx <= w && gy >= -1 && gy <= h && rr >= 0 && rr < RT_DH && rc >= 0 && rc < RT_DW;
+#pragma unroll
+                for (int k = 0; k < 3; k++) s_p[k][r][c] = ok ? s_p[k][rr][rc] : 0.f;
             }
         }
-    }
-    __syncthreads();
-    int best = INT_MIN;
-    for (int i = tid; i < RESP_TH * RESP_TW; i += nthr) {
-        const int r = i / RESP_TW, c = i - r * RESP_TW;
-        const int gx = tx0 + c, gy = ty0 + r;
-        if (gx < w && gy < h) {
-            double sxx = 0.0, sxy = 0.0, syy = 0.0;
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const float dx = s_dx[r + j][c + k], dy = s_dy[r + j][c + k];
-                    sxx += (double)__fmul_rn(dx, dx);
-                    sxy += (double)__fmul_rn(dx, dy);
-                    syy += (double)__fmul_rn(dy, dy);
-                }
-            const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
-            const float amc = __fsub_rn(a, cc);
-            const float lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
-            eig[(size_t)gy * w + gx] = lam;
-            if (max_out != nullptr && (mask == nullptr || mask[(size_t)gy * mask_pitch + gx] != 0)) {
-                const int o = f2ord(lam);
-                best = o > best ? o : best;
-            }
-        }
-    }
-    if (max_out != nullptr) {
-        best = __reduce_max_sync(0xffffffffu, best);
-        if ((tid & 31) == 0) s_max[tid >> 5] = best;
         __syncthreads();
-        if (tid == 0) {
-            int m = s_max[0];
-            for (int i = 1; i < nthr / 32; i++) m = s_max[i] > m ? s_max[i] : m;
-            if (m != INT_MIN) atomicMax(max_out, m);
+    }
+    // P3: horizontal 3-sums accumulated in double (cv::boxFilter: RowSum<float,double>)
+    for (int i = tid; i < RT_DH * RT_LW; i += 256) {
+        const int r = i >> 6, c = i & 63;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            s_h[k][r][c] = ((double)s_p[k][r][c] + (double)s_p[k][r][c + 1]) + (double)s_p[k][r][c + 2];
+    }
+    __syncthreads();
+    // P4: vertical 3-sums (ColumnSum<double,float>) and lambda on the 64 x 16 region; 4 rows per thread
+    const int c = tid & 63, rbase = tid >> 6;
+    int best = INT_MIN;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int r = rbase + 4 * q;
+        const int gx = lx0 + c, gy = ly0 + r;
+        float lam = 0.f;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+            const float cxx = (float)((s_h[0][r][c] + s_h[0][r + 1][c]) + s_h[0][r + 2][c]);
+            const float cxy = (float)((s_h[1][r][c] + s_h[1][r + 1][c]) + s_h[1][r + 2][c]);
+            const float cyy = (float)((s_h[2][r][c] + s_h[2][r + 1][c]) + s_h[2][r + 2][c]);
+            const float a = __fmul_rn(cxx, 0.5f), b = cxy, cc = __fmul_rn(cyy, 0.5f);
+            const float amc = __fsub_rn(a, cc);
+            lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+            const bool owned = c >= 1 && c <= RT_OW && r >= 1 && r <= RT_OH;
+            if (owned) {
+                if (WRITE_EIG) eig[(size_t)gy * w + gx] = lam;
+                if (EMIT && mask[(size_t)gy * mask_pitch + gx] != 0) best = max(best, f2ord(lam));
+            }
         }
+        s_lam[r][c] = lam;
+    }
+    if (!EMIT) return;
+    __syncthreads();
+    // P5: masked maximum of the tile; pre-candidates = 3x3 local maxima with mask != 0 inside the 1-pixel border
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((tid & 31) == 0) s_max[tid >> 5] = best;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int r = rbase + 4 * q;
+        const int gx = lx0 + c, gy = ly0 + r;
+        bool is_cand = false;
+        float v = 0.f;
+        if (c >= 1 && c <= RT_OW && r >= 1 && r <= RT_OH && gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
+            v = s_lam[r][c];
+            if (v != 0.f && mask[(size_t)gy * mask_pitch + gx] != 0) {
+                float m = fmaxf(fmaxf(s_lam[r - 1][c - 1], s_lam[r - 1][c]), fmaxf(s_lam[r - 1][c + 1], s_lam[r][c - 1]));
+                m = fmaxf(m, fmaxf(fmaxf(s_lam[r][c + 1], s_lam[r + 1][c - 1]), fmaxf(s_lam[r + 1][c], s_lam[r + 1][c + 1])));
+                is_cand = !(m > v);
+            }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+        if (ballot) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&counters[0], __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (is_cand) {
+                const int pos = base + __popc(ballot & ((1u << lane) - 1));
+                if (pos < cand_cap)
+                    cand[pos] = ((unsigned long long)((unsigned)f2ord(v) ^ 0x80000000u) << 32) | (unsigned)(gy * w + gx);
+                else
+                    counters[2] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = s_max[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) m = max(m, s_max[i]);
+        if (m != INT_MIN) atomicMax(&counters[1], m);
     }
 }
 
 __global__ void __launch_bounds__(256) k_gftt_response(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.z];
-    if (!gftt_job_active(J)) return;
-    const int tx0 = blockIdx.x * RESP_TW, ty0 = blockIdx.y * RESP_TH;
-    if (tx0 >= J.w || ty0 >= J.h) return;
-    if (J.eig_in != nullptr) {
-        // externally supplied response map: only the masked max is needed
-        int best = INT_MIN;
-        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-        for (int i = tid; i < RESP_TH * RESP_TW; i += blockDim.x * blockDim.y) {
-            const int gx = tx0 + i % RESP_TW, gy = ty0 + i / RESP_TW;
-            if (gx < J.w && gy < J.h && J.mask[(size_t)gy * J.mask_pitch + gx] != 0) {
-                const int o = f2ord(J.eig_in[(size_t)gy * J.w + gx]);
-                best = o > best ? o : best;
-            }
-        }
-        best = __reduce_max_sync(0xffffffffu, best);
-        if ((tid & 31) == 0 && best != INT_MIN) atomicMax(&J.counters[1], best);
-        return;
-    }
-    resp_tile(J.img, J.img_pitch, J.w, J.h, tx0, ty0, J.eig, J.mask, J.mask_pitch, &J.counters[1]);
+    if (!gftt_job_active(J) || J.eig_in != nullptr) return;
+    const int ox0 = blockIdx.x * RT_OW, oy0 = blockIdx.y * RT_OH;
+    if (ox0 >= J.w || oy0 >= J.h) return;
+    resp_tile<false, true>(J.img, J.img_pitch, J.w, J.h, ox0, oy0, nullptr, J.mask, J.mask_pitch, J.counters, J.cand,
+                           J.cand_cap);
 }
 
 __global__ void __launch_bounds__(256) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
-    resp_tile(img, pitch, w, h, blockIdx.x * RESP_TW, blockIdx.y * RESP_TH, eig, nullptr, 0, nullptr);
+    resp_tile<true, false>(img, pitch, w, h, blockIdx.x * RT_OW, blockIdx.y * RT_OH, eig, nullptr, 0, nullptr, nullptr, 0);
 }
 
-// ---- candidates: threshold, 3x3 local max, mask -----------------------------------------------------
-__global__ void __launch_bounds__(256) k_gftt_candidates(const GfttJob* __restrict__ jobs) {
+// ---- externally supplied response map (seam op): masked max, then the same pre-candidates ---------------
+__global__ void __launch_bounds__(256) k_gftt_max_ext(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.z];
-    if (!gftt_job_active(J)) return;
+    if (!gftt_job_active(J) || J.eig_in == nullptr) return;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const float* __restrict__ eig = J.eig_in ? J.eig_in : J.eig;
-    const int mo = J.counters[1];
-    const double maxVal = (mo == INT_MIN) ? 0.0 : (double)ord2f(mo);
-    const float thr = (float)(maxVal * J.quality);
+    int best = INT_MIN;
+    if (x < J.w && y < J.h && J.mask[(size_t)y * J.mask_pitch + x] != 0) best = f2ord(J.eig_in[(size_t)y * J.w + x]);
+    best = __reduce_max_sync(0xffffffffu, best);
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && best != INT_MIN) atomicMax(&J.counters[1], best);
+}
+
+__global__ void __launch_bounds__(256) k_gftt_candidates_ext(const GfttJob* __restrict__ jobs) {
+    const GfttJob& J = jobs[blockIdx.z];
+    if (!gftt_job_active(J) || J.eig_in == nullptr) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const float* __restrict__ eig = J.eig_in;
     bool is_cand = false;
     float v = 0.f;
     if (x >= 1 && x < J.w - 1 && y >= 1 && y < J.h - 1) {
         v = eig[(size_t)y * J.w + x];
-        if (v > thr && v != 0.f && J.mask[(size_t)y * J.mask_pitch + x] != 0) {
-            // dilate(3x3) of the thresholded map equals v  <=>  no neighbour above both thr and v
+        if (v != 0.f && J.mask[(size_t)y * J.mask_pitch + x] != 0) {
             const float* p = eig + (size_t)y * J.w + x;
             float m = fmaxf(fmaxf(p[-J.w - 1], p[-J.w]), fmaxf(p[-J.w + 1], p[-1]));
             m = fmaxf(m, fmaxf(fmaxf(p[1], p[J.w - 1]), fmaxf(p[J.w], p[J.w + 1])));
@@ -248,25 +302,37 @@ __global__ void __launch_bounds__(256) k_gftt_candidates(const GfttJob* __restri
     }
 }
 
-// ---- selection: parallel greedy min-distance suppression + top-K, one CTA per job ------------------------
+// ---- selection: quality threshold, parallel greedy min-distance suppression, top-K; one CTA per job -------------
 __device__ __forceinline__ int block_excl_scan_inplace(int* data, int n, int* s_part /* [NMS_THREADS] */) {
     // exclusive scan of data[0..n) in place, returns the total; all threads of the block participate
     const int tid = threadIdx.x;
     const int per = (n + NMS_THREADS - 1) / NMS_THREADS;
-    const int b = tid * per, e = min(b + per, n);
+    const int b = min(tid * per, n), e = min(b + per, n);
     int sum = 0;
     for (int i = b; i < e; i++) sum += data[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the partial sums
-    for (int off = 1; off < NMS_THREADS; off <<= 1) {
-        const int v = (tid >= off) ? s_part[tid - off] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
+    // block-wide inclusive scan of the partial sums: warp shuffles + one pass over the 32 warp totals
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
     }
-    const int total = s_part[NMS_THREADS - 1];
-    int run = s_part[tid] - sum;
+    __syncthreads();
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int wsum = s_part[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wsum, off);
+            if (lane >= off) wsum += v;
+        }
+        s_part[32 + lane] = wsum;      // inclusive totals per warp
+    }
+    __syncthreads();
+    const int total = s_part[32 + 31];
+    int run = incl - sum + (warp > 0 ? s_part[32 + warp - 1] : 0);
     for (int i = b; i < e; i++) {
         const int v = data[i];
         data[i] = run;
@@ -276,17 +342,53 @@ __device__ __forceinline__ int block_excl_scan_inplace(int* data, int n, int* s_
     return total;
 }
 
+// K-th largest key (1-based k) among keys[0..n) that satisfy pred; 8 radix passes of 8 bits from the top.
+template <typename Pred>
+__device__ __forceinline__ unsigned long long block_select_kth(const unsigned long long* __restrict__ keys, int n, int k,
+                                                               Pred pred, int* s_hist, unsigned long long* s_prefix,
+                                                               int* s_remaining) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { *s_prefix = 0ull; *s_remaining = k; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = *s_prefix;
+        const unsigned long long himask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const unsigned long long key = keys[i];
+            if ((key & himask) == prefix && pred(i, key)) atomicAdd(&s_hist[(int)((key >> shift) & 255)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rem = *s_remaining, b = 255;
+            for (; b > 0; b--) {
+                if (s_hist[b] >= rem) break;
+                rem -= s_hist[b];
+            }
+            *s_remaining = rem;
+            *s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    return *s_prefix;
+}
+
+#define NMS_SMEM_STATE 16384
+
 __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __restrict__ jobs) {
-    __shared__ int s_part[NMS_THREADS];
+    __shared__ int s_part[64];
     __shared__ unsigned long long s_sel[NMS_MAX_K];
     __shared__ int s_hist[256];
     __shared__ int s_cnt;
     __shared__ unsigned long long s_prefix;
     __shared__ int s_remaining;
+    __shared__ uint8_t s_state[NMS_SMEM_STATE];
 
     const GfttJob& J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
-    if (tid == 0) J.counters[4] = 0;       // new_cnt
+    if (tid == 0) J.counters[4] = 0;       // number of new corners
     if (!gftt_job_active(J)) return;
     const int n_old = *J.n;
     int K = J.max_cnt - n_old;
@@ -294,6 +396,27 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     int nc = J.counters[0];
     if (nc > J.cand_cap) nc = J.cand_cap;
     if (nc <= 0) return;
+
+    // quality threshold: keep lambda > (float)(maxVal * quality)   (cv::threshold THRESH_TOZERO, strict)
+    const int mo = J.counters[1];
+    const double maxVal = (mo == INT_MIN) ? 0.0 : (double)ord2f(mo);
+    const float thr = (float)(maxVal * J.quality);
+    const unsigned long long thr_key = ((unsigned long long)((unsigned)f2ord(thr) ^ 0x80000000u) << 32) | 0xffffffffull;
+    const unsigned long long* __restrict__ all = J.cand;
+
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    {
+        int c = 0;
+        for (int i = tid; i < nc; i += NMS_THREADS) c += all[i] > thr_key ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    }
+    __syncthreads();
+    const int nv = s_cnt;                   // candidates above the threshold (cv: tmpCorners.size())
+    __syncthreads();
+    if (tid == 0) J.counters[3] = nv;
+    if (nv == 0) return;
 
     const int w = J.w;
     const int cell = (int)lrintf(J.min_dist) > 0 ? (int)lrintf(J.min_dist) : 1;
@@ -304,141 +427,144 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     const double md2 = (double)J.min_dist * (double)J.min_dist;
     const bool use_nms = J.min_dist >= 1.f;
 
-    unsigned long long* sorted = J.cand2;        // candidates grouped by cell, descending key inside a cell
-    volatile uint8_t* state = J.state;           // 0 undecided, 1 accepted, 2 rejected
-
-    if (use_nms) {
-        for (int i = tid; i < 2 * (ncell + 1); i += NMS_THREADS) cstart[i] = 0;
+    unsigned long long* work = J.cand2;          // the M strongest candidates (unordered)
+    unsigned long long* cs = J.cand3;            // the same, grouped by cell, descending key inside a cell
+    // Only the first K accepted corners in rank order are wanted, and whether a candidate is accepted depends only
+    // on stronger candidates: the greedy result restricted to the M strongest candidates is a prefix of the full
+    // result.  Start with a small M and grow it until K corners are accepted or every candidate is in.
+    int M = min(nv, max(512, 16 * K));
+    int n_acc = 0;
+    volatile uint8_t* state = nullptr;
+    for (;;) {
+        unsigned long long tkey = thr_key + 1ull;       // keep keys >= tkey
+        if (M < nv) {
+            tkey = block_select_kth(all, nc, M, [&](int, unsigned long long key) { return key > thr_key; }, s_hist,
+                                    &s_prefix, &s_remaining);
+        }
+        if (tid == 0) s_cnt = 0;
         __syncthreads();
-        for (int i = tid; i < nc; i += NMS_THREADS) {
-            const unsigned idx = (unsigned)J.cand[i];
-            const int y = idx / w, x = idx - y * w;
-            atomicAdd(&cstart[(y / cell) * gw + x / cell], 1);
+        for (int i0 = 0; i0 < nc; i0 += NMS_THREADS) {
+            const int i = i0 + tid;
+            const unsigned long long key = i < nc ? all[i] : 0ull;
+            const bool keep = i < nc && key >= tkey && key > thr_key;
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if ((tid & 31) == 0 && ballot) base = atomicAdd(&s_cnt, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) work[base + __popc(ballot & ((1u << (tid & 31)) - 1))] = key;
         }
         __syncthreads();
-        block_excl_scan_inplace(cstart, ncell + 1, s_part);
-        // scatter into cells (unordered), then rank-sort each cell back into J.cand
-        for (int i = tid; i < nc; i += NMS_THREADS) {
-            const unsigned long long key = J.cand[i];
-            const unsigned idx = (unsigned)key;
-            const int y = idx / w, x = idx - y * w;
-            const int c = (y / cell) * gw + x / cell;
-            const int pos = atomicAdd(&ccur[c], 1);
-            sorted[cstart[c] + pos] = key;
-        }
-        __syncthreads();
-        {
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int c = warp; c < ncell; c += NMS_THREADS / 32) {
-                const int b = cstart[c], m = cstart[c + 1] - b;
-                for (int e = lane; e < m; e += 32) {
-                    const unsigned long long key = sorted[b + e];
-                    int rank = 0;
-                    for (int o = 0; o < m; o++) rank += (sorted[b + o] > key) ? 1 : 0;
-                    J.cand[b + rank] = key;
-                }
+        // (s_cnt == M: keys are unique)
+        state = (M <= NMS_SMEM_STATE) ? (volatile uint8_t*)s_state : (volatile uint8_t*)J.state;
+        if (use_nms) {
+            for (int i = tid; i < 2 * (ncell + 1); i += NMS_THREADS) cstart[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < M; i += NMS_THREADS) {
+                const unsigned idx = (unsigned)work[i];
+                const int y = idx / w, x = idx - y * w;
+                atomicAdd(&cstart[(y / cell) * gw + x / cell], 1);
             }
-        }
-        __syncthreads();
-        // J.cand is now cell-grouped and sorted; decide by rounds
-        const unsigned long long* __restrict__ cs = J.cand;
-        for (int i = tid; i < nc; i += NMS_THREADS) state[i] = 0;
-        __syncthreads();
-        for (;;) {
-            int undecided = 0;
-            for (int i = tid; i < nc; i += NMS_THREADS) {
-                if (state[i] != 0) continue;
-                const unsigned long long key = cs[i];
+            __syncthreads();
+            block_excl_scan_inplace(cstart, ncell + 1, s_part);
+            for (int i = tid; i < M; i += NMS_THREADS) {
+                const unsigned long long key = work[i];
                 const unsigned idx = (unsigned)key;
                 const int y = idx / w, x = idx - y * w;
-                const int xc = x / cell, yc = y / cell;
-                const int x1 = max(xc - 1, 0), x2 = min(xc + 1, gw - 1);
-                const int y1 = max(yc - 1, 0), y2 = min(yc + 1, gh - 1);
-                bool rejected = false, blocked = false;
-                for (int yy = y1; yy <= y2 && !rejected; yy++)
-                    for (int xx = x1; xx <= x2 && !rejected; xx++) {
-                        const int c = yy * gw + xx;
-                        const int e = cstart[c + 1];
-                        for (int j = cstart[c]; j < e; j++) {
-                            const unsigned long long kj = cs[j];
-                            if (kj <= key) break;                 // only stronger candidates matter
-                            const unsigned ij = (unsigned)kj;
-                            const int yj = ij / w, xj = ij - yj * w;
-                            const int dx = x - xj, dy = y - yj;
-                            if ((double)(dx * dx + dy * dy) < md2) {
-                                const uint8_t sj = state[j];
-                                if (sj == 1) { rejected = true; break; }
-                                if (sj == 0) blocked = true;
+                const int c = (y / cell) * gw + x / cell;
+                const int pos = atomicAdd(&ccur[c], 1);
+                cs[cstart[c] + pos] = key;
+            }
+            __syncthreads();
+            // rank-sort every cell (descending) from cs back into work, then swap roles
+            {
+                const int warp = tid >> 5, lane = tid & 31;
+                for (int c = warp; c < ncell; c += NMS_THREADS / 32) {
+                    const int b = cstart[c], m = cstart[c + 1] - b;
+                    for (int e = lane; e < m; e += 32) {
+                        const unsigned long long key = cs[b + e];
+                        int rank = 0;
+                        for (int o = 0; o < m; o++) rank += (cs[b + o] > key) ? 1 : 0;
+                        work[b + rank] = key;
+                    }
+                }
+            }
+            __syncthreads();
+            const unsigned long long* __restrict__ srt = work;
+            for (int i = tid; i < M; i += NMS_THREADS) state[i] = 0;
+            __syncthreads();
+            for (;;) {
+                int undecided = 0;
+                for (int i = tid; i < M; i += NMS_THREADS) {
+                    if (state[i] != 0) continue;
+                    const unsigned long long key = srt[i];
+                    const unsigned idx = (unsigned)key;
+                    const int y = idx / w, x = idx - y * w;
+                    const int xc = x / cell, yc = y / cell;
+                    const int x1 = max(xc - 1, 0), x2 = min(xc + 1, gw - 1);
+                    const int y1 = max(yc - 1, 0), y2 = min(yc + 1, gh - 1);
+                    bool rejected = false, blocked = false;
+                    for (int yy = y1; yy <= y2 && !rejected; yy++)
+                        for (int xx = x1; xx <= x2 && !rejected; xx++) {
+                            const int c = yy * gw + xx;
+                            const int e = cstart[c + 1];
+                            for (int j = cstart[c]; j < e; j++) {
+                                const unsigned long long kj = srt[j];
+                                if (kj <= key) break;                 // only stronger candidates matter
+                                const unsigned ij = (unsigned)kj;
+                                const int yj = ij / w, xj = ij - yj * w;
+                                const int dx = x - xj, dy = y - yj;
+                                if ((double)(dx * dx + dy * dy) < md2) {
+                                    const uint8_t sj = state[j];
+                                    if (sj == 1) { rejected = true; break; }
+                                    if (sj == 0) blocked = true;
+                                }
                             }
                         }
-                    }
-                if (rejected) state[i] = 2;
-                else if (!blocked) state[i] = 1;
-                else undecided = 1;
+                    if (rejected) state[i] = 2;
+                    else if (!blocked) state[i] = 1;
+                    else undecided = 1;
+                }
+                if (!__syncthreads_or(undecided)) break;
             }
-            if (!__syncthreads_or(undecided)) break;
+        } else {
+            for (int i = tid; i < M; i += NMS_THREADS) state[i] = 1;
+            __syncthreads();
         }
-    } else {
-        for (int i = tid; i < nc; i += NMS_THREADS) state[i] = 1;
+        // count the accepted
+        if (tid == 0) s_cnt = 0;
         __syncthreads();
+        {
+            int c = 0;
+            for (int i = tid; i < M; i += NMS_THREADS) c += state[i] == 1 ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+        }
+        __syncthreads();
+        n_acc = s_cnt;
+        __syncthreads();
+        if (n_acc >= K || M >= nv) break;
+        M = min(nv, 4 * M);
     }
 
-    // ---- collect accepted keys into `sorted` (unordered) ----
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < nc; i0 += NMS_THREADS) {
-        const int i = i0 + tid;
-        const bool acc = (i < nc) && state[i] == 1;
-        const unsigned ballot = __ballot_sync(0xffffffffu, acc);
-        int base = 0;
-        if ((tid & 31) == 0 && ballot) base = atomicAdd(&s_cnt, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (acc) sorted[base + __popc(ballot & ((1u << (tid & 31)) - 1))] = J.cand[i];
-    }
-    __syncthreads();
-    const int n_acc = s_cnt;
+    // ---- the K strongest accepted keys (all of them if fewer), sorted descending ----
+    const unsigned long long* __restrict__ fin = work;
     int n_sel = n_acc;
-    unsigned long long kth = 0;       // keep keys >= kth
+    unsigned long long kth = 0ull;
     if (n_acc > K) {
-        // radix select of the K-th largest 64-bit key, 8 bits per pass from the top
-        if (tid == 0) { s_prefix = 0; s_remaining = K; }
-        __syncthreads();
-        for (int pass = 0; pass < 8; pass++) {
-            const int shift = 56 - 8 * pass;
-            if (tid < 256) s_hist[tid] = 0;
-            __syncthreads();
-            const unsigned long long prefix = s_prefix;
-            const unsigned long long himask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
-            for (int i = tid; i < n_acc; i += NMS_THREADS) {
-                const unsigned long long k = sorted[i];
-                if ((k & himask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 255)], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int rem = s_remaining, b = 255;
-                for (; b > 0; b--) {
-                    if (s_hist[b] >= rem) break;
-                    rem -= s_hist[b];
-                }
-                s_remaining = rem;
-                s_prefix = prefix | ((unsigned long long)b << shift);
-            }
-            __syncthreads();
-        }
-        kth = s_prefix;
+        kth = block_select_kth(fin, M, K, [&](int i, unsigned long long) { return state[i] == 1; }, s_hist, &s_prefix,
+                               &s_remaining);
         n_sel = K;
     }
-    // ---- gather the selected keys into shared memory, bitonic sort descending ----
     int npow = 1;
     while (npow < n_sel) npow <<= 1;
     for (int i = tid; i < npow; i += NMS_THREADS) s_sel[i] = 0ull;
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    for (int i = tid; i < n_acc; i += NMS_THREADS) {
-        const unsigned long long k = sorted[i];
-        if (k >= kth) {
+    for (int i = tid; i < M; i += NMS_THREADS) {
+        const unsigned long long key = fin[i];
+        if (state[i] == 1 && key >= kth) {
             const int pos = atomicAdd(&s_cnt, 1);
-            if (pos < NMS_MAX_K) s_sel[pos] = k;
+            if (pos < NMS_MAX_K) s_sel[pos] = key;
         }
     }
     __syncthreads();
@@ -459,7 +585,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
         const int y = idx / w, x = idx - y * w;
         J.pts[n_old + r] = make_float2((float)x, (float)y);
     }
-    if (tid == 0) { J.counters[4] = n_sel; J.counters[3] = n_acc; }
+    if (tid == 0) { J.counters[4] = n_sel; J.counters[5] = M; J.counters[6] = n_acc; }
 }
 
 // ids = global_id_count++ in acceptance order; jobs that share an id counter are served in job order
@@ -493,13 +619,13 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
         dim3 grid(max_pts, n_jobs);
         DVFE_LAUNCH(k_gftt_discs, grid, 128, 0, st, d_jobs);
     }
-    {
-        dim3 blk(32, 8), grid((max_w + RESP_TW - 1) / RESP_TW, (max_h + RESP_TH - 1) / RESP_TH, n_jobs);
-        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
-    }
-    {
+    if (h_jobs != nullptr && h_jobs[0].eig_in != nullptr) {     // seam op with an external response map
         dim3 blk(32, 8), grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
-        DVFE_LAUNCH(k_gftt_candidates, grid, blk, 0, st, d_jobs);
+        DVFE_LAUNCH(k_gftt_max_ext, grid, blk, 0, st, d_jobs);
+        DVFE_LAUNCH(k_gftt_candidates_ext, grid, blk, 0, st, d_jobs);
+    } else {
+        dim3 blk(256), grid((max_w + RT_OW - 1) / RT_OW, (max_h + RT_OH - 1) / RT_OH, n_jobs);
+        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
     }
     DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, 0, st, d_jobs);
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
@@ -508,7 +634,7 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
 }
 
 int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st) {
-    dim3 blk(32, 8), grid((w + RESP_TW - 1) / RESP_TW, (h + RESP_TH - 1) / RESP_TH);
+    dim3 blk(256), grid((w + RT_OW - 1) / RT_OW, (h + RT_OH - 1) / RT_OH);
     DVFE_LAUNCH(k_min_eigen_val, grid, blk, 0, st, img, pitch, w, h, eig);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;

@@ -12,7 +12,8 @@ struct PyrImgSet {
 };
 
 // pyramid.cu
-int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st);
+int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
+                          bool level0_in_place = false);
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);
 
 // lk.cu
@@ -31,9 +32,11 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     const float* eig_in;         // nullable: externally supplied response map (seam op)
     unsigned long long* cand;    // candidate keys scratch [cand_cap]
     unsigned long long* cand2;   // second buffer [cand_cap]
+    unsigned long long* cand3;   // third buffer [cand_cap]
     int cand_cap;
     int* cell_count;             // scratch [n_cells + 1]
-    int* counters;               // [8]: 0 n_cand, 1 masked max (ordered int), 2 overflow flag, 3 n_accepted, 4 n_new
+    int* counters;               // [8]: 0 n_precand, 1 masked max (ordered int), 2 overflow flag, 3 n above threshold,
+                                 //      4 n_new, 5 M examined, 6 n_accepted
     uint8_t* state;              // scratch [cand_cap]
     // point set the discs come from and new corners are appended to
     float2* pts;

@@ -7,94 +7,146 @@
 // (the reference rebuilds both pyramids inside each of its 4 LK calls per stereo frame).
 #include "kernels.cuh"
 
-// ---- level 0: copy the u8 image into the padded level and fill the border --------------------
-__global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, int spitch) {
-    const int img = blockIdx.z;
-    const int which = img >= set.per_set;
-    const int idx = which ? img - set.per_set : img;
-    const uint8_t* __restrict__ src = set.src[which] + (size_t)idx * set.src_stride;
-    uint8_t* __restrict__ dst = set.dst[which] + (size_t)idx * set.dst_stride + L.offset;
-
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;      // word index in the padded row
-    const int py = blockIdx.y * blockDim.y + threadIdx.y;      // padded row
-    if (wx * 4 >= L.pitch || py >= L.h + 2 * DVFE_PADY) return;
-    const int y = reflect101(py - DVFE_PADY, L.h);
-    const int x0 = wx * 4 - DVFE_PADX;
-    const uint8_t* row = src + (size_t)y * spitch;
-    uint32_t v;
-    if (x0 >= 0 && x0 + 3 < L.w && ((((uintptr_t)row) + x0) & 3) == 0) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
-    } else {
-        v = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) v |= (uint32_t)__ldg(row + reflect101(x0 + i, L.w)) << (8 * i);
-    }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)py * L.pitch + wx * 4) = v;
+__device__ __forceinline__ void pyr_select(const PyrImgSet& set, int img, const uint8_t*& src, uint8_t*& dst) {
+    const bool second = img >= set.per_set;
+    const int idx = second ? img - set.per_set : img;
+    src = (second ? set.src[1] : set.src[0]) + (size_t)idx * set.src_stride;
+    dst = (second ? set.dst[1] : set.dst[0]) + (size_t)idx * set.dst_stride;
 }
 
-// ---- level l from level l-1 (both padded) ---------------------------------------------------
+// ---- level 0 interior: copy the u8 image into the padded level; one thread = 16 bytes ------------------
+__global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, int spitch) {
+    const uint8_t* src; uint8_t* dst;
+    pyr_select(set, blockIdx.z, src, dst);
+    dst += L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= L.w || y >= L.h) return;
+    const uint8_t* row = src + (size_t)y * spitch + x0;
+    uint8_t* out = dst + (size_t)y * L.pitch + x0;
+    if (x0 + 15 < L.w && (((uintptr_t)row) & 15) == 0) {
+        *reinterpret_cast<uint4*>(out) = __ldg(reinterpret_cast<const uint4*>(row));
+    } else if (x0 + 15 < L.w && (((uintptr_t)row) & 3) == 0) {
+        const unsigned* p = reinterpret_cast<const unsigned*>(row);
+        *reinterpret_cast<uint4*>(out) = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    } else {
+        for (int i = 0; i < 16 && x0 + i < L.w; i++) out[i] = __ldg(row + i);
+    }
+}
+
+// ---- REFLECT_101 border of a level, copied from its own interior; one warp per padded row ------------------
+__global__ void __launch_bounds__(256) k_pyr_border(PyrImgSet set, PyrLevel L) {
+    const uint8_t* src; uint8_t* base;
+    pyr_select(set, blockIdx.z, src, base);
+    uint8_t* lvl = base + L.offset;
+    const uint8_t* __restrict__ in = lvl + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;      // pixel (0,0)
+    const int py = blockIdx.x * blockDim.y + threadIdx.y;
+    if (py >= L.h + 2 * DVFE_PADY) return;
+    const int lane = threadIdx.x;
+    const int y = py - DVFE_PADY;
+    const uint8_t* __restrict__ srow = in + (size_t)reflect101(y, L.h) * L.pitch;
+    unsigned* orow = reinterpret_cast<unsigned*>(lvl + (size_t)py * L.pitch);
+    const int nwords = L.pitch / 4;
+    const int right0 = (DVFE_PADX + L.w) / 4;          // first word that holds a right-border byte
+    const bool band = y < 0 || y >= L.h;
+    // band rows: every word; side rows: the left pad words, then the words from right0 on
+    const int count = band ? nwords : (DVFE_PADX / 4 + nwords - right0);
+    for (int t = lane; t < count; t += 32) {
+        const int wq = band ? t : (t < DVFE_PADX / 4 ? t : right0 + (t - DVFE_PADX / 4));
+        const int x0 = wq * 4 - DVFE_PADX;
+        unsigned v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) v |= (unsigned)srow[reflect101(x0 + i, L.w)] << (8 * i);
+        orow[wq] = v;
+    }
+}
+
+// ---- level l interior from level l-1 (padded, border already filled) -------------------------------------
 __device__ __forceinline__ int pyr_tap5(const uint8_t* __restrict__ p) {
     return (int)p[-2] + 4 * (int)p[-1] + 6 * (int)p[0] + 4 * (int)p[1] + (int)p[2];
 }
 
+// one thread = 8 consecutive outputs of two consecutive rows.  It reads 7 source rows (one 16-byte and two
+// 4-byte aligned loads each) and evaluates the separable 5x5 kernel with dp4a: the horizontal taps (1 4 6 4)
+// times the vertical weight fit int8, the fifth tap is a second dp4a.
 __global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D) {
-    const int img = blockIdx.z;
-    const int which = img >= set.per_set;
-    const int idx = which ? img - set.per_set : img;
-    uint8_t* base = set.dst[which] + (size_t)idx * set.dst_stride;
+    const uint8_t* unused; uint8_t* base;
+    pyr_select(set, blockIdx.z, unused, base);
     const uint8_t* __restrict__ src = base + S.offset + (size_t)DVFE_PADY * S.pitch + DVFE_PADX;   // pixel (0,0)
-    uint8_t* __restrict__ dst = base + D.offset;
+    uint8_t* __restrict__ dst = base + D.offset + (size_t)DVFE_PADY * D.pitch + DVFE_PADX;
 
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = blockIdx.y * blockDim.y + threadIdx.y;
-    if (wx * 4 >= D.pitch || py >= D.h + 2 * DVFE_PADY) return;
-    const int y = reflect101(py - DVFE_PADY, D.h);
-    const int x0 = wx * 4 - DVFE_PADX;
-    uint32_t out = 0;
-    if (x0 >= 0 && x0 + 3 < D.w) {
-        // interior word: 4 outputs share their taps; aligned word loads (2*x0 is a multiple of 8)
-        int acc[4] = {0, 0, 0, 0};
-        const int kw[5] = {1, 4, 6, 4, 1};
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+    if (x0 >= D.w || y0 >= D.h) return;
+    if (x0 + 7 < D.w && y0 + 1 < D.h) {
+        unsigned acc0[8], acc1[8];
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(src + (size_t)(2 * y + r - 2) * S.pitch + 2 * x0 - 4);
-            const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2), w3 = __ldg(rp + 3);
-            // bytes b[-4..11] ; need b[-2..8]
-            int b[11];
-            b[0] = (w0 >> 16) & 255; b[1] = w0 >> 24;
-            b[2] = w1 & 255; b[3] = (w1 >> 8) & 255; b[4] = (w1 >> 16) & 255; b[5] = w1 >> 24;
-            b[6] = w2 & 255; b[7] = (w2 >> 8) & 255; b[8] = (w2 >> 16) & 255; b[9] = w2 >> 24;
-            b[10] = w3 & 255;
+        for (int j = 0; j < 8; j++) { acc0[j] = 128u; acc1[j] = 128u; }
+        // source rows 2*y0-2 .. 2*y0+4 ; output row 0 uses rows 0..4, output row 1 uses rows 2..6
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                acc[j] += kw[r] * (b[2 * j] + 4 * b[2 * j + 1] + 6 * b[2 * j + 2] + 4 * b[2 * j + 3] + b[2 * j + 4]);
+        for (int r = 0; r < 7; r++) {
+            const uint8_t* rp = src + (size_t)(2 * y0 - 2 + r) * S.pitch + 2 * x0;
+            unsigned W[6];
+            W[0] = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp));
+            W[1] = q.x; W[2] = q.y; W[3] = q.z; W[4] = q.w;
+            W[5] = __ldg(reinterpret_cast<const unsigned*>(rp + 16));
+            // vertical weight of this source row for each output row (0 = unused)
+            const int k0 = (r == 0 || r == 4) ? 1 : (r == 1 || r == 3) ? 4 : (r == 2) ? 6 : 0;
+            const int k1 = (r == 2 || r == 6) ? 1 : (r == 3 || r == 5) ? 4 : (r == 4) ? 6 : 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int m = j >> 1;
+                unsigned A, E;     // A: bytes [2j-2, 2j+2) ; E: word holding byte 2j+2
+                unsigned esel;     // weight position of byte 2j+2 inside E
+                if ((j & 1) == 0) { A = __funnelshift_r(W[m], W[m + 1], 16); E = W[m + 1]; esel = 16; }
+                else { A = W[m + 1]; E = W[m + 2]; esel = 0; }
+                if (k0) {
+                    acc0[j] = __dp4a(A, (unsigned)(k0 * 0x04060401), acc0[j]);
+                    acc0[j] = __dp4a(E, (unsigned)k0 << esel, acc0[j]);
+                }
+                if (k1) {
+                    acc1[j] = __dp4a(A, (unsigned)(k1 * 0x04060401), acc1[j]);
+                    acc1[j] = __dp4a(E, (unsigned)k1 << esel, acc1[j]);
+                }
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) out |= (uint32_t)((acc[j] + 128) >> 8) << (8 * j);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int x = reflect101(x0 + i, D.w);
-            const uint8_t* c = src + (size_t)(2 * y) * S.pitch + 2 * x;
+        uint2 o0, o1;
+        o0.x = (acc0[0] >> 8) | ((acc0[1] >> 8) << 8) | ((acc0[2] >> 8) << 16) | ((acc0[3] >> 8) << 24);
+        o0.y = (acc0[4] >> 8) | ((acc0[5] >> 8) << 8) | ((acc0[6] >> 8) << 16) | ((acc0[7] >> 8) << 24);
+        o1.x = (acc1[0] >> 8) | ((acc1[1] >> 8) << 8) | ((acc1[2] >> 8) << 16) | ((acc1[3] >> 8) << 24);
+        o1.y = (acc1[4] >> 8) | ((acc1[5] >> 8) << 8) | ((acc1[6] >> 8) << 16) | ((acc1[7] >> 8) << 24);
+        *reinterpret_cast<uint2*>(dst + (size_t)y0 * D.pitch + x0) = o0;
+        *reinterpret_cast<uint2*>(dst + (size_t)(y0 + 1) * D.pitch + x0) = o1;
+        return;
+    }
+    // the ragged right / bottom edge of the interior (w % 8, odd h)
+    for (int rr = 0; rr < 2 && y0 + rr < D.h; rr++)
+        for (int i = 0; i < 8 && x0 + i < D.w; i++) {
+            const uint8_t* c = src + (size_t)(2 * (y0 + rr)) * S.pitch + 2 * (x0 + i);
             const int s = pyr_tap5(c - 2 * S.pitch) + 4 * pyr_tap5(c - S.pitch) + 6 * pyr_tap5(c) +
                           4 * pyr_tap5(c + S.pitch) + pyr_tap5(c + 2 * S.pitch);
-            out |= (uint32_t)((s + 128) >> 8) << (8 * i);
+            dst[(size_t)(y0 + rr) * D.pitch + x0 + i] = (uint8_t)((s + 128) >> 8);
         }
-    }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)py * D.pitch + wx * 4) = out;
 }
 
-int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st) {
+// level0_in_place: level 0's interior has already been written (H2D straight into the padded layout)
+int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
+                          bool level0_in_place) {
     const dim3 blk(32, 8);
-    {
+    if (!level0_in_place) {
         const PyrLevel& L = desc.lv[0];
-        dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * DVFE_PADY + 7) / 8, n_img);
+        dim3 grid(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, n_img);
         DVFE_LAUNCH(k_pyr_level0, grid, blk, 0, st, set, L, spitch);
     }
-    for (int l = 1; l < desc.n_levels; l++) {
+    for (int l = 0; l < desc.n_levels; l++) {
         const PyrLevel& D = desc.lv[l];
-        dim3 grid((D.pitch / 4 + 31) / 32, (D.h + 2 * DVFE_PADY + 7) / 8, n_img);
-        DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D);
+        if (l > 0) {
+            dim3 grid(((D.w + 7) / 8 + 31) / 32, ((D.h + 1) / 2 + 7) / 8, n_img);
+            DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D);
+        }
+        dim3 bgrid((D.h + 2 * DVFE_PADY + 7) / 8, 1, n_img);
+        DVFE_LAUNCH(k_pyr_border, bgrid, blk, 0, st, set, D);
     }
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;

@@ -76,6 +76,7 @@ int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist
     DVFE_CHECK(dmalloc(&sc->eig, (size_t)n_jobs * w * h));
     DVFE_CHECK(dmalloc(&sc->cand, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->cand2, (size_t)n_jobs * sc->cand_cap));
+    DVFE_CHECK(dmalloc(&sc->cand3, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->state, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->cell_count, (size_t)n_jobs * 2 * (sc->n_cells + 1)));
     DVFE_CHECK(dmalloc(&sc->counters, (size_t)n_jobs * 8));
@@ -83,7 +84,7 @@ int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist
 }
 
 void free_gftt_scratch(GfttScratch* sc) {
-    cudaFree(sc->mask); cudaFree(sc->eig); cudaFree(sc->cand); cudaFree(sc->cand2); cudaFree(sc->state);
+    cudaFree(sc->mask); cudaFree(sc->eig); cudaFree(sc->cand); cudaFree(sc->cand2); cudaFree(sc->cand3); cudaFree(sc->state);
     cudaFree(sc->cell_count); cudaFree(sc->counters);
     memset(sc, 0, sizeof(*sc));
 }
@@ -94,6 +95,7 @@ void gftt_job_bind_scratch(GfttJob* J, const GfttScratch& sc, int j) {
     J->eig = sc.eig + (size_t)j * sc.w * sc.h;
     J->cand = sc.cand + (size_t)j * sc.cand_cap;
     J->cand2 = sc.cand2 + (size_t)j * sc.cand_cap;
+    J->cand3 = sc.cand3 + (size_t)j * sc.cand_cap;
     J->cand_cap = sc.cand_cap;
     J->state = sc.state + (size_t)j * sc.cand_cap;
     J->cell_count = sc.cell_count + (size_t)j * 2 * (sc.n_cells + 1);
@@ -148,7 +150,6 @@ int dvfe_tracker::init() {
     for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[i]));
     const size_t P = (size_t)W * H;
     for (int s = 0; s < 3; s++) DVFE_CHECK(dmalloc(&pyr[s], (size_t)B * desc.bytes));
-    DVFE_CHECK(dmalloc(&d_in, 2 * B * P));
     DVFE_CHECK(alloc_point_sets(&bg, B, cap));
     DVFE_CHECK(dmalloc(&d_next_id, (size_t)B));
     {
@@ -231,7 +232,6 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     cudaSetDevice(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
     for (int s = 0; s < 3; s++) cudaFree(t->pyr[s]);
-    cudaFree(t->d_in);
     free_point_sets(&t->bg);
     cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFreeHost(t->h_dt);
     cudaFree(t->d_obs); cudaFree(t->d_nobs); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_nobs);
@@ -250,9 +250,9 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
 
 // The frame step with the images already on the device (dense or pitched, strided per stream).
 int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
-                              const double* time0, bool semantic) {
+                              const double* time0, bool semantic, bool level0_in_place, bool has_right) {
     DVFE_CUDA(cudaSetDevice(cfg.device));
-    const bool stereo_now = cfg.stereo && d_right != nullptr;
+    const bool stereo_now = cfg.stereo && (d_right != nullptr || (level0_in_place && has_right));
     const int par = cur;
     for (int s = 0; s < B; s++) h_dt[s] = time0[s] - prev_time[s];       // cur_time - prev_time
     DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt, B * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -262,7 +262,7 @@ int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, siz
     set.src[0] = d_left; set.src[1] = d_right;
     set.dst[0] = pyr[par]; set.dst[1] = pyr[2];
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
-    DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st));
+    DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
     if (frames > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
         DVFE_CHECK(launch_lk(d_groups[par][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
@@ -298,14 +298,27 @@ int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, siz
     return DVFE_OK;
 }
 
-int dvfe_tracker::upload(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
-    const size_t P = (size_t)W * H;
-    for (int s = 0; s < B; s++) {
-        DVFE_CUDA(cudaMemcpy2DAsync(d_in + s * P, W, left + s * stream_stride, pitch, W, (size_t)H,
-                                    cudaMemcpyHostToDevice, st));
-        if (right)
-            DVFE_CUDA(cudaMemcpy2DAsync(d_in + (B + s) * P, W, right + s * stream_stride, pitch, W, (size_t)H,
-                                        cudaMemcpyHostToDevice, st));
+// Host images -> level 0 of the pyramids, one pitched 3-D copy per camera (no staging buffer, no copy kernel).
+int dvfe_tracker::upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
+    const PyrLevel& L0 = desc.lv[0];
+    const size_t inner = L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+    for (int cam = 0; cam < 2; cam++) {
+        const uint8_t* src = cam ? right : left;
+        if (!src) continue;
+        uint8_t* dst = (cam ? pyr[2] : pyr[cur]) + inner;
+        if (stream_stride % (size_t)pitch == 0) {
+            cudaMemcpy3DParms p;
+            memset(&p, 0, sizeof(p));
+            p.srcPtr = make_cudaPitchedPtr((void*)src, (size_t)pitch, (size_t)W, stream_stride / (size_t)pitch);
+            p.dstPtr = make_cudaPitchedPtr((void*)dst, (size_t)L0.pitch, (size_t)W, desc.bytes / (size_t)L0.pitch);
+            p.extent = make_cudaExtent((size_t)W, (size_t)H, (size_t)B);
+            p.kind = cudaMemcpyHostToDevice;
+            DVFE_CUDA(cudaMemcpy3DAsync(&p, st));
+        } else {
+            for (int s = 0; s < B; s++)
+                DVFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)s * desc.bytes, L0.pitch, src + s * stream_stride, pitch, W,
+                                            (size_t)H, cudaMemcpyHostToDevice, st));
+        }
     }
     return DVFE_OK;
 }
@@ -322,15 +335,8 @@ extern "C" int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint
                                 int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
-    const size_t P = (size_t)t->W * t->H;
-    // one contiguous copy when the host layout is dense
-    if (pitch == t->W && stream_stride == P) {
-        DVFE_CUDA(cudaMemcpyAsync(t->d_in, left, t->B * P, cudaMemcpyHostToDevice, t->st));
-        if (right) DVFE_CUDA(cudaMemcpyAsync(t->d_in + t->B * P, right, t->B * P, cudaMemcpyHostToDevice, t->st));
-    } else {
-        DVFE_CHECK(t->upload(left, right, stream_stride, pitch));
-    }
-    return t->step_device(t->d_in, right ? t->d_in + t->B * P : nullptr, P, t->W, time0, false);
+    DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
+    return t->step_device(nullptr, nullptr, 0, 0, time0, false, true, right != nullptr);
 }
 
 extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
@@ -346,7 +352,7 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     if (!exist_inst) { dvfe_set_error("track_semantic_image: exist_inst is null"); return DVFE_ERR_INVALID; }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     const size_t P = (size_t)t->W * t->H;
-    DVFE_CHECK(t->upload(left, right, stream_stride, pitch));
+    DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
     bool any = false;
     for (int s = 0; s < t->B; s++) {
         t->h_exist[s] = exist_inst[s] ? 1 : 0;
@@ -363,7 +369,7 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
     DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
                                  t->d_exist, t->st));
-    return t->step_device(t->d_in, right ? t->d_in + t->B * P : nullptr, P, t->W, time0, true);
+    return t->step_device(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr);
 }
 
 extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out) {

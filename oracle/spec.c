@@ -317,21 +317,31 @@ void spec_min_eigen_val(const uint8_t* img, int w, int h, int stride, float* out
         }
     }
     free(dxr); free(smr);
-    for (int y = 0; y < h; y++) {
+    /* cv::boxFilter(cov, cov, CV_32F, Size(3,3), normalize=false, BORDER_REFLECT_101): RowSum<float,double>
+     * (horizontal 3-sum, left to right) then ColumnSum<double,float> (vertical 3-sum, top to bottom) */
+    double* H = (double*)malloc(sizeof(double) * n * 3);
+    for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             double sxx = 0, sxy = 0, syy = 0;
-            for (int j = -1; j <= 1; j++) {
-                int yy = reflect101(y + j, h);
-                for (int i = -1; i <= 1; i++) {
-                    int xx = reflect101(x + i, w);
-                    float dx = Dx[(size_t)yy * w + xx], dy = Dy[(size_t)yy * w + xx];
-                    sxx += (double)(dx * dx); sxy += (double)(dx * dy); syy += (double)(dy * dy);
-                }
+            for (int i = -1; i <= 1; i++) {
+                int xx = reflect101(x + i, w);
+                float dx = Dx[(size_t)y * w + xx], dy = Dy[(size_t)y * w + xx];
+                sxx += (double)(dx * dx); sxy += (double)(dx * dy); syy += (double)(dy * dy);
             }
-            float a = (float)sxx * 0.5f, b = (float)sxy, c = (float)syy * 0.5f;
+            H[((size_t)y * w + x) * 3 + 0] = sxx; H[((size_t)y * w + x) * 3 + 1] = sxy; H[((size_t)y * w + x) * 3 + 2] = syy;
+        }
+    for (int y = 0; y < h; y++) {
+        int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+        for (int x = 0; x < w; x++) {
+            const double* h0 = H + ((size_t)ym * w + x) * 3;
+            const double* h1 = H + ((size_t)y * w + x) * 3;
+            const double* h2 = H + ((size_t)yp * w + x) * 3;
+            float a = (float)((h0[0] + h1[0]) + h2[0]) * 0.5f, b = (float)((h0[1] + h1[1]) + h2[1]);
+            float c = (float)((h0[2] + h1[2]) + h2[2]) * 0.5f;
             out[(size_t)y * w + x] = (a + c) - sqrtf((a - c) * (a - c) + b * b);
         }
     }
+    free(H);
     free(Dx); free(Dy);
 }
 
