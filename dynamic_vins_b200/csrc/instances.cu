@@ -1,18 +1,373 @@
-// Per-instance tracking (InstsFeatManager::InstsTrack / Output) — see instances section of DESIGN.md.
+// Per-instance tracking — replaces InstsFeatManager::InstsTrack / ManageInstances / Output / AddViodeInstances
+// (dynamic_vins/src/front_end/dynamic_tracker.cpp:348-493, 499-514, 521-577, 585-605) and the caller's per-frame
+// instance reset (dynamic_vins/src/system/main.cpp:198-202), minus the DeepSORT / PCL / 3-D box branches.
+//
+// Host side: the instance table (track id -> slot, lost_num, visibility, boxes) — the same bookkeeping the
+// reference does on the host.  Device side: every visible instance of the frame is one job of each batched
+// launch (ROI crop, zero-padded ROI pyramids, LK on the previous-box crop -> current-box crop in ROI-local
+// coordinates, mask erosion, Shi-Tomasi on the ROI, offset undistortion, full-image left->right LK).
+//
+// Order of feature-id assignment: the background step of the frame (dvfe_track_semantic_image) runs first, then
+// the instances in ascending instance id (the reference races the two threads on one counter and iterates an
+// unordered_map; see oracle/cv_front_end.py header).
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <vector>
+
 #include "kernels.cuh"
 #include "state.cuh"
 #include "tracker.h"
 
-void dvfe_tracker::free_instances() {}
+#define DVFE_CHECK(call)                 \
+    do {                                 \
+        int rc__ = (call);               \
+        if (rc__ != DVFE_OK) return rc__; \
+    } while (0)
 
-extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* insts, int n_insts, double time0) {
-    (void)t; (void)stream; (void)insts; (void)n_insts; (void)time0;
-    dvfe_set_error("dvfe_insts_track: not built yet");
-    return DVFE_ERR_INVALID;
+namespace {
+struct InstHost {
+    uint32_t track_id = 0;
+    int slot = -1;
+    int lost_num = 0;
+    bool visible = false;          // is_curr_visible
+    bool has_box = false;          // box2d != nullptr
+    int x = 0, y = 0, w = 0, h = 0;      // box2d->rect of the current frame
+    int prev_w = 0, prev_h = 0;    // size of roi->prev_roi_gray (0 = empty)
+    int cur_buf = 0;               // which of the two ROI buffers holds roi_gray
+    int roi_w = 0, roi_h = 0;      // size of roi->roi_gray
+};
+
+struct InstStream {
+    std::map<uint32_t, InstHost> insts;      // ascending instance id = the deterministic ExecInst order
+    std::vector<int> free_slots;
+    double last_time = 0.0;
+    std::vector<dvfe_inst_obs> out;          // Output() of the last call
+};
+
+template <typename T>
+int dmalloc(T** p, size_t count) {
+    DVFE_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    DVFE_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+    return DVFE_OK;
 }
+
+// pinned host staging + device copy of a small per-call descriptor array
+template <typename T>
+struct Staged {
+    T* h = nullptr;
+    T* d = nullptr;
+    int cap = 0;
+    int alloc(int n) {
+        cap = n;
+        DVFE_CUDA(cudaMallocHost((void**)&h, sizeof(T) * n));
+        DVFE_CUDA(cudaMalloc((void**)&d, sizeof(T) * n));
+        return DVFE_OK;
+    }
+    int push(int n, cudaStream_t st) {
+        if (n > 0) DVFE_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+        return DVFE_OK;
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+    }
+};
+}  // namespace
+
+struct InstanceState {
+    int MI = 0, cap = 0;                 // slots per stream, points per slot (max_dynamic_cnt)
+    size_t P = 0;                        // W*H: capacity of one ROI buffer
+    PyrDesc full{};                      // capacity of one ROI pyramid
+    std::vector<InstStream> streams;
+    PointSetArrays pts{};                // B*MI sets
+    uint8_t *roi_gray = nullptr;         // [B*MI][2][P]
+    uint8_t *roi_mask = nullptr, *roi_mask_tmp = nullptr, *roi_mask_er = nullptr;   // [B*MI][P]
+    uint8_t *pyr_prev = nullptr, *pyr_cur = nullptr;                                 // [B*MI][full.bytes]
+    GfttScratch gsc{};                   // B*MI jobs at full image size
+    dvfe_inst_obs* d_out = nullptr;      // [B*MI*cap]
+    dvfe_inst_obs* h_out = nullptr;      // pinned
+    int* h_n = nullptr;                  // pinned [B*MI]
+    // per-call descriptors (MI entries; one stream per call)
+    Staged<CropJob> crop;
+    Staged<PyrJob> pyr;                  // 2*MI
+    Staged<LkGroup> lk_t, lk_s;
+    Staged<ErodeJob> erode;
+    Staged<GfttJob> gftt;
+    Staged<uint8_t> act_track, act_vis, clear_flags;    // indexed by slot within the stream
+    Staged<double> dt;
+    Staged<float2> offs;
+    Staged<uint32_t> inst_id;
+};
+
+int dvfe_tracker::init_instances() {
+    if (cfg.max_instances <= 0) return DVFE_OK;
+    if (cfg.max_dynamic_cnt < 1 || cfg.max_dynamic_cnt > 2048 || cfg.min_dynamic_dist < 1) {
+        dvfe_set_error("dvfe_create: invalid instance config (max_dynamic_cnt=%d min_dynamic_dist=%d)", cfg.max_dynamic_cnt,
+                       cfg.min_dynamic_dist);
+        return DVFE_ERR_CONFIG;
+    }
+    inst = new InstanceState();
+    InstanceState& I = *inst;
+    I.MI = cfg.max_instances; I.cap = cfg.max_dynamic_cnt; I.P = (size_t)W * H;
+    I.full = make_pyr_desc(W, H, cfg.lk_max_level);
+    const size_t NS = (size_t)B * I.MI;
+    I.streams.resize(B);
+    for (auto& s : I.streams)
+        for (int k = I.MI - 1; k >= 0; k--) s.free_slots.push_back(k);
+    DVFE_CHECK(alloc_point_sets(&I.pts, (int)NS, I.cap));
+    DVFE_CHECK(dmalloc(&I.roi_gray, NS * 2 * I.P));
+    DVFE_CHECK(dmalloc(&I.roi_mask, NS * I.P));
+    DVFE_CHECK(dmalloc(&I.roi_mask_tmp, NS * I.P));
+    DVFE_CHECK(dmalloc(&I.roi_mask_er, NS * I.P));
+    DVFE_CHECK(dmalloc(&I.pyr_prev, NS * I.full.bytes));
+    DVFE_CHECK(dmalloc(&I.pyr_cur, NS * I.full.bytes));
+    DVFE_CHECK(alloc_gftt_scratch(&I.gsc, (int)NS, W, H, (float)cfg.min_dynamic_dist));
+    DVFE_CHECK(dmalloc(&I.d_out, NS * I.cap));
+    DVFE_CUDA(cudaMallocHost((void**)&I.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
+    DVFE_CUDA(cudaMallocHost((void**)&I.h_n, NS * sizeof(int)));
+    DVFE_CHECK(I.crop.alloc(I.MI));
+    DVFE_CHECK(I.pyr.alloc(2 * I.MI));
+    DVFE_CHECK(I.lk_t.alloc(I.MI));
+    DVFE_CHECK(I.lk_s.alloc(I.MI));
+    DVFE_CHECK(I.erode.alloc(I.MI));
+    DVFE_CHECK(I.gftt.alloc(I.MI));
+    DVFE_CHECK(I.act_track.alloc(I.MI));
+    DVFE_CHECK(I.act_vis.alloc(I.MI));
+    DVFE_CHECK(I.clear_flags.alloc(I.MI));
+    DVFE_CHECK(I.dt.alloc(I.MI));
+    DVFE_CHECK(I.offs.alloc(I.MI));
+    DVFE_CHECK(I.inst_id.alloc(I.MI));
+    return DVFE_OK;
+}
+
+void dvfe_tracker::free_instances() {
+    if (!inst) return;
+    InstanceState& I = *inst;
+    free_point_sets(&I.pts);
+    cudaFree(I.roi_gray); cudaFree(I.roi_mask); cudaFree(I.roi_mask_tmp); cudaFree(I.roi_mask_er);
+    cudaFree(I.pyr_prev); cudaFree(I.pyr_cur);
+    free_gftt_scratch(&I.gsc);
+    cudaFree(I.d_out); cudaFreeHost(I.h_out); cudaFreeHost(I.h_n);
+    I.crop.release(); I.pyr.release(); I.lk_t.release(); I.lk_s.release(); I.erode.release(); I.gftt.release();
+    I.act_track.release(); I.act_vis.release(); I.clear_flags.release(); I.dt.release(); I.offs.release();
+    I.inst_id.release();
+    delete inst;
+    inst = nullptr;
+}
+
+// InstsFeatManager::ManageInstances (front_end/dynamic_tracker.cpp:499-514)
+static void manage_instances(InstStream& S) {
+    for (auto it = S.insts.begin(); it != S.insts.end();) {
+        InstHost& in = it->second;
+        if (in.lost_num == 0 && !in.has_box) in.lost_num++;
+        if (in.lost_num > 0) {
+            in.lost_num++;
+            if (in.lost_num > 3) {
+                S.free_slots.push_back(in.slot);
+                it = S.insts.erase(it);
+                continue;
+            }
+        }
+        ++it;
+    }
+}
+
+extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n_boxes, double time0) {
+    if (!t || !t->inst || stream < 0 || stream >= t->B || n_boxes < 0 || (n_boxes > 0 && !boxes)) {
+        dvfe_set_error("insts_track: bad argument (max_instances must be > 0 at create)");
+        return DVFE_ERR_INVALID;
+    }
+    if (t->frames == 0) {
+        dvfe_set_error("insts_track: no frame has been uploaded yet (call dvfe_track_semantic_image first)");
+        return DVFE_ERR_INVALID;
+    }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    InstanceState& I = *t->inst;
+    InstStream& S = I.streams[stream];
+    cudaStream_t st = t->st;
+    const int W = t->W, H = t->H, MI = I.MI, cap = I.cap;
+    const size_t P = I.P;
+    const size_t base_set = (size_t)stream * MI;
+    // the frame uploaded by the last background step: left = pyr[1 - cur], right = pyr[2]
+    const PyrLevel& L0 = t->desc.lv[0];
+    const uint8_t* left_pyr = t->pyr[1 - t->cur] + (size_t)stream * t->desc.bytes;
+    const uint8_t* right_pyr = t->pyr[2] + (size_t)stream * t->desc.bytes;
+    const uint8_t* left_px = left_pyr + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+    const bool stereo_now = t->cfg.stereo && t->last_has_right;
+
+    // ---- caller's per-frame reset (system/main.cpp:198-202) + AddViodeInstances (dynamic_tracker.cpp:585-605) ----
+    for (auto& kv : S.insts) { kv.second.visible = false; kv.second.has_box = false; }
+    for (int b = 0; b < n_boxes; b++) {
+        const dvfe_inst_in& bx = boxes[b];
+        if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
+            bx.mask_pitch < bx.w) {
+            dvfe_set_error("insts_track: box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask", b, bx.x, bx.y,
+                           bx.w, bx.h, W, H);
+            return DVFE_ERR_INVALID;
+        }
+        auto it = S.insts.find(bx.track_id);
+        if (it == S.insts.end()) {
+            if (S.free_slots.empty()) {
+                dvfe_set_error("insts_track: more than max_instances=%d live instances in stream %d", MI, stream);
+                return DVFE_ERR_CAPACITY;
+            }
+            InstHost in;
+            in.track_id = bx.track_id;
+            in.slot = S.free_slots.back();
+            S.free_slots.pop_back();
+            const int zero = 0;
+            DVFE_CUDA(cudaMemcpyAsync(I.pts.n + base_set + in.slot, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+            it = S.insts.emplace(bx.track_id, in).first;
+        }
+        InstHost& in = it->second;
+        in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
+        in.visible = true; in.has_box = true;
+        // inst.roi->mask_cv = det_box->roi->mask_cv
+        DVFE_CUDA(cudaMemcpy2DAsync(I.roi_mask + (base_set + in.slot) * P, bx.w, bx.mask, bx.mask_pitch, bx.w, bx.h,
+                                    cudaMemcpyHostToDevice, st));
+    }
+    // ---- lost_num bookkeeping (:355-362) ----
+    for (auto& kv : S.insts) {
+        if (!kv.second.visible) kv.second.lost_num++;
+        else kv.second.lost_num = 0;
+    }
+    const bool exist_inst = n_boxes > 0;
+    S.out.clear();
+
+    if (exist_inst) {
+        // jobs in ascending instance id; every job is a visible instance (lost_num == 0)
+        std::vector<InstHost*> vis;
+        for (auto& kv : S.insts)
+            if (kv.second.lost_num == 0) vis.push_back(&kv.second);
+        const int nv = (int)vis.size();
+        memset(I.act_track.h, 0, MI); memset(I.act_vis.h, 0, MI);
+        int n_track = 0, max_rw = 1, max_rh = 1, max_pw = 1, max_ph = 1, max_lv = 1;
+        for (int j = 0; j < nv; j++) {
+            InstHost& in = *vis[j];
+            const size_t set = base_set + in.slot;
+            // roi_gray = gray0(rect): crop into the buffer that does not hold prev_roi_gray
+            in.cur_buf = in.prev_w > 0 ? 1 - in.cur_buf : in.cur_buf;
+            in.roi_w = in.w; in.roi_h = in.h;
+            CropJob& c = I.crop.h[j];
+            c.src = left_px; c.spitch = L0.pitch; c.x = in.x; c.y = in.y; c.w = in.w; c.h = in.h;
+            c.dst = I.roi_gray + (set * 2 + in.cur_buf) * P;
+            max_rw = std::max(max_rw, in.w); max_rh = std::max(max_rh, in.h);
+            I.act_vis.h[in.slot] = 1;
+            I.dt.h[in.slot] = time0 - S.last_time;                      // curr_time - last_time
+            I.offs.h[in.slot] = make_float2((float)in.x, (float)in.y);    // box2d->rect.tl()
+            I.inst_id.h[in.slot] = in.track_id;
+            if (in.prev_w > 0) {
+                // InstanceImagePadding: both crops zero-padded to (max rows, max cols)
+                const int pw = std::max(in.prev_w, in.w), ph = std::max(in.prev_h, in.h);
+                const PyrDesc d = make_pyr_desc(pw, ph, t->cfg.lk_max_level);
+                PyrJob& a = I.pyr.h[2 * n_track];
+                PyrJob& b = I.pyr.h[2 * n_track + 1];
+                a.src = I.roi_gray + (set * 2 + (1 - in.cur_buf)) * P; a.sw = in.prev_w; a.sh = in.prev_h; a.spitch = in.prev_w;
+                a.dst = I.pyr_prev + set * I.full.bytes; a.desc = d;
+                b.src = c.dst; b.sw = in.w; b.sh = in.h; b.spitch = in.w;
+                b.dst = I.pyr_cur + set * I.full.bytes; b.desc = d;
+                LkGroup& G = I.lk_t.h[n_track];
+                memset(&G, 0, sizeof(G));
+                G.pyrA = a.dst; G.pyrB = b.dst; G.desc = d;
+                G.ptsA = I.pts.pts + set * cap; G.ptsB = I.pts.lk_out + set * cap; G.status = I.pts.status + set * cap;
+                G.n = I.pts.n + set;
+                I.act_track.h[in.slot] = 1;
+                max_pw = std::max(max_pw, pw); max_ph = std::max(max_ph, ph); max_lv = std::max(max_lv, d.n_levels);
+                n_track++;
+            }
+            // detection job (:418-446)
+            ErodeJob& e = I.erode.h[j];
+            e.src = I.roi_mask + set * P; e.tmp = I.roi_mask_tmp + set * P; e.dst = I.roi_mask_er + set * P;
+            e.w = in.w; e.h = in.h; e.k = 5;
+            GfttJob& J = I.gftt.h[j];
+            memset(&J, 0, sizeof(J));
+            J.img = c.dst; J.img_pitch = in.w; J.w = in.w; J.h = in.h;
+            J.region_mask = e.dst; J.region_pitch = in.w;
+            gftt_job_bind_scratch(&J, I.gsc, (int)set);
+            J.pts = I.pts.pts + set * cap; J.ids = I.pts.ids + set * cap; J.track_cnt = I.pts.track_cnt + set * cap;
+            J.n = I.pts.n + set; J.next_id = t->d_next_id + stream;
+            J.max_cnt = t->cfg.max_dynamic_cnt; J.min_needed = 1;
+            J.disc_radius = t->cfg.min_dynamic_dist; J.min_dist = (float)t->cfg.min_dynamic_dist; J.quality = 0.01;
+            // stereo job: TrackRightByPad — full images, points offset by rect.tl()
+            LkGroup& R = I.lk_s.h[j];
+            memset(&R, 0, sizeof(R));
+            R.pyrA = left_pyr; R.pyrB = right_pyr; R.desc = t->desc;
+            R.ptsA = I.pts.pts + set * cap; R.ptsB = I.pts.rpts + set * cap; R.status = I.pts.rstatus + set * cap;
+            R.n = I.pts.n + set; R.offx = (float)in.x; R.offy = (float)in.y;
+        }
+        DVFE_CHECK(I.crop.push(nv, st)); DVFE_CHECK(I.pyr.push(2 * n_track, st)); DVFE_CHECK(I.lk_t.push(n_track, st));
+        DVFE_CHECK(I.lk_s.push(nv, st)); DVFE_CHECK(I.erode.push(nv, st)); DVFE_CHECK(I.gftt.push(nv, st));
+        DVFE_CHECK(I.act_track.push(MI, st)); DVFE_CHECK(I.act_vis.push(MI, st)); DVFE_CHECK(I.dt.push(MI, st));
+        DVFE_CHECK(I.offs.push(MI, st)); DVFE_CHECK(I.inst_id.push(MI, st));
+
+        // per-stream views of the point sets (MI sets)
+        PointSetArrays V = I.pts;
+        const size_t o = base_set * cap;
+        V.pts += o; V.lk_out += o; V.un += o; V.vel += o; V.ids += o; V.track_cnt += o; V.status += o; V.rpts += o;
+        V.rstatus += o; V.rprev_un += o; V.rprev_valid += o; V.n += base_set;
+
+        DVFE_CHECK(launch_crop_jobs(I.crop.d, nv, max_rw, max_rh, st));
+        // inst.TrackLeft(roi_gray_padded, prev_roi_gray_padded): previous-box crop -> current-box crop (:381-413)
+        DVFE_CHECK(launch_build_pyramids_jobs(I.pyr.d, 2 * n_track, max_pw, max_ph, max_lv, st));
+        DVFE_CHECK(launch_lk(I.lk_t.d, n_track, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
+        DVFE_CHECK(launch_compact(V, MI, cap, st, I.act_track.d));
+        // ErodeMask(roi mask, 5) + discs(min_dynamic_dist) + goodFeaturesToTrack on the ROI + ids (:418-446)
+        DVFE_CHECK(launch_erode_jobs(I.erode.d, nv, max_rw, max_rh, st));
+        DVFE_CHECK(launch_gftt(I.gftt.d, nullptr, nv, max_rw, max_rh, cap, st));
+        // UndistortedPointsWithAddOffset(cam0) + PtsVelocity(curr_time - last_time) (:448-457)
+        DVFE_CHECK(launch_left_post(V, MI, cap, t->cam0, I.dt.d, I.offs.d, st, I.act_vis.d));
+        // TrackRightByPad + RightUndistortedPts + RightPtsVelocity (:462-471), then the Output() records
+        if (stereo_now) DVFE_CHECK(launch_lk(I.lk_s.d, nv, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
+        DVFE_CHECK(launch_inst_post_pack(V, MI, cap, t->cam1, I.dt.d, I.act_vis.d, stereo_now ? 1 : 0, I.inst_id.d,
+                                         I.d_out + o, st));
+        DVFE_CUDA(cudaMemcpyAsync(I.h_n + base_set, I.pts.n + base_set, MI * sizeof(int), cudaMemcpyDeviceToHost, st));
+        DVFE_CUDA(cudaMemcpyAsync(I.h_out + o, I.d_out + o, (size_t)MI * cap * sizeof(dvfe_inst_obs), cudaMemcpyDeviceToHost,
+                                  st));
+        DVFE_CUDA(cudaStreamSynchronize(st));
+
+        manage_instances(S);                                                      // :474
+        // PostProcess for every instance that is still live and not lost (:479-481): prev_roi_gray = roi_gray
+        for (auto& kv : S.insts) {
+            InstHost& in = kv.second;
+            if (in.lost_num > 0) continue;
+            in.prev_w = in.roi_w; in.prev_h = in.roi_h;
+        }
+        // Output() (:521-577): lost_num == 0 && is_curr_visible, ascending instance id, ascending feature id
+        for (auto& kv : S.insts) {
+            const InstHost& in = kv.second;
+            if (in.lost_num > 0 || !in.visible) continue;
+            const size_t set = base_set + in.slot;
+            const int n = I.h_n[set];
+            S.out.insert(S.out.end(), I.h_out + set * cap, I.h_out + set * cap + n);
+        }
+    } else {
+        manage_instances(S);
+        // ClearState (:41-58) for the instances ExecInst still visits (lost_num == 0)
+        memset(I.clear_flags.h, 0, MI);
+        bool any = false;
+        for (auto& kv : S.insts)
+            if (kv.second.lost_num == 0) { I.clear_flags.h[kv.second.slot] = 1; any = true; }
+        if (any) {
+            DVFE_CHECK(I.clear_flags.push(MI, st));
+            DVFE_CHECK(launch_clear_sets(I.pts.n + base_set, I.clear_flags.d, MI, st));
+            DVFE_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    S.last_time = time0;
+    return DVFE_OK;
+}
+
 extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out) {
-    (void)t; (void)stream; (void)out; (void)cap;
-    if (n_out) *n_out = 0;
-    dvfe_set_error("dvfe_insts_output: not built yet");
-    return DVFE_ERR_INVALID;
+    if (!t || !t->inst || stream < 0 || stream >= t->B || !n_out) {
+        dvfe_set_error("insts_output: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    const std::vector<dvfe_inst_obs>& v = t->inst->streams[stream].out;
+    *n_out = (int)v.size();
+    if ((int)v.size() > cap) { dvfe_set_error("insts_output: %d records, capacity %d", (int)v.size(), cap); return DVFE_ERR_CAPACITY; }
+    if (!v.empty() && out) memcpy(out, v.data(), v.size() * sizeof(dvfe_inst_obs));
+    return DVFE_OK;
 }

@@ -11,9 +11,31 @@ struct PyrImgSet {
     int per_set;
 };
 
+// job-based variants (per-instance ROIs have individual sizes)
+struct PyrJob {
+    const uint8_t* src;      // dense source image
+    int sw, sh, spitch;      // its size; zero-extended to desc.lv[0]
+    uint8_t* dst;            // pyramid allocation
+    PyrDesc desc;
+};
+struct CropJob {
+    const uint8_t* src;      // pixel (0,0) of the pitched source image
+    int spitch;
+    int x, y, w, h;
+    uint8_t* dst;            // dense w x h
+};
+struct ErodeJob {
+    const uint8_t* src;      // dense w x h
+    uint8_t* tmp;
+    uint8_t* dst;
+    int w, h, k;
+};
+
 // pyramid.cu
 int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
                           bool level0_in_place = false);
+int launch_build_pyramids_jobs(const PyrJob* d_jobs, int n_jobs, int max_w, int max_h, int max_levels, cudaStream_t st);
+int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st);
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);
 
 // lk.cu
@@ -28,7 +50,7 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     int region_pitch;
     uint8_t* mask;               // detection mask scratch (w x h, pitch mask_pitch): region minus discs
     int mask_pitch;
-    float* eig;                  // response map scratch (w x h, dense)
+    float* eig;                  // unused by the fused path (kept for layout stability)
     const float* eig_in;         // nullable: externally supplied response map (seam op)
     unsigned long long* cand;    // candidate keys scratch [cand_cap]
     unsigned long long* cand2;   // second buffer [cand_cap]
@@ -60,6 +82,8 @@ int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, 
 // morph.cu
 int launch_erode_rect(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, uint8_t* tmp, int w, int h, int k,
                       int n_img, size_t img_stride, const int* enable, cudaStream_t st);
+
+int launch_erode_jobs(const ErodeJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st);
 
 // points.cu
 struct CamParams {

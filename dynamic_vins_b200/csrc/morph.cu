@@ -47,3 +47,39 @@ int launch_erode_rect(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, 
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }
+
+// job-based variant: one image per job, individual sizes (instance ROI masks)
+__global__ void __launch_bounds__(256) k_erode_h_jobs(const ErodeJob* __restrict__ jobs) {
+    const ErodeJob& J = jobs[blockIdx.z];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= J.w || y >= J.h) return;
+    const uint8_t* row = J.src + (size_t)y * J.w;
+    const int a = J.k / 2;
+    const int x0 = max(x - a, 0), x1 = min(x - a + J.k - 1, J.w - 1);
+    int m = 255;
+    for (int i = x0; i <= x1; i++) m = min(m, (int)row[i]);
+    J.tmp[(size_t)y * J.w + x] = (uint8_t)m;
+}
+
+__global__ void __launch_bounds__(256) k_erode_v_jobs(const ErodeJob* __restrict__ jobs) {
+    const ErodeJob& J = jobs[blockIdx.z];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= J.w || y >= J.h) return;
+    const uint8_t* col = J.tmp + x;
+    const int a = J.k / 2;
+    const int y0 = max(y - a, 0), y1 = min(y - a + J.k - 1, J.h - 1);
+    int m = 255;
+    for (int j = y0; j <= y1; j++) m = min(m, (int)col[(size_t)j * J.w]);
+    J.dst[(size_t)y * J.w + x] = (uint8_t)m;
+}
+
+int launch_erode_jobs(const ErodeJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st) {
+    if (n_jobs <= 0) return DVFE_OK;
+    dim3 blk(32, 8), grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
+    DVFE_LAUNCH(k_erode_h_jobs, grid, blk, 0, st, d_jobs);
+    DVFE_LAUNCH(k_erode_v_jobs, grid, blk, 0, st, d_jobs);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}

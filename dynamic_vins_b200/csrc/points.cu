@@ -60,10 +60,11 @@ int launch_lift(const CamParams& cam, const float2* pts, int n, float offx, floa
 
 // ---- ReduceVector after the temporal LK: keep status != 0, preserve order; track_cnt++ ---------------
 // One block per point set; in-place (destination index <= source index, chunks are read before written).
-__global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int cap) {
+__global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int cap, const uint8_t* __restrict__ active) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int set = blockIdx.x;
+    if (active != nullptr && !active[set]) return;      // TrackLeft was not called for this set
     const size_t o = (size_t)set * cap;
     const int n = S.n[set];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,17 +100,19 @@ __global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int c
     if (tid == 0) S.n[set] = s_base;
 }
 
-int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st) {
+int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st, const uint8_t* d_active) {
     if (n_sets <= 0) return DVFE_OK;
-    DVFE_LAUNCH(k_compact_tracked, n_sets, 256, 0, st, S, cap);
+    DVFE_LAUNCH(k_compact_tracked, n_sets, 256, 0, st, S, cap, d_active);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }
 
 // ---- UndistortedPts + PtsVelocity for the left image; un[] holds prev_id_pts on entry, curr on exit ------
 __global__ void __launch_bounds__(128) k_left_post(PointSetArrays S, int cap, CamParams cam, const double* __restrict__ dt,
-                                                   const float2* __restrict__ offset /* nullable, per set */) {
+                                                   const float2* __restrict__ offset /* nullable, per set */,
+                                                   const uint8_t* __restrict__ active) {
     const int set = blockIdx.y;
+    if (active != nullptr && !active[set]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.n[set]) return;
     const size_t k = (size_t)set * cap + i;
@@ -130,10 +133,10 @@ __global__ void __launch_bounds__(128) k_left_post(PointSetArrays S, int cap, Ca
 }
 
 int launch_left_post(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam, const double* d_dt,
-                     const float2* d_offset, cudaStream_t st) {
+                     const float2* d_offset, cudaStream_t st, const uint8_t* d_active) {
     if (n_sets <= 0) return DVFE_OK;
     dim3 grid((cap + 127) / 128, n_sets);
-    DVFE_LAUNCH(k_left_post, grid, 128, 0, st, S, cap, cam, d_dt, d_offset);
+    DVFE_LAUNCH(k_left_post, grid, 128, 0, st, S, cap, cam, d_dt, d_offset, d_active);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }
@@ -203,6 +206,68 @@ int launch_right_post_pack(const PointSetArrays& S, int n_sets, int cap, const C
                            int stereo_now, dvfe_obs* obs, int* n_obs, cudaStream_t st) {
     if (n_sets <= 0) return DVFE_OK;
     DVFE_LAUNCH(k_right_post_pack, n_sets, 256, 0, st, S, cap, cam1, d_dt, stereo_now, obs, n_obs);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// ---- instances: RightUndistortedPts + RightPtsVelocity + InstsFeatManager::Output record -----------------------
+// (front_end/dynamic_tracker.cpp:462-471, 521-577).  One record per point at out[set*cap + i]; ids ascend with i.
+__global__ void __launch_bounds__(128) k_inst_post_pack(PointSetArrays S, int cap, CamParams cam1, const double* __restrict__ dt,
+                                                        const uint8_t* __restrict__ active, int stereo_now,
+                                                        const uint32_t* __restrict__ inst_id, dvfe_inst_obs* __restrict__ out) {
+    const int set = blockIdx.y;
+    if (!active[set]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n[set]) return;
+    const size_t k = (size_t)set * cap + i;
+    const bool has_r = stereo_now && S.rstatus[k] != 0;
+    float2 run = make_float2(0, 0), rvel = run;
+    if (has_r) {
+        const float2 rp = S.rpts[k];
+        run = lift_projective(cam1, rp.x, rp.y);
+        if (S.rprev_valid[k]) {
+            const float2 prev = S.rprev_un[k];
+            const double d = dt[set];
+            rvel.x = (float)((double)(run.x - prev.x) / d);
+            rvel.y = (float)((double)(run.y - prev.y) / d);
+        }
+    }
+    if (stereo_now) {      // right_prev_id_pts = right_curr_id_pts (PostProcess)
+        S.rprev_valid[k] = has_r ? 1 : 0;
+        if (has_r) S.rprev_un[k] = run;
+    }
+    const float2 p = S.pts[k], un = S.un[k], vel = S.vel[k];
+    dvfe_inst_obs r;
+    r.inst_id = inst_id[set]; r.id = S.ids[k]; r.is_stereo = has_r ? 1 : 0; r.reserved = 0;
+    r.point[0] = un.x; r.point[1] = un.y; r.point[2] = 1.0;
+    r.vel[0] = vel.x; r.vel[1] = vel.y;
+    r.point_right[0] = has_r ? (double)run.x : 0.0; r.point_right[1] = has_r ? (double)run.y : 0.0;
+    r.point_right[2] = has_r ? 1.0 : 0.0;
+    r.vel_right[0] = has_r ? (double)rvel.x : 0.0; r.vel_right[1] = has_r ? (double)rvel.y : 0.0;
+    r.uv[0] = p.x; r.uv[1] = p.y;
+    r.disp = 0.0;
+    out[k] = r;
+}
+
+int launch_inst_post_pack(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam1, const double* d_dt,
+                          const uint8_t* d_active, int stereo_now, const uint32_t* d_inst_id, dvfe_inst_obs* out,
+                          cudaStream_t st) {
+    if (n_sets <= 0) return DVFE_OK;
+    dim3 grid((cap + 127) / 128, n_sets);
+    DVFE_LAUNCH(k_inst_post_pack, grid, 128, 0, st, S, cap, cam1, d_dt, d_active, stereo_now, d_inst_id, out);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// n[set] = 0 for the flagged sets (InstsFeatManager::ClearState, front_end/dynamic_tracker.cpp:41-58)
+__global__ void k_clear_sets(int* n, const uint8_t* __restrict__ flags, int n_sets) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_sets && flags[i]) n[i] = 0;
+}
+
+int launch_clear_sets(int* d_n, const uint8_t* d_flags, int n_sets, cudaStream_t st) {
+    if (n_sets <= 0) return DVFE_OK;
+    DVFE_LAUNCH(k_clear_sets, (n_sets + 127) / 128, 128, 0, st, d_n, d_flags, n_sets);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

@@ -35,14 +35,10 @@ __global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, i
 }
 
 // ---- REFLECT_101 border of a level, copied from its own interior; one warp per padded row ------------------
-__global__ void __launch_bounds__(256) k_pyr_border(PyrImgSet set, PyrLevel L) {
-    const uint8_t* src; uint8_t* base;
-    pyr_select(set, blockIdx.z, src, base);
+__device__ __forceinline__ void pyr_border_body(uint8_t* base, const PyrLevel& L, int py, int lane) {
     uint8_t* lvl = base + L.offset;
     const uint8_t* __restrict__ in = lvl + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;      // pixel (0,0)
-    const int py = blockIdx.x * blockDim.y + threadIdx.y;
     if (py >= L.h + 2 * DVFE_PADY) return;
-    const int lane = threadIdx.x;
     const int y = py - DVFE_PADY;
     const uint8_t* __restrict__ srow = in + (size_t)reflect101(y, L.h) * L.pitch;
     unsigned* orow = reinterpret_cast<unsigned*>(lvl + (size_t)py * L.pitch);
@@ -61,6 +57,18 @@ __global__ void __launch_bounds__(256) k_pyr_border(PyrImgSet set, PyrLevel L) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_pyr_border(PyrImgSet set, PyrLevel L) {
+    const uint8_t* src; uint8_t* base;
+    pyr_select(set, blockIdx.z, src, base);
+    pyr_border_body(base, L, blockIdx.x * blockDim.y + threadIdx.y, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256) k_pyr_border_jobs(const PyrJob* __restrict__ jobs, int level) {
+    const PyrJob& J = jobs[blockIdx.z];
+    if (level >= J.desc.n_levels) return;
+    pyr_border_body(J.dst, J.desc.lv[level], blockIdx.x * blockDim.y + threadIdx.y, threadIdx.x);
+}
+
 // ---- level l interior from level l-1 (padded, border already filled) -------------------------------------
 __device__ __forceinline__ int pyr_tap5(const uint8_t* __restrict__ p) {
     return (int)p[-2] + 4 * (int)p[-1] + 6 * (int)p[0] + 4 * (int)p[1] + (int)p[2];
@@ -69,14 +77,9 @@ __device__ __forceinline__ int pyr_tap5(const uint8_t* __restrict__ p) {
 // one thread = 8 consecutive outputs of two consecutive rows.  It reads 7 source rows (one 16-byte and two
 // 4-byte aligned loads each) and evaluates the separable 5x5 kernel with dp4a: the horizontal taps (1 4 6 4)
 // times the vertical weight fit int8, the fifth tap is a second dp4a.
-__global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D) {
-    const uint8_t* unused; uint8_t* base;
-    pyr_select(set, blockIdx.z, unused, base);
+__device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, const PyrLevel& D, int x0, int y0) {
     const uint8_t* __restrict__ src = base + S.offset + (size_t)DVFE_PADY * S.pitch + DVFE_PADX;   // pixel (0,0)
     uint8_t* __restrict__ dst = base + D.offset + (size_t)DVFE_PADY * D.pitch + DVFE_PADX;
-
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
     if (x0 >= D.w || y0 >= D.h) return;
     if (x0 + 7 < D.w && y0 + 1 < D.h) {
         unsigned acc0[8], acc1[8];
@@ -128,6 +131,70 @@ __global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, Pyr
                           4 * pyr_tap5(c + S.pitch) + pyr_tap5(c + 2 * S.pitch);
             dst[(size_t)(y0 + rr) * D.pitch + x0 + i] = (uint8_t)((s + 128) >> 8);
         }
+}
+
+__global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D) {
+    const uint8_t* unused; uint8_t* base;
+    pyr_select(set, blockIdx.z, unused, base);
+    pyr_down_body(base, S, D, (blockIdx.x * blockDim.x + threadIdx.x) * 8, (blockIdx.y * blockDim.y + threadIdx.y) * 2);
+}
+
+__global__ void __launch_bounds__(256) k_pyr_down_jobs(const PyrJob* __restrict__ jobs, int level) {
+    const PyrJob& J = jobs[blockIdx.z];
+    if (level >= J.desc.n_levels) return;
+    pyr_down_body(J.dst, J.desc.lv[level - 1], J.desc.lv[level], (blockIdx.x * blockDim.x + threadIdx.x) * 8,
+                  (blockIdx.y * blockDim.y + threadIdx.y) * 2);
+}
+
+// level 0 of a job: the source image (sw x sh) zero-extended at the bottom/right to the level size
+// (InstanceImagePadding: cv::copyMakeBorder(..., BORDER_CONSTANT, 0), front_end/feature_utils.cpp:406-413)
+__global__ void __launch_bounds__(256) k_pyr_level0_jobs(const PyrJob* __restrict__ jobs) {
+    const PyrJob& J = jobs[blockIdx.z];
+    const PyrLevel L = J.desc.lv[0];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= L.w || y >= L.h) return;
+    uint8_t v = 0;
+    if (x < J.sw && y < J.sh) v = J.src[(size_t)y * J.spitch + x];
+    J.dst[L.offset + (size_t)(y + DVFE_PADY) * L.pitch + DVFE_PADX + x] = v;
+}
+
+int launch_build_pyramids_jobs(const PyrJob* d_jobs, int n_jobs, int max_w, int max_h, int max_levels, cudaStream_t st) {
+    if (n_jobs <= 0) return DVFE_OK;
+    const dim3 blk(32, 8);
+    {
+        dim3 grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
+        DVFE_LAUNCH(k_pyr_level0_jobs, grid, blk, 0, st, d_jobs);
+    }
+    int w = max_w, h = max_h;
+    for (int l = 0; l < max_levels; l++) {
+        if (l > 0) {
+            w = (w + 1) / 2; h = (h + 1) / 2;
+            dim3 grid(((w + 7) / 8 + 31) / 32, ((h + 1) / 2 + 7) / 8, n_jobs);
+            DVFE_LAUNCH(k_pyr_down_jobs, grid, blk, 0, st, d_jobs, l);
+        }
+        dim3 bgrid((h + 2 * DVFE_PADY + 7) / 8, 1, n_jobs);
+        DVFE_LAUNCH(k_pyr_border_jobs, bgrid, blk, 0, st, d_jobs, l);
+    }
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// crop of a rectangle out of a pitched image into a dense buffer (SemanticImage::SetMaskAndRoi: gray0(rect))
+__global__ void __launch_bounds__(256) k_crop_jobs(const CropJob* __restrict__ jobs) {
+    const CropJob& J = jobs[blockIdx.z];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= J.w || y >= J.h) return;
+    J.dst[(size_t)y * J.w + x] = J.src[(size_t)(J.y + y) * J.spitch + J.x + x];
+}
+
+int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st) {
+    if (n_jobs <= 0) return DVFE_OK;
+    dim3 blk(32, 8), grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
+    DVFE_LAUNCH(k_crop_jobs, grid, blk, 0, st, d_jobs);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
 }
 
 // level0_in_place: level 0's interior has already been written (H2D straight into the padded layout)

@@ -73,7 +73,6 @@ int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist
     sc->cand_cap = (w * h) / 4 + 4096;
     sc->n_cells = gftt_cells(w, h, min_dist);
     DVFE_CHECK(dmalloc(&sc->mask, (size_t)n_jobs * sc->mask_pitch * h));
-    DVFE_CHECK(dmalloc(&sc->eig, (size_t)n_jobs * w * h));
     DVFE_CHECK(dmalloc(&sc->cand, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->cand2, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->cand3, (size_t)n_jobs * sc->cand_cap));
@@ -84,7 +83,7 @@ int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist
 }
 
 void free_gftt_scratch(GfttScratch* sc) {
-    cudaFree(sc->mask); cudaFree(sc->eig); cudaFree(sc->cand); cudaFree(sc->cand2); cudaFree(sc->cand3); cudaFree(sc->state);
+    cudaFree(sc->mask); cudaFree(sc->cand); cudaFree(sc->cand2); cudaFree(sc->cand3); cudaFree(sc->state);
     cudaFree(sc->cell_count); cudaFree(sc->counters);
     memset(sc, 0, sizeof(*sc));
 }
@@ -92,7 +91,7 @@ void free_gftt_scratch(GfttScratch* sc) {
 void gftt_job_bind_scratch(GfttJob* J, const GfttScratch& sc, int j) {
     J->mask = sc.mask + (size_t)j * sc.mask_pitch * sc.h;
     J->mask_pitch = sc.mask_pitch;
-    J->eig = sc.eig + (size_t)j * sc.w * sc.h;
+    J->eig = nullptr;
     J->cand = sc.cand + (size_t)j * sc.cand_cap;
     J->cand2 = sc.cand2 + (size_t)j * sc.cand_cap;
     J->cand3 = sc.cand3 + (size_t)j * sc.cand_cap;
@@ -223,6 +222,7 @@ int dvfe_tracker::init() {
             DVFE_CHECK(dmalloc(&d_jobs[par][kind], (size_t)B));
             DVFE_CUDA(cudaMemcpy(d_jobs[par][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
         }
+    DVFE_CHECK(init_instances());
     DVFE_CUDA(cudaDeviceSynchronize());
     return DVFE_OK;
 }
@@ -293,6 +293,7 @@ int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, siz
         prof_steps++;
     }
     for (int s = 0; s < B; s++) prev_time[s] = time0[s];
+    last_has_right = stereo_now;
     cur = 1 - cur;
     frames++;
     return DVFE_OK;

@@ -8,7 +8,6 @@
 struct GfttScratch {
     int n_jobs, w, h, mask_pitch, cand_cap, n_cells;
     uint8_t* mask;
-    float* eig;
     unsigned long long *cand, *cand2, *cand3;
     uint8_t* state;
     int* cell_count;
@@ -33,6 +32,7 @@ struct dvfe_tracker {
     uint8_t* pyr[3] = {nullptr, nullptr, nullptr};   // left (even frames), left (odd frames), right
     int cur = 0;                                     // pyr[cur] receives the current left image
     long frames = 0;
+    bool last_has_right = false;                     // the last uploaded frame had a right image
     PointSetArrays bg{};                             // background point sets, one per stream
     uint32_t* d_next_id = nullptr;                   // [B] InstFeat::global_id_count per stream
     double* d_dt = nullptr;
@@ -63,5 +63,6 @@ struct dvfe_tracker {
     int upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
     int step_device(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
                     bool semantic, bool level0_in_place = false, bool has_right = false);
+    int init_instances();
     void free_instances();
 };

@@ -15,7 +15,8 @@ POS_TOL = 0.02        # px  (north_star)
 def cfg_of(name, n_streams=1, **kw):
     c = dict(synth.CONFIGS[name])
     c.update(kw)
-    return make_config(n_streams=n_streams, **{k: v for k, v in c.items() if k not in ("n_objects", "config_id")})
+    c.pop("n_objects", None); c.pop("config_id", None)
+    return make_config(n_streams=n_streams, **c)
 
 
 def params_of(name):
@@ -193,3 +194,100 @@ def test_reference_api_names():
     assert sorted(out) == list(range(1, 151))       # global_id_count starts at 1
     txt = dv.tracker.serialize_point_features(out)
     assert txt.count("\n") == 150 and txt.startswith("0 1 ")
+
+
+# ---- dynamic mode: TrackSemanticImage + InstsTrack + Output (BASELINE.json config 3) --------------------------
+def inst_rows(records):
+    """dvfe_inst_obs records -> rows comparable with the oracle's Output()"""
+    return [(int(r["inst_id"]), int(r["id"]), int(r["is_stereo"]), r["point"].copy(), r["vel"].copy(),
+             r["point_right"].copy(), r["vel_right"].copy(), r["uv"].copy()) for r in records]
+
+
+def oracle_inst_rows(instances):
+    rows = []
+    for inst_id, inst in instances.items():
+        for fid, f in inst["features"].items():
+            rows.append((inst_id, fid, int(f["is_stereo"]), f["point"], f["vel"], f["point_right"], f["vel_right"], f["uv"]))
+    return rows
+
+
+def compare_instances(got, want, cam0, dt_min=0.05):
+    assert [(a[0], a[1], a[2]) for a in got] == [(b[0], b[1], b[2]) for b in want], \
+        "instance ids / feature ids / stereo bits differ"
+    un_tol = 1.5 * POS_TOL / min(cam0["fx"], cam0["fy"])
+    for a, b in zip(got, want):
+        assert np.abs(a[7] - b[7]).max() <= POS_TOL                  # ROI-local pixel position
+        assert np.abs(a[3] - b[3]).max() <= un_tol and np.abs(a[5] - b[5]).max() <= un_tol
+        assert np.abs(a[4] - b[4]).max() <= 2 * un_tol / dt_min and np.abs(a[6] - b[6]).max() <= 2 * un_tol / dt_min
+
+
+def test_dynamic_mode_vs_oracle():
+    """8 moving objects with per-instance masks; objects drop out for 1-2 frames (kept, lost_num <= 3), for good
+    (erased after > 3 lost frames) and a frame has no detections at all"""
+    name = "c3_zed_dynamic"
+    c = synth.CONFIGS[name]
+    st = synth.make_stream(name, 0)
+    fe = cvfe.FrontEnd(params_of(name), c["cam0"], c["cam1"], "dynamic")
+    trk = BatchTracker(cfg_of(name, max_instances=12))
+    n_inst_feats = 0
+    for k in range(12):
+        fr = st.frame(k)
+        drop = set()
+        if k in (3, 4):
+            drop = {2}                  # instance 2 is missed for two frames and comes back
+        if k >= 5:
+            drop = {7}                  # instance 7 disappears for good
+        if k == 8:
+            drop = set(range(1, 9))     # no detections at all in this frame
+        fr.boxes = [b for b in fr.boxes if b["track_id"] not in drop]
+        if drop:
+            merge = np.zeros_like(fr.merge_mask)
+            for b in fr.boxes:
+                x, y, w, h = b["rect"]
+                merge[y:y + h, x:x + w] |= b["mask"]
+            fr.merge_mask, fr.inv_merge_mask, fr.exist_inst = merge, (255 - merge).astype(np.uint8), len(fr.boxes) > 0
+        want = fe.step(fr)
+        trk.track_semantic_image(fr.gray0, fr.gray1, fr.inv_merge_mask, fr.exist_inst, fr.time0)
+        trk.insts_track(0, fr.boxes, fr.time0)
+        ids, cams, v = feature_map_arrays(want["features"])
+        compare_records(trk.features(0), ids, cams, v, c["cam0"])
+        got_i, want_i = inst_rows(trk.insts_output(0)), oracle_inst_rows(want["instances"])
+        compare_instances(got_i, want_i, c["cam0"])
+        n_inst_feats += len(got_i)
+        if k == 8:
+            assert len(got_i) == 0
+    assert n_inst_feats > 2000
+    trk.close()
+
+
+def test_dynamic_mode_vs_golden():
+    name = "c3_zed_dynamic"
+    g = load_golden(f"tracker_{name}_dynamic.npz")
+    c = synth.CONFIGS[name]
+    st = synth.make_stream(name, 0)
+    trk = BatchTracker(cfg_of(name, max_instances=8))
+    for k in range(int(g["n_frames"])):
+        fr = st.frame(k)
+        assert crc(fr.gray0) == int(g[f"f{k}_crc0"])
+        trk.track_semantic_image(fr.gray0, fr.gray1, fr.inv_merge_mask, fr.exist_inst, fr.time0)
+        trk.insts_track(0, fr.boxes, fr.time0)
+        compare_records(trk.features(0), g[f"f{k}_ids"], g[f"f{k}_cams"], g[f"f{k}_v"], c["cam0"])
+        rows = g[f"f{k}_inst"]
+        rec = trk.insts_output(0)
+        assert np.array_equal(rec["inst_id"], rows[:, 0].astype(np.uint32))
+        assert np.array_equal(rec["id"], rows[:, 1].astype(np.uint32))
+        assert np.array_equal(rec["is_stereo"], rows[:, 2].astype(np.int32))
+        assert np.abs(rec["uv"] - rows[:, 13:15]).max() <= POS_TOL
+
+
+def test_instance_capacity_and_argument_errors():
+    name = "c3_zed_dynamic"
+    fr = synth.make_stream(name, 0).frame(0)
+    trk = BatchTracker(cfg_of(name, max_instances=4))
+    trk.track_semantic_image(fr.gray0, fr.gray1, fr.inv_merge_mask, fr.exist_inst, fr.time0)
+    with pytest.raises(dv.DvfeError) as e:
+        trk.insts_track(0, fr.boxes, fr.time0)          # 8 instances > 4 slots
+    assert e.value.code == -4
+    raw = BatchTracker(cfg_of("c2_kitti_stereo"))       # max_instances = 0
+    with pytest.raises(dv.DvfeError):
+        raw.insts_track(0, [], 0.0)
