@@ -1,0 +1,53 @@
+// C++ drop-in check: drives include/dvfe/feature_tracker.hpp (the reference-shaped C++ API) exactly like
+// FeatureTrack() in dynamic_vins/src/system/main.cpp:178-330 does, on frames dumped by the python test, and writes the
+// features in the reference's SerializePointFeature text format (utils/io/feature_serialization.cpp:26-38).
+//   usage: test_feature_tracker <config.yaml> <frames.bin> <n_frames> <stereo 0|1> <out_prefix>
+// frames.bin: n_frames x (time0 f64, gray0 H*W, [gray1 H*W])
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+#include "dvfe/feature_tracker.hpp"
+
+int main(int argc, char** argv) {
+    if (argc < 6) { std::fprintf(stderr, "usage\n"); return 2; }
+    try {
+        dynamic_vins::FeatureTracker tracker(argv[1]);
+        const int n_frames = std::atoi(argv[3]);
+        const bool stereo = std::atoi(argv[4]) != 0;
+        const int W = tracker.config().width, H = tracker.config().height;
+        std::ifstream fin(argv[2], std::ios::binary);
+        std::vector<uint8_t> g0((size_t)W * H), g1((size_t)W * H);
+        for (int k = 0; k < n_frames; k++) {
+            dynamic_vins::SemanticImage img;
+            fin.read(reinterpret_cast<char*>(&img.time0), sizeof(double));
+            fin.read(reinterpret_cast<char*>(g0.data()), (std::streamsize)g0.size());
+            img.gray0 = {g0.data(), H, W, W};
+            if (stereo) {
+                fin.read(reinterpret_cast<char*>(g1.data()), (std::streamsize)g1.size());
+                img.gray1 = {g1.data(), H, W, W};
+            }
+            img.seq = (unsigned)k;
+            dynamic_vins::FeatureBackground fb = tracker.TrackImage(img);
+            char path[512];
+            std::snprintf(path, sizeof(path), "%s_%d_point.txt", argv[5], k);
+            std::FILE* fo = std::fopen(path, "w");
+            for (const auto& kv : fb.points) {
+                std::fprintf(fo, "%d %u", kv.second.size() == 1 ? 0 : 1, kv.first);
+                for (const auto& obs : kv.second)
+                    for (double v : obs.second) std::fprintf(fo, " %.17g", v);
+                std::fprintf(fo, "\n");
+            }
+            std::fclose(fo);
+        }
+        // the reference throws on a wrong settings path (front_end_parameters.cpp:20-22)
+        bool threw = false;
+        try { dynamic_vins::FeatureTracker bad("/nonexistent/config.yaml"); } catch (const std::runtime_error&) { threw = true; }
+        if (!threw) { std::fprintf(stderr, "bad config path did not throw\n"); return 3; }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,5 +1,7 @@
 """GPU parity tests of the frame step (TrackImage / TrackSemanticImage) through the C ABI, against the committed
 golden fixtures and the cv2 oracle run live on the same seeded frames (SURVEY.md Appendix D protocol)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -291,3 +293,49 @@ def test_instance_capacity_and_argument_errors():
     raw = BatchTracker(cfg_of("c2_kitti_stereo"))       # max_instances = 0
     with pytest.raises(dv.DvfeError):
         raw.insts_track(0, [], 0.0)
+
+
+def test_cpp_reference_shaped_api(tmp_path):
+    """the C++ mirror of FeatureTracker (include/dvfe/feature_tracker.hpp) driven like FeatureTrack() in
+    system/main.cpp, from a yaml config in the reference's format; output compared with the oracle through the
+    reference's SerializePointFeature text format"""
+    import subprocess
+    from conftest import ROOT
+    name = "c2_kitti_stereo"
+    c = synth.CONFIGS[name]
+    for i, cam in enumerate((c["cam0"], c["cam1"])):
+        (tmp_path / f"cam{i}.yaml").write_text(
+            "%YAML:1.0\n---\nmodel_type: PINHOLE\ncamera_name: camera\n"
+            f"image_width: {c['width']}\nimage_height: {c['height']}\ndistortion_parameters:\n"
+            f"   k1: {cam['k1']!r}\n   k2: {cam['k2']!r}\n   p1: {cam['p1']!r}\n   p2: {cam['p2']!r}\n"
+            f"projection_parameters:\n   fx: {cam['fx']!r}\n   fy: {cam['fy']!r}\n   cx: {cam['cx']!r}\n   cy: {cam['cy']!r}\n")
+    (tmp_path / "cfg.yaml").write_text(
+        "%YAML:1.0\n\nnum_of_cam: 2\nslam_type: \"raw\"\n"
+        f"image_width: {c['width']}\nimage_height: {c['height']}\ncam0_calib: \"cam0.yaml\"\ncam1_calib: \"cam1.yaml\"\n"
+        f"max_cnt: {c['max_cnt']}\nmin_dist: {c['min_dist']}\nF_threshold: 1.0\nshow_track: 0\nflow_back: 1\n"
+        "min_dynamic_dist: 5\nmax_dynamic_cnt: 50\nuse_mask_morphology: 0\nmask_morphology_size: 5\n")
+    exe = str(tmp_path / "test_feature_tracker")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_feature_tracker.cpp"),
+                           "-L" + os.path.join(ROOT, "dynamic_vins_b200"), "-ldvfe",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe])
+    st = synth.make_stream(name, 5)
+    n_frames = 4
+    fe = cvfe.FrontEnd(params_of(name), c["cam0"], c["cam1"], "raw")
+    want = []
+    with open(tmp_path / "frames.bin", "wb") as f:
+        for k in range(n_frames):
+            fr = st.frame(k)
+            f.write(np.float64(fr.time0).tobytes()); f.write(fr.gray0.tobytes()); f.write(fr.gray1.tobytes())
+            want.append(fe.step(fr)["features"])
+    subprocess.check_call([exe, str(tmp_path / "cfg.yaml"), str(tmp_path / "frames.bin"), str(n_frames), "1",
+                           str(tmp_path / "out")])
+    for k in range(n_frames):
+        lines = open(tmp_path / f"out_{k}_point.txt").read().strip().split("\n")
+        assert len(lines) == len(want[k])
+        for ln, (fid, obs) in zip(lines, want[k].items()):
+            tok = ln.split()
+            assert int(tok[1]) == fid and int(tok[0]) == (1 if len(obs) == 2 else 0)
+            vals = np.array([float(x) for x in tok[2:]])
+            ref = np.concatenate([o[1] for o in obs])
+            assert len(vals) == len(ref) and np.abs(vals[3:5] - ref[3:5]).max() <= POS_TOL
