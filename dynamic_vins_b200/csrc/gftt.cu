@@ -90,172 +90,135 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 }
 
 // ---- response map (cv::cornerMinEigenVal, blockSize 3, ksize 3), masked max, local maxima ------------------
-// One block owns a 30x14 tile of pixels and computes lambda on the 32x16 region around it (1-pixel ring for the
-// 3x3 local-maximum test), from Sobel derivatives on 34x18 and image pixels on 36x20, all staged in shared
-// memory.  Nothing but the pre-candidates (local maxima with mask != 0) and the masked maximum leaves the chip;
-// the quality threshold needs the global maximum and is applied by the selection kernel.
-#define RT_OW 62
-#define RT_OH 14
-#define RT_LW 64
-#define RT_LH 16
-#define RT_DW 66
-#define RT_DH 18
-#define RT_IW 68
-#define RT_IH 20
+// Marching stencil: a warp owns a strip of 28 columns x RS_ROWS rows and walks down the image one row per step
+// with everything in registers.  Lane l holds column xb + l - 2 (two halo columns on each side); horizontal
+// neighbours come from warp shuffles.  Loading image row y yields, in the same step,
+//     Sobel derivatives and their products (the CV_32F cov image) of row y-1,
+//     the horizontal 3-sums H(y-1) in double        (cv::boxFilter RowSum<float,double>),
+//     the vertical 3-sum / lambda of row y-2        (ColumnSum<double,float> + calcMinEigenVal),
+//     the 3x3 local-maximum test of row y-3.
+// Nothing but the pre-candidates (local maxima with mask != 0) and the masked maximum leaves the chip; the
+// quality threshold needs the global maximum and is applied by the selection kernel.
+#define RS_COLS 28
+#define RS_ROWS 48
+#define RS_WARPS 8
 
 template <bool WRITE_EIG, bool EMIT>
-__device__ __forceinline__ void resp_tile(const uint8_t* __restrict__ img, int pitch, int w, int h, int ox0, int oy0,
-                                          float* __restrict__ eig, const uint8_t* __restrict__ mask, int mask_pitch,
-                                          int* __restrict__ counters, unsigned long long* __restrict__ cand, int cand_cap) {
-    __shared__ uint8_t s_img[RT_IH][RT_IW + 4];
-    __shared__ float s_p[3][RT_DH][RT_DW + 1];       // derivative products xx, xy, yy (the CV_32F cov image)
-    __shared__ double s_h[3][RT_DH][RT_LW];          // horizontal 3-sums
-    __shared__ float s_lam[RT_LH][RT_LW + 1];
-    __shared__ int s_max[8];
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int pitch, int w, int h, int xb, int y0,
+                                           float* __restrict__ eig, const uint8_t* __restrict__ mask, int mask_pitch,
+                                           int* __restrict__ counters, unsigned long long* __restrict__ cand, int cand_cap) {
+    const int lane = threadIdx.x & 31;
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = s * 2.0f;
-    const int lx0 = ox0 - 1, ly0 = oy0 - 1;      // lambda region origin
-    const int dx0 = lx0 - 1, dy0 = ly0 - 1;      // derivative region origin
-    const int ix0 = dx0 - 1, iy0 = dy0 - 1;      // image region origin
+    const int x = xb + lane - 2;
+    const int y1 = min(y0 + RS_ROWS, h);
+    const uint8_t* __restrict__ col = img + reflect101(x, w);
+    const uint8_t* __restrict__ col_edge = img + reflect101(lane == 0 ? x - 1 : x + 1, w);   // lanes 0 / 31 only
+    const bool owned_col = lane >= 2 && lane < 2 + RS_COLS && x < w;
+    const bool cand_col = owned_col && x >= 1 && x < w - 1;
 
-    if (EMIT) {
-        // a tile whose owned pixels are all masked out contributes neither candidates nor the maximum
-        int any = 0;
-        for (int i = tid; i < RT_OW * RT_OH; i += 256) {
-            const int r = i / RT_OW, c = i - r * RT_OW;
-            const int gx = ox0 + c, gy = oy0 + r;
-            if (gx < w && gy < h) any |= mask[(size_t)gy * mask_pitch + gx];
-        }
-        if (!__syncthreads_or(any)) return;
-    }
-    // P0: image region, REFLECT_101
-    for (int i = tid; i < RT_IH * RT_IW; i += 256) {
-        const int r = i / RT_IW, c = i - r * RT_IW;
-        s_img[r][c] = __ldg(img + (size_t)reflect101(iy0 + r, h) * pitch + reflect101(ix0 + c, w));
-    }
-    __syncthreads();
-    // P1: Sobel at the in-image positions of the derivative region, products rounded to float
-    for (int i = tid; i < RT_DH * RT_DW; i += 256) {
-        const int r = i / RT_DW, c = i - r * RT_DW;
-        const int gx = dx0 + c, gy = dy0 + r;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-            const float a00 = s_img[r][c], a01 = s_img[r][c + 1], a02 = s_img[r][c + 2];
-            const float a10 = s_img[r + 1][c], a12 = s_img[r + 1][c + 2];
-            const float a20 = s_img[r + 2][c], a21 = s_img[r + 2][c + 1], a22 = s_img[r + 2][c + 2];
-            // Dx: row kernel [-1 0 1] exact, column kernel [1 2 1]*scale -> fma(s, d0 + d2, (2s)*d1)
-            const float d0 = a02 - a00, d1 = a12 - a10, d2 = a22 - a20;
-            const float dx = __fmaf_rn(s, __fadd_rn(d0, d2), __fmul_rn(s2, d1));
-            // Dy: row kernel [1 2 1]*scale -> fma(s, r, fma(2s, c, s*l)); column kernel [-1 0 1]
-            const float top = __fmaf_rn(s, a02, __fmaf_rn(s2, a01, __fmul_rn(s, a00)));
-            const float bot = __fmaf_rn(s, a22, __fmaf_rn(s2, a21, __fmul_rn(s, a20)));
-            const float dy = __fsub_rn(bot, top);
-            s_p[0][r][c] = __fmul_rn(dx, dx);
-            s_p[1][r][c] = __fmul_rn(dx, dy);
-            s_p[2][r][c] = __fmul_rn(dy, dy);
-        }
-    }
-    __syncthreads();
-    // P2: positions one step outside the image take the products of their REFLECT_101 position (the box
-    // filter's border rule applies to the cov image, not to the input image)
-    if (dx0 < 0 || dy0 < 0 || dx0 + RT_DW > w || dy0 + RT_DH > h) {
-        for (int i = tid; i < RT_DH * RT_DW; i += 256) {
-            const int r = i / RT_DW, c = i - r * RT_DW;
-            const int gx = dx0 + c, gy = dy0 + r;
-            if (!(gx >= 0 && gx < w && gy >= 0 && gy < h)) {
-                const int rr = reflect101(gy, h) - dy0, rc = reflect101(gx, w) - dx0;
-                const bool ok = gx >= -1 && gx <= w && gy >= -1 && gy <= h && rr >= 0 && rr < RT_DH && rc >= 0 && rc < RT_DW;
-#pragma unroll
-                for (int k = 0; k < 3; k++) s_p[k][r][c] = ok ? s_p[k][rr][rc] : 0.f;
-            }
-        }
-        __syncthreads();
-    }
-    // P3: horizontal 3-sums accumulated in double (cv::boxFilter: RowSum<float,double>)
-    for (int i = tid; i < RT_DH * RT_LW; i += 256) {
-        const int r = i >> 6, c = i & 63;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            s_h[k][r][c] = ((double)s_p[k][r][c] + (double)s_p[k][r][c + 1]) + (double)s_p[k][r][c + 2];
-    }
-    __syncthreads();
-    // P4: vertical 3-sums (ColumnSum<double,float>) and lambda on the 64 x 16 region; 4 rows per thread
-    const int c = tid & 63, rbase = tid >> 6;
+    float dxr0 = 0.f, dxr1 = 0.f, smr0 = 0.f, smr1 = 0.f;           // row-filter outputs of rows y-2, y-1
+    double h0x = 0.0, h0y = 0.0, h0z = 0.0, h1x = 0.0, h1y = 0.0, h1z = 0.0;   // H(y-3), H(y-2)
+    float lam1 = 0.f, lr1 = 0.f, hm1 = 0.f, hm0 = 0.f;               // lambda row y-3 (lam, left/right max), hm of y-3, y-4
     int best = INT_MIN;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int r = rbase + 4 * q;
-        const int gx = lx0 + c, gy = ly0 + r;
+
+    const int y_last = y1 + (EMIT ? 2 : 1);
+    for (int y = y0 - 3; y <= y_last; y++) {
+        // ---- image row y (REFLECT_101), horizontal neighbours by shuffle ----
+        const size_t ro = (size_t)reflect101(y, h) * pitch;
+        const float c = (float)__ldg(col + ro);
+        float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+        if (lane == 0) l = (float)__ldg(col_edge + ro);
+        if (lane == 31) r = (float)__ldg(col_edge + ro);
+        // row filters: [-1 0 1] exact; [1 2 1]*scale as fma(s, r, fma(2s, c, s*l))
+        const float dxr2 = r - l;
+        const float smr2 = __fmaf_rn(s, r, __fmaf_rn(s2, c, __fmul_rn(s, l)));
+        // ---- derivatives of row y-1: column filters [1 2 1]*scale -> fma(s, d0 + d2, (2s)*d1) ; [-1 0 1] ----
+        const float dx = __fmaf_rn(s, __fadd_rn(dxr0, dxr2), __fmul_rn(s2, dxr1));
+        const float dy = __fsub_rn(smr2, smr0);
+        dxr0 = dxr1; dxr1 = dxr2; smr0 = smr1; smr1 = smr2;
+        float pxx = __fmul_rn(dx, dx), pxy = __fmul_rn(dx, dy), pyy = __fmul_rn(dy, dy);
+        // box-filter border rule (REFLECT_101 on the cov image): column -1 takes column 1, column w takes w-2
+        if (xb < 2 || xb + 30 > w) {
+            const float axx = __shfl_down_sync(0xffffffffu, pxx, 2), axy = __shfl_down_sync(0xffffffffu, pxy, 2),
+                        ayy = __shfl_down_sync(0xffffffffu, pyy, 2);
+            const float bxx = __shfl_up_sync(0xffffffffu, pxx, 2), bxy = __shfl_up_sync(0xffffffffu, pxy, 2),
+                        byy = __shfl_up_sync(0xffffffffu, pyy, 2);
+            if (x == -1) { pxx = axx; pxy = axy; pyy = ayy; }
+            if (x == w) { pxx = bxx; pxy = bxy; pyy = byy; }
+        }
+        // ---- H(y-1): horizontal 3-sum in double, left to right ----
+        const float lxx = __shfl_up_sync(0xffffffffu, pxx, 1), lxy = __shfl_up_sync(0xffffffffu, pxy, 1),
+                    lyy = __shfl_up_sync(0xffffffffu, pyy, 1);
+        const float rxx = __shfl_down_sync(0xffffffffu, pxx, 1), rxy = __shfl_down_sync(0xffffffffu, pxy, 1),
+                    ryy = __shfl_down_sync(0xffffffffu, pyy, 1);
+        double h2x = ((double)lxx + (double)pxx) + (double)rxx;
+        double h2y = ((double)lxy + (double)pxy) + (double)rxy;
+        double h2z = ((double)lyy + (double)pyy) + (double)ryy;
+        // ---- lambda of row yl = y-2: vertical 3-sum top to bottom; rows -1 / h take rows 1 / h-2 ----
+        const int yl = y - 2;
+        double ax = h0x, ay = h0y, az = h0z;
+        if (yl == 0) { ax = h2x; ay = h2y; az = h2z; }
+        if (yl == h - 1) { h2x = h0x; h2y = h0y; h2z = h0z; }
+        const float cxx = (float)((ax + h1x) + h2x);
+        const float cxy = (float)((ay + h1y) + h2y);
+        const float cyy = (float)((az + h1z) + h2z);
+        h0x = h1x; h0y = h1y; h0z = h1z; h1x = h2x; h1y = h2y; h1z = h2z;
         float lam = 0.f;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-            const float cxx = (float)((s_h[0][r][c] + s_h[0][r + 1][c]) + s_h[0][r + 2][c]);
-            const float cxy = (float)((s_h[1][r][c] + s_h[1][r + 1][c]) + s_h[1][r + 2][c]);
-            const float cyy = (float)((s_h[2][r][c] + s_h[2][r + 1][c]) + s_h[2][r + 2][c]);
+        if (yl >= 0 && yl < h && x >= 0 && x < w) {
             const float a = __fmul_rn(cxx, 0.5f), b = cxy, cc = __fmul_rn(cyy, 0.5f);
             const float amc = __fsub_rn(a, cc);
             lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
-            const bool owned = c >= 1 && c <= RT_OW && r >= 1 && r <= RT_OH;
-            if (owned) {
-                if (WRITE_EIG) eig[(size_t)gy * w + gx] = lam;
-                if (EMIT && mask[(size_t)gy * mask_pitch + gx] != 0) best = max(best, f2ord(lam));
+            if (owned_col && yl >= y0 && yl < y1) {
+                if (WRITE_EIG) eig[(size_t)yl * w + x] = lam;
+                if (EMIT && mask[(size_t)yl * mask_pitch + x] != 0) best = max(best, f2ord(lam));
             }
         }
-        s_lam[r][c] = lam;
-    }
-    if (!EMIT) return;
-    __syncthreads();
-    // P5: masked maximum of the tile; pre-candidates = 3x3 local maxima with mask != 0 inside the 1-pixel border
-    best = __reduce_max_sync(0xffffffffu, best);
-    if ((tid & 31) == 0) s_max[tid >> 5] = best;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int r = rbase + 4 * q;
-        const int gx = lx0 + c, gy = ly0 + r;
+        if (!EMIT) continue;
+        // ---- 3x3 local maximum of row yc = y-3 ----
+        const float ll = __shfl_up_sync(0xffffffffu, lam, 1), rl = __shfl_down_sync(0xffffffffu, lam, 1);
+        const float lr2 = fmaxf(ll, rl), hm2 = fmaxf(lr2, lam);
+        const int yc = y - 3;
         bool is_cand = false;
-        float v = 0.f;
-        if (c >= 1 && c <= RT_OW && r >= 1 && r <= RT_OH && gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
-            v = s_lam[r][c];
-            if (v != 0.f && mask[(size_t)gy * mask_pitch + gx] != 0) {
-                float m = fmaxf(fmaxf(s_lam[r - 1][c - 1], s_lam[r - 1][c]), fmaxf(s_lam[r - 1][c + 1], s_lam[r][c - 1]));
-                m = fmaxf(m, fmaxf(fmaxf(s_lam[r][c + 1], s_lam[r + 1][c - 1]), fmaxf(s_lam[r + 1][c], s_lam[r + 1][c + 1])));
-                is_cand = !(m > v);
-            }
+        if (cand_col && yc >= y0 && yc < y1 && yc >= 1 && yc < h - 1 && lam1 != 0.f) {
+            const float m = fmaxf(fmaxf(hm0, hm2), lr1);
+            if (!(m > lam1)) is_cand = mask[(size_t)yc * mask_pitch + x] != 0;
         }
+        const float v = lam1;
+        hm0 = hm1; hm1 = hm2; lam1 = lam; lr1 = lr2;
         const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
         if (ballot) {
-            const int lane = tid & 31;
             int base = 0;
             if (lane == 0) base = atomicAdd(&counters[0], __popc(ballot));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (is_cand) {
                 const int pos = base + __popc(ballot & ((1u << lane) - 1));
                 if (pos < cand_cap)
-                    cand[pos] = ((unsigned long long)((unsigned)f2ord(v) ^ 0x80000000u) << 32) | (unsigned)(gy * w + gx);
+                    cand[pos] = ((unsigned long long)((unsigned)f2ord(v) ^ 0x80000000u) << 32) | (unsigned)(yc * w + x);
                 else
                     counters[2] = 1;
             }
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        int m = s_max[0];
-#pragma unroll
-        for (int i = 1; i < 8; i++) m = max(m, s_max[i]);
-        if (m != INT_MIN) atomicMax(&counters[1], m);
+    if (EMIT) {
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (lane == 0 && best != INT_MIN) atomicMax(&counters[1], best);
     }
 }
 
-__global__ void __launch_bounds__(256) k_gftt_response(const GfttJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(RS_WARPS * 32) k_gftt_response(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.z];
     if (!gftt_job_active(J) || J.eig_in != nullptr) return;
-    const int ox0 = blockIdx.x * RT_OW, oy0 = blockIdx.y * RT_OH;
-    if (ox0 >= J.w || oy0 >= J.h) return;
-    resp_tile<false, true>(J.img, J.img_pitch, J.w, J.h, ox0, oy0, nullptr, J.mask, J.mask_pitch, J.counters, J.cand,
-                           J.cand_cap);
+    const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
+    if (xb >= J.w || y0 >= J.h) return;
+    resp_strip<false, true>(J.img, J.img_pitch, J.w, J.h, xb, y0, nullptr, J.mask, J.mask_pitch, J.counters, J.cand,
+                            J.cand_cap);
 }
 
-__global__ void __launch_bounds__(256) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
-    resp_tile<true, false>(img, pitch, w, h, blockIdx.x * RT_OW, blockIdx.y * RT_OH, eig, nullptr, 0, nullptr, nullptr, 0);
+__global__ void __launch_bounds__(RS_WARPS * 32) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
+    const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
+    if (xb >= w || y0 >= h) return;
+    resp_strip<true, false>(img, pitch, w, h, xb, y0, eig, nullptr, 0, nullptr, nullptr, 0);
 }
 
 // ---- externally supplied response map (seam op): masked max, then the same pre-candidates ---------------
@@ -624,7 +587,8 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
         DVFE_LAUNCH(k_gftt_max_ext, grid, blk, 0, st, d_jobs);
         DVFE_LAUNCH(k_gftt_candidates_ext, grid, blk, 0, st, d_jobs);
     } else {
-        dim3 blk(256), grid((max_w + RT_OW - 1) / RT_OW, (max_h + RT_OH - 1) / RT_OH, n_jobs);
+        dim3 blk(RS_WARPS * 32),
+            grid((max_w + RS_COLS * RS_WARPS - 1) / (RS_COLS * RS_WARPS), (max_h + RS_ROWS - 1) / RS_ROWS, n_jobs);
         DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
     }
     DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, 0, st, d_jobs);
@@ -634,7 +598,7 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
 }
 
 int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st) {
-    dim3 blk(256), grid((w + RT_OW - 1) / RT_OW, (h + RT_OH - 1) / RT_OH);
+    dim3 blk(RS_WARPS * 32), grid((w + RS_COLS * RS_WARPS - 1) / (RS_COLS * RS_WARPS), (h + RS_ROWS - 1) / RS_ROWS);
     DVFE_LAUNCH(k_min_eigen_val, grid, blk, 0, st, img, pitch, w, h, eig);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
