@@ -37,56 +37,62 @@ __device__ __forceinline__ bool gftt_job_active(const GfttJob& J) {
 }
 
 // ---- detection mask: region (or 255) ... -------------------------------------------------------
+// one thread = 16 bytes of a mask row (mask rows are 16-byte aligned)
 __global__ void __launch_bounds__(256) k_gftt_mask_fill(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.z];
     if (!gftt_job_active(J)) return;
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8 && threadIdx.y == 0) {
-        // reset the per-job counters: n_cand, max, overflow, n_accepted, new_cnt ...
+        // reset the per-job counters: n_precand, max, overflow, ...
         J.counters[threadIdx.x] = (threadIdx.x == 1) ? INT_MIN : 0;
     }
     if (x >= J.w || y >= J.h) return;
     uint8_t* m = J.mask + (size_t)y * J.mask_pitch + x;
-    if (J.region_mask == nullptr) {
-        if (x + 3 < J.w && (J.mask_pitch & 3) == 0) *reinterpret_cast<uint32_t*>(m) = 0xffffffffu;
-        else for (int i = 0; i < 4 && x + i < J.w; i++) m[i] = 255;
+    const bool aligned_dst = (J.mask_pitch & 15) == 0 && ((uintptr_t)J.mask & 15) == 0;   // the row may be over-written
+    if (J.region_mask == nullptr) {                                                       // up to the pitch
+        if (aligned_dst) *reinterpret_cast<uint4*>(m) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        else for (int i = 0; i < 16 && x + i < J.w; i++) m[i] = 255;
     } else {
         const uint8_t* r = J.region_mask + (size_t)y * J.region_pitch + x;
-        for (int i = 0; i < 4 && x + i < J.w; i++) m[i] = r[i];
+        if (aligned_dst && x + 15 < J.w && (((uintptr_t)r) & 15) == 0) *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(r);
+        else for (int i = 0; i < 16 && x + i < J.w; i++) m[i] = r[i];
     }
 }
 
 // ---- ... minus a filled disc around every tracked point:  cleared <=> dx^2+dy^2 <= r^2 ------------------
+// one warp per disc; a lane clears whole row spans [cx - hw, cx + hw], hw = floor(sqrt(r^2 - dy^2))
+__device__ __forceinline__ void disc_clear(uint8_t* __restrict__ mask, int pitch, int w, int h, float2 p, int r, int lane) {
+    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+    const int r2 = r * r;
+    for (int dy = -r + lane; dy <= r; dy += 32) {
+        const int y = cy + dy;
+        if (y < 0 || y >= h) continue;
+        const int rem = r2 - dy * dy;
+        int hw = (int)sqrtf((float)rem);
+        while (hw * hw > rem) hw--;
+        while ((hw + 1) * (hw + 1) <= rem) hw++;
+        int xa = max(cx - hw, 0), xb = min(cx + hw, w - 1);      // inclusive
+        uint8_t* row = mask + (size_t)y * pitch;
+        while (xa <= xb && (((uintptr_t)(row + xa)) & 3)) row[xa++] = 0;
+        for (; xa + 3 <= xb; xa += 4) *reinterpret_cast<unsigned*>(row + xa) = 0u;
+        while (xa <= xb) row[xa++] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_gftt_discs(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.y];
     if (!gftt_job_active(J)) return;
-    const int i = blockIdx.x;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= *J.n) return;
-    const float2 p = J.pts[i];
-    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
-    const int r = J.disc_radius, d = 2 * r + 1, r2 = r * r;
-    for (int t = threadIdx.x; t < d * d; t += blockDim.x) {
-        const int dy = t / d - r, dx = t - (t / d) * d - r;
-        const int x = cx + dx, y = cy + dy;
-        if (x < 0 || x >= J.w || y < 0 || y >= J.h) continue;
-        if (dx * dx + dy * dy <= r2) J.mask[(size_t)y * J.mask_pitch + x] = 0;
-    }
+    disc_clear(J.mask, J.mask_pitch, J.w, J.h, J.pts[i], J.disc_radius, threadIdx.x & 31);
 }
 
 __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n,
                                                       int r) {
-    const int i = blockIdx.x;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= *n) return;
-    const float2 p = pts[i];
-    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
-    const int d = 2 * r + 1, r2 = r * r;
-    for (int t = threadIdx.x; t < d * d; t += blockDim.x) {
-        const int dy = t / d - r, dx = t - (t / d) * d - r;
-        const int x = cx + dx, y = cy + dy;
-        if (x < 0 || x >= w || y < 0 || y >= h) continue;
-        if (dx * dx + dy * dy <= r2) mask[(size_t)y * pitch + x] = 0;
-    }
+    disc_clear(mask, pitch, w, h, pts[i], r, threadIdx.x & 31);
 }
 
 // ---- response map (cv::cornerMinEigenVal, blockSize 3, ksize 3), masked max, local maxima ------------------
@@ -575,11 +581,11 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
     (void)h_jobs;
     if (n_jobs <= 0) return DVFE_OK;
     {
-        dim3 blk(32, 8), grid(((max_w + 3) / 4 + 31) / 32, (max_h + 7) / 8, n_jobs);
+        dim3 blk(32, 8), grid(((max_w + 15) / 16 + 31) / 32, (max_h + 7) / 8, n_jobs);
         DVFE_LAUNCH(k_gftt_mask_fill, grid, blk, 0, st, d_jobs);
     }
     if (max_pts > 0) {
-        dim3 grid(max_pts, n_jobs);
+        dim3 grid((max_pts + 3) / 4, n_jobs);
         DVFE_LAUNCH(k_gftt_discs, grid, 128, 0, st, d_jobs);
     }
     if (h_jobs != nullptr && h_jobs[0].eig_in != nullptr) {     // seam op with an external response map
@@ -607,7 +613,7 @@ int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig
 int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n, int max_pts, int radius,
                      cudaStream_t st) {
     if (max_pts <= 0) return DVFE_OK;
-    DVFE_LAUNCH(k_disc_mask_op, max_pts, 128, 0, st, mask, pitch, w, h, pts, n, radius);
+    DVFE_LAUNCH(k_disc_mask_op, (max_pts + 3) / 4, 128, 0, st, mask, pitch, w, h, pts, n, radius);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

@@ -83,15 +83,81 @@ __device__ __forceinline__ unsigned load4(const uint8_t* __restrict__ row, int x
         T[6] = __byte_perm(A_hi, B_hi, 0x7632);                              \
     }
 
+// d = sum_i a.u8[i] * b.s8[i] + c
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+#define LK_WIN_BYTES (24 * 24 + 16)
+
+// Template of one run (7 pixels of window row `ry`, columns x0..x0+6) from the staged 24x24 window:
+// Scharr derivatives at the 8x2 taps the run's bilinear samples touch, computed with dp4a on 4-byte windows
+// (row filter and the vertical 3/10/3 resp. -1/+1 weights folded into the int8 tap weights), then the 14-bit
+// fixed-point bilinear samples of I, Ix, Iy.
+__device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win, int ry, int x0, bool valid, bool interior,
+                                                int ipx, int ipy, int lw, int lh, int iw00, int iw01, int iw10, int iw11,
+                                                int (&Ix)[LK_RUN], int (&Iy)[LK_RUN], int& c1, int& c2, int& sA11,
+                                                int& sA12, int& sA22) {
+    int gx0[8], gx1[8], gy0[8], gy1[8];      // d/dx and d/dy at tap rows ry, ry+1 ; tap columns x0..x0+7
+#pragma unroll
+    for (int j = 0; j < 8; j++) { gx0[j] = 0; gx1[j] = 0; gy0[j] = 0; gy1[j] = 0; }
+    unsigned Wa[8], Wb[8];                   // 4-byte windows of image rows ry+1 (= window row of the pixels) and ry+2
+    const int sh = (x0 & 3) * 8;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        // image row (ipy - 1 + ry + r): 12 bytes from window column x0 (= image column ipx - 1 + x0)
+        const unsigned* wp = reinterpret_cast<const unsigned*>(win + (ry + r) * 24 + (x0 & ~3));
+        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        unsigned R[3];
+        R[0] = __funnelshift_r(w0, w1, sh); R[1] = __funnelshift_r(w1, w2, sh); R[2] = __funnelshift_r(w2, w3, sh);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned W = (j & 3) ? __funnelshift_r(R[j >> 2], R[(j >> 2) + 1], 8 * (j & 3)) : R[j >> 2];
+            // bytes of W: I(x-1), I(x), I(x+1), - for tap column x = x0 + j of this image row
+            // d/dx = 3*hd(y-1) + 10*hd(y) + 3*hd(y+1), hd = I(x+1) - I(x-1);  d/dy = hs(y+1) - hs(y-1), hs = 3,10,3
+            if (r == 0) { gx0[j] = dp4a_us(W, 0x000300FD, gx0[j]); gy0[j] = dp4a_us(W, 0x00FDF6FD, gy0[j]); }
+            if (r == 1) { gx0[j] = dp4a_us(W, 0x000A00F6, gx0[j]); gx1[j] = dp4a_us(W, 0x000300FD, gx1[j]);
+                          gy1[j] = dp4a_us(W, 0x00FDF6FD, gy1[j]); Wa[j] = W; }
+            if (r == 2) { gx0[j] = dp4a_us(W, 0x000300FD, gx0[j]); gx1[j] = dp4a_us(W, 0x000A00F6, gx1[j]);
+                          gy0[j] = dp4a_us(W, 0x00030A03, gy0[j]); Wb[j] = W; }
+            if (r == 3) { gx1[j] = dp4a_us(W, 0x000300FD, gx1[j]); gy1[j] = dp4a_us(W, 0x00030A03, gy1[j]); }
+        }
+    }
+    if (!interior) {
+        // the derivative image has a ZERO border (cv::copyMakeBorder BORDER_CONSTANT): taps outside the image are 0
+        const bool r0 = (unsigned)(ipy + ry) < (unsigned)lh, r1 = (unsigned)(ipy + ry + 1) < (unsigned)lh;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const bool cv = (unsigned)(ipx + x0 + j) < (unsigned)lw;
+            if (!(cv && r0)) { gx0[j] = 0; gy0[j] = 0; }
+            if (!(cv && r1)) { gx1[j] = 0; gy1[j] = 0; }
+        }
+    }
+    const int W01 = (iw00 & 0xffff) | (iw01 << 16);
+    const int W23 = (iw10 & 0xffff) | (iw11 << 16);
+#pragma unroll
+    for (int j = 0; j < LK_RUN; j++) {
+        // pixel (x0 + j, ry): I taps are bytes 1,2 of the windows at column j of image rows ry+1 / ry+2 of the window
+        const unsigned T = __byte_perm(Wa[j], Wb[j], 0x6521);
+        const int ival = dp2a_hi_su(W23, T, dp2a_lo_su(W01, T, 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+        int ixv = (gx0[j] * iw00 + gx0[j + 1] * iw01 + gx1[j] * iw10 + gx1[j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+        int iyv = (gy0[j] * iw00 + gy0[j + 1] * iw01 + gy1[j] * iw10 + gy1[j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+        if (!valid) { ixv = 0; iyv = 0; }
+        Ix[j] = ixv; Iy[j] = iyv;
+        c1 += ival * ixv; c2 += ival * iyv;
+        sA11 += ixv * ixv; sA12 += ixv * iyv; sA22 += iyv * iyv;
+    }
+}
+
 __global__ void __launch_bounds__(LK_WARPS * 32, 4) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back) {
-    __shared__ __align__(16) uint8_t s_win[LK_WARPS][24 * 24];
-    __shared__ __align__(16) short2 s_der[LK_WARPS][22 * 22];
+    __shared__ __align__(16) uint8_t s_win[LK_WARPS][LK_WIN_BYTES];
     const LkGroup& G = groups[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * LK_WARPS + warp;
     if (i >= *G.n) return;
     uint8_t* __restrict__ win = s_win[warp];
-    short2* __restrict__ der = s_der[warp];
     const float FLT_SCALE = 1.f / (1 << 20);
 
     // this lane's two runs: run r -> window row r / 3, first column 7 * (r % 3)
@@ -137,55 +203,26 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) k_lk_track(const LkGroup* __
                 if (level == 0) st = 0;
                 continue;
             }
-            // ---- stage the 24x24 window of I around the patch; Scharr taps (zero outside the image) ----
+            // ---- stage the 24x24 window of I around the patch (rows ipy-1.., columns ipx-1..) ----
             __syncwarp();
             for (int t = lane; t < 24 * 6; t += 32) {          // 24 rows x 6 words, rows are 4-byte aligned in smem
                 const int r = t / 6, c4 = (t - r * 6) * 4;
                 *reinterpret_cast<unsigned*>(win + r * 24 + c4) = load4(Ipx + (ipy - 1 + r) * L.pitch, ipx - 1 + c4);
             }
             __syncwarp();
-            for (int t = lane; t < 22 * 22; t += 32) {
-                const int r = t / 22, c = t - r * 22;
-                const int gx = ipx + c, gy = ipy + r;
-                short2 d = make_short2(0, 0);
-                if (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) {
-                    const uint8_t* w0 = win + r * 24 + c;
-                    const int a00 = w0[0], a01 = w0[1], a02 = w0[2];
-                    const int a10 = w0[24], a12 = w0[26];
-                    const int a20 = w0[48], a21 = w0[49], a22 = w0[50];
-                    const int t0m = 3 * (a00 + a20) + 10 * a10, t0p = 3 * (a02 + a22) + 10 * a12;
-                    const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
-                    d.x = (short)(t0p - t0m);
-                    d.y = (short)(3 * (t1p + t1m) + 10 * t1c);
-                }
-                der[t] = d;
-            }
-            __syncwarp();
 
             float a = prevx - (float)ipx, b = prevy - (float)ipy;
             int iw00, iw01, iw10, iw11;
             lk_weights(a, b, iw00, iw01, iw10, iw11);
+            const bool interior = ipx >= 0 && ipy >= 0 && ipx + 22 <= L.w && ipy + 22 <= L.h;
 
-            int Iw[2][LK_RUN], Ix[2][LK_RUN], Iy[2][LK_RUN];
+            int Ix0[LK_RUN], Iy0[LK_RUN], Ix1[LK_RUN], Iy1[LK_RUN];
+            int c1 = 0, c2 = 0;          // sum I*Ix, sum I*Iy over this lane's pixels (constant over the iterations)
             int sA11 = 0, sA12 = 0, sA22 = 0;
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int y = q ? ry1 : ry0, x0 = q ? rx1 : rx0;
-                const bool valid = q ? has1 : true;
-#pragma unroll
-                for (int j = 0; j < LK_RUN; j++) {
-                    const int x = x0 + j;
-                    const uint8_t* w0 = win + (y + 1) * 24 + x + 1;
-                    const int ival = (w0[0] * iw00 + w0[1] * iw01 + w0[24] * iw10 + w0[25] * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                    const short2 d00 = der[y * 22 + x], d01 = der[y * 22 + x + 1];
-                    const short2 d10 = der[(y + 1) * 22 + x], d11 = der[(y + 1) * 22 + x + 1];
-                    int ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    int iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    if (!valid) { ixv = 0; iyv = 0; }
-                    Iw[q][j] = ival; Ix[q][j] = ixv; Iy[q][j] = iyv;
-                    sA11 += ixv * ixv; sA12 += ixv * iyv; sA22 += iyv * iyv;
-                }
-            }
+            lk_template_run(win, ry0, rx0, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
+                            sA11, sA12, sA22);
+            lk_template_run(win, ry1, rx1, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
+                            sA11, sA12, sA22);
             const float A11 = __ll2float_rn(warp_sum_i64(sA11)) * FLT_SCALE;
             const float A12 = __ll2float_rn(warp_sum_i64(sA12)) * FLT_SCALE;
             const float A22 = __ll2float_rn(warp_sum_i64(sA22)) * FLT_SCALE;
@@ -211,21 +248,30 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) k_lk_track(const LkGroup* __
                 const int W01 = (iw00 & 0xffff) | (iw01 << 16);
                 const int W23 = (iw10 & 0xffff) | (iw11 << 16);
                 const uint8_t* __restrict__ Jw = Jpx + iny * L.pitch;
-                int sb1 = 0, sb2 = 0;
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const uint8_t* rowA = Jw + (q ? roff1 : roff0);
-                    const int x = inx + (q ? rx1 : rx0);
+                // sum (J - I) * Ix = sum J * Ix - sum I * Ix
+                int sb1 = -c1, sb2 = -c2;
+                {
                     unsigned A_lo, A_hi, B_lo, B_hi, T[LK_RUN];
-                    load8(rowA, x, A_lo, A_hi);
-                    load8(rowA + L.pitch, x, B_lo, B_hi);
+                    load8(Jw + roff0, inx + rx0, A_lo, A_hi);
+                    load8(Jw + roff0 + L.pitch, inx + rx0, B_lo, B_hi);
                     LK_TAPS(A_lo, A_hi, B_lo, B_hi, T);
 #pragma unroll
                     for (int j = 0; j < LK_RUN; j++) {
-                        const int v = dp2a_hi_su(W23, T[j], dp2a_lo_su(W01, T[j], 1 << (W_BITS - 5 - 1)));
-                        const int diff = (v >> (W_BITS - 5)) - Iw[q][j];
-                        sb1 += diff * Ix[q][j];
-                        sb2 += diff * Iy[q][j];
+                        const int v = dp2a_hi_su(W23, T[j], dp2a_lo_su(W01, T[j], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        sb1 += v * Ix0[j];
+                        sb2 += v * Iy0[j];
+                    }
+                }
+                {
+                    unsigned A_lo, A_hi, B_lo, B_hi, T[LK_RUN];
+                    load8(Jw + roff1, inx + rx1, A_lo, A_hi);
+                    load8(Jw + roff1 + L.pitch, inx + rx1, B_lo, B_hi);
+                    LK_TAPS(A_lo, A_hi, B_lo, B_hi, T);
+#pragma unroll
+                    for (int j = 0; j < LK_RUN; j++) {
+                        const int v = dp2a_hi_su(W23, T[j], dp2a_lo_su(W01, T[j], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        sb1 += v * Ix1[j];
+                        sb2 += v * Iy1[j];
                     }
                 }
                 const float b1 = __ll2float_rn(warp_sum_i64(sb1)) * FLT_SCALE;
