@@ -10,8 +10,9 @@ points with min-distance 25, left->right LK, undistortion, velocity).  A "step" 
 rank by one frame.  Streams are independent, so N GPUs run N x 64 streams with no collective ("scaling": weak).
 
   value  frames/s with the frames already resident in HBM (dvfe_track_image_device), outputs read back;
-  e2e    frames/s through the host-buffer C-ABI call (dvfe_track_image): pinned host images are copied to the
-         device and the FeatureFrame records are copied back inside the timed region.
+  e2e    frames/s through the host-buffer C-ABI calls (dvfe_track_image_async + dvfe_wait, the pipelined form of
+         dvfe_track_image): every step copies its pinned host images to the device and its FeatureFrame records
+         back to the host inside the timed region; the H2D of frame k+1 overlaps the kernels of frame k.
 Timing: CUDA events on the stream the kernels run on, barrier + synchronize on both sides, max over ranks.
 Each step reads a different 118 MB set of frames plus its pyramids (working set >> the 126 MB L2), so no
 explicit L2 flush is needed ("l2": "inputs_larger_than_L2").
@@ -132,7 +133,7 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
     """Compulsory HBM bytes of one launch group, SURVEY.md §8(d) (P = W*H pixels per image):
        pyramid     read P + write the padded level 0 (P) + levels 1..3 (0.328 P), per image, 2 images per stream
        lk_*        both pyramids of the pair read once (2 * 1.328 P) + 17 B per point (8 in, 8 out, 1 status)
-       gftt        read P (image) + mask P written and read + response map 4P written and read
+       gftt        read P (image) + mask P written and read (the response map stays on chip) + 8 B per candidate
     """
     P = float(W * H)
     pyr = sum(1.0 / 4 ** l for l in range(n_levels))
@@ -141,7 +142,7 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
     if stage in ("lk_temporal", "lk_stereo"):
         return S * 2 * P * pyr + 17.0 * n_pts_total
     if stage == "gftt":
-        return S * (P + 2 * P + 8 * P)
+        return S * (P + 2 * P) + 8.0 * 20000 * S
     return 0.0
 
 
@@ -224,11 +225,18 @@ def run_dvfe(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.warmup, args.warmup + args.steps):
-            trk.track_image(host_np[order[i], 0], host_np[order[i], 1], times[i])
+        # the public pipelined call: the H2D of frame k+1 overlaps the kernels of frame k; every step's records
+        # are read back to the host (dvfe_wait) inside the timed region
+        first = args.warmup
+        trk.track_image_async(host_np[order[first], 0], host_np[order[first], 1], times[first])
+        for i in range(first + 1, first + args.steps):
+            trk.track_image_async(host_np[order[i], 0], host_np[order[i], 1], times[i])
+            trk.wait()
+        trk.wait()
         e1.record(stream)
         barrier()
         ms_e2e = e0.elapsed_time(e1)
+        n_obs_e2e = sum(len(trk.features(s)) for s in range(S))
     trk.close()
 
     t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device=dev)

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvfe.so")
+LIB_PATH = os.environ.get("DVFE_LIB", os.path.join(_HERE, "libdvfe.so"))   # DVFE_LIB: development override
 
 DVFE_OK = 0
 ERRORS = {-1: "DVFE_ERR_INVALID", -2: "DVFE_ERR_CUDA", -3: "DVFE_ERR_CONFIG", -4: "DVFE_ERR_CAPACITY",
@@ -68,7 +68,7 @@ class State(C.Structure):
 # every symbol include/dvfe.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "dvfe_create", "dvfe_destroy", "dvfe_config_from_yaml", "dvfe_last_error", "dvfe_version",
-    "dvfe_kernel_launches", "dvfe_set_stream", "dvfe_profile", "dvfe_profile_read", "dvfe_track_image", "dvfe_track_image_device", "dvfe_track_semantic_image",
+    "dvfe_kernel_launches", "dvfe_set_stream", "dvfe_profile", "dvfe_profile_read", "dvfe_track_image", "dvfe_track_image_async", "dvfe_wait", "dvfe_track_image_device", "dvfe_track_semantic_image",
     "dvfe_insts_track", "dvfe_get_features", "dvfe_insts_output", "dvfe_get_state", "dvfe_set_state",
     "dvfe_op_build_pyramid", "dvfe_op_lk", "dvfe_op_min_eigen_val", "dvfe_op_good_features",
     "dvfe_op_disc_mask", "dvfe_op_erode_rect", "dvfe_op_lift_projective",
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
         L.dvfe_profile.argtypes = [C.c_void_p, C.c_int]
         L.dvfe_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]
         L.dvfe_track_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.dvfe_track_image_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.dvfe_wait.argtypes = [C.c_void_p]
         L.dvfe_track_image_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.dvfe_track_semantic_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                                 C.c_void_p, C.c_void_p]

@@ -129,10 +129,16 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
     int best = INT_MIN;
 
     const int y_last = y1 + (EMIT ? 2 : 1);
+    uint8_t mk1 = 0;                                                 // mask of row y-3 at this column
     for (int y = y0 - 3; y <= y_last; y++) {
-        // ---- image row y (REFLECT_101), horizontal neighbours by shuffle ----
-        const size_t ro = (size_t)reflect101(y, h) * pitch;
+        // ---- image row y (REFLECT_101; y is within 3 rows of the image), horizontal neighbours by shuffle ----
+        const int ry = y < 0 ? -y : (y >= h ? 2 * (h - 1) - y : y);
+        const int ro = ry * pitch;
         const float c = (float)__ldg(col + ro);
+        const int yl = y - 2;
+        // mask of row yl, needed for the masked maximum now and for the candidate test of the next step
+        uint8_t mk2 = 0;
+        if (EMIT && owned_col && yl >= y0 && yl < y1) mk2 = __ldg(mask + yl * mask_pitch + x);
         float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
         if (lane == 0) l = (float)__ldg(col_edge + ro);
         if (lane == 31) r = (float)__ldg(col_edge + ro);
@@ -162,10 +168,11 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
         double h2y = ((double)lxy + (double)pxy) + (double)rxy;
         double h2z = ((double)lyy + (double)pyy) + (double)ryy;
         // ---- lambda of row yl = y-2: vertical 3-sum top to bottom; rows -1 / h take rows 1 / h-2 ----
-        const int yl = y - 2;
         double ax = h0x, ay = h0y, az = h0z;
-        if (yl == 0) { ax = h2x; ay = h2y; az = h2z; }
-        if (yl == h - 1) { h2x = h0x; h2y = h0y; h2z = h0z; }
+        if (yl == 0 || yl == h - 1) {
+            if (yl == 0) { ax = h2x; ay = h2y; az = h2z; }
+            if (yl == h - 1) { h2x = h0x; h2y = h0y; h2z = h0z; }
+        }
         const float cxx = (float)((ax + h1x) + h2x);
         const float cxy = (float)((ay + h1y) + h2y);
         const float cyy = (float)((az + h1z) + h2z);
@@ -177,7 +184,7 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
             lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
             if (owned_col && yl >= y0 && yl < y1) {
                 if (WRITE_EIG) eig[(size_t)yl * w + x] = lam;
-                if (EMIT && mask[(size_t)yl * mask_pitch + x] != 0) best = max(best, f2ord(lam));
+                if (EMIT && mk2 != 0) best = max(best, f2ord(lam));
             }
         }
         if (!EMIT) continue;
@@ -188,10 +195,10 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
         bool is_cand = false;
         if (cand_col && yc >= y0 && yc < y1 && yc >= 1 && yc < h - 1 && lam1 != 0.f) {
             const float m = fmaxf(fmaxf(hm0, hm2), lr1);
-            if (!(m > lam1)) is_cand = mask[(size_t)yc * mask_pitch + x] != 0;
+            if (!(m > lam1)) is_cand = mk1 != 0;
         }
         const float v = lam1;
-        hm0 = hm1; hm1 = hm2; lam1 = lam; lr1 = lr2;
+        hm0 = hm1; hm1 = hm2; lam1 = lam; lr1 = lr2; mk1 = mk2;
         const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
         if (ballot) {
             int base = 0;

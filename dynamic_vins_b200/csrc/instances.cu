@@ -185,16 +185,17 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
         return DVFE_ERR_INVALID;
     }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
     InstanceState& I = *t->inst;
     InstStream& S = I.streams[stream];
     cudaStream_t st = t->st;
     const int W = t->W, H = t->H, MI = I.MI, cap = I.cap;
     const size_t P = I.P;
     const size_t base_set = (size_t)stream * MI;
-    // the frame uploaded by the last background step: left = pyr[1 - cur], right = pyr[2]
+    // the frame uploaded by the last background step
     const PyrLevel& L0 = t->desc.lv[0];
-    const uint8_t* left_pyr = t->pyr[1 - t->cur] + (size_t)stream * t->desc.bytes;
-    const uint8_t* right_pyr = t->pyr[2] + (size_t)stream * t->desc.bytes;
+    const uint8_t* left_pyr = t->left_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
+    const uint8_t* right_pyr = t->right_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
     const uint8_t* left_px = left_pyr + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
     const bool stereo_now = t->cfg.stereo && t->last_has_right;
 

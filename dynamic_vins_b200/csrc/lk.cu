@@ -23,6 +23,9 @@
 #include "kernels.cuh"
 
 #define LK_WARPS 4
+#ifndef LK_MIN_BLOCKS
+#define LK_MIN_BLOCKS 6          // resident blocks per SM the register allocation targets
+#endif
 #define LK_RUN 7                  // pixels per run; 3 runs per window row
 #define W_BITS 14
 
@@ -151,7 +154,7 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
     }
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32, 4) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back) {
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back) {
     __shared__ __align__(16) uint8_t s_win[LK_WARPS][LK_WIN_BYTES];
     const LkGroup& G = groups[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -146,9 +146,15 @@ extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
 
 int dvfe_tracker::init() {
     DVFE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[i]));
+    DVFE_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    for (int p = 0; p < 2; p++) {
+        for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[p][i]));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_up[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_done[p], cudaEventDisableTiming));
+    }
     const size_t P = (size_t)W * H;
-    for (int s = 0; s < 3; s++) DVFE_CHECK(dmalloc(&pyr[s], (size_t)B * desc.bytes));
+    for (int s = 0; s < 3; s++) DVFE_CHECK(dmalloc(&pyrL[s], (size_t)B * desc.bytes));
+    for (int s = 0; s < 2; s++) DVFE_CHECK(dmalloc(&pyrR[s], (size_t)B * desc.bytes));
     DVFE_CHECK(alloc_point_sets(&bg, B, cap));
     DVFE_CHECK(dmalloc(&d_next_id, (size_t)B));
     {
@@ -156,13 +162,15 @@ int dvfe_tracker::init() {
         DVFE_CUDA(cudaMemcpy(d_next_id, ones.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     DVFE_CHECK(dmalloc(&d_dt, (size_t)B));
-    DVFE_CUDA(cudaMallocHost((void**)&h_dt, B * sizeof(double)));
     prev_time.assign(B, 0.0);
     DVFE_CHECK(dmalloc(&d_obs, (size_t)B * 2 * cap));
     DVFE_CHECK(dmalloc(&d_nobs, (size_t)B));
-    DVFE_CUDA(cudaMallocHost((void**)&h_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs)));
-    DVFE_CUDA(cudaMallocHost((void**)&h_nobs, B * sizeof(int)));
-    memset(h_nobs, 0, B * sizeof(int));
+    for (int p = 0; p < 2; p++) {
+        DVFE_CUDA(cudaMallocHost((void**)&h_dt[p], B * sizeof(double)));
+        DVFE_CUDA(cudaMallocHost((void**)&h_obs[p], (size_t)B * 2 * cap * sizeof(dvfe_obs)));
+        DVFE_CUDA(cudaMallocHost((void**)&h_nobs[p], B * sizeof(int)));
+        memset(h_nobs[p], 0, B * sizeof(int));
+    }
     DVFE_CHECK(dmalloc(&d_region, (size_t)B * P));
     DVFE_CHECK(dmalloc(&d_region_tmp, (size_t)B * P));
     DVFE_CHECK(dmalloc(&d_inv_in, (size_t)B * P));
@@ -170,11 +178,11 @@ int dvfe_tracker::init() {
     DVFE_CUDA(cudaMallocHost((void**)&h_exist, B * sizeof(int)));
     DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
 
-    // LK groups: [parity][temporal raw | temporal semantic | stereo]
+    // LK groups: [phase][temporal raw | temporal semantic | stereo]
     std::vector<LkGroup> g(B);
-    for (int par = 0; par < 2; par++) {
-        uint8_t* cur = pyr[par];
-        uint8_t* prev = pyr[1 - par];
+    for (int ph = 0; ph < 6; ph++) {
+        uint8_t* cur = left_slot(ph);
+        uint8_t* prev = left_slot(ph + 2);
         for (int kind = 0; kind < 3; kind++) {
             for (int s = 0; s < B; s++) {
                 LkGroup& G = g[s];
@@ -188,24 +196,24 @@ int dvfe_tracker::init() {
                     if (kind == 1) { G.mask = d_region + (size_t)s * P; G.mask_pitch = W; }
                 } else {
                     G.pyrA = cur + (size_t)s * desc.bytes;
-                    G.pyrB = pyr[2] + (size_t)s * desc.bytes;
+                    G.pyrB = right_slot(ph) + (size_t)s * desc.bytes;
                     G.ptsA = bg.pts + o; G.ptsB = bg.rpts + o; G.status = bg.rstatus + o;
                 }
                 G.n = bg.n + s;
             }
-            DVFE_CHECK(dmalloc(&d_groups[par][kind], (size_t)B));
-            DVFE_CUDA(cudaMemcpy(d_groups[par][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
+            DVFE_CHECK(dmalloc(&d_groups[ph][kind], (size_t)B));
+            DVFE_CUDA(cudaMemcpy(d_groups[ph][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
         }
     }
-    // GFTT jobs: [parity][raw | semantic]
+    // GFTT jobs: [phase][raw | semantic]
     std::vector<GfttJob> jobs(B);
-    for (int par = 0; par < 2; par++)
+    for (int ph = 0; ph < 6; ph++)
         for (int kind = 0; kind < 2; kind++) {
             for (int s = 0; s < B; s++) {
                 GfttJob& J = jobs[s];
                 memset(&J, 0, sizeof(J));
                 const PyrLevel& L0 = desc.lv[0];
-                J.img = pyr[par] + (size_t)s * desc.bytes + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+                J.img = left_slot(ph) + (size_t)s * desc.bytes + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
                 J.img_pitch = L0.pitch;
                 J.w = W; J.h = H;
                 if (kind == 1) { J.region_mask = d_region + (size_t)s * P; J.region_pitch = W; }
@@ -219,8 +227,8 @@ int dvfe_tracker::init() {
                 J.min_dist = (float)cfg.min_dist;
                 J.quality = 0.01;
             }
-            DVFE_CHECK(dmalloc(&d_jobs[par][kind], (size_t)B));
-            DVFE_CUDA(cudaMemcpy(d_jobs[par][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
+            DVFE_CHECK(dmalloc(&d_jobs[ph][kind], (size_t)B));
+            DVFE_CUDA(cudaMemcpy(d_jobs[ph][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
         }
     DVFE_CHECK(init_instances());
     DVFE_CUDA(cudaDeviceSynchronize());
@@ -231,82 +239,112 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     if (!t) return;
     cudaSetDevice(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
-    for (int s = 0; s < 3; s++) cudaFree(t->pyr[s]);
+    if (t->cs) cudaStreamSynchronize(t->cs);
+    for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
+    for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
-    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFreeHost(t->h_dt);
-    cudaFree(t->d_obs); cudaFree(t->d_nobs); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_nobs);
+    cudaFree(t->d_next_id); cudaFree(t->d_dt);
+    cudaFree(t->d_obs); cudaFree(t->d_nobs);
+    for (int p = 0; p < 2; p++) {
+        cudaFreeHost(t->h_dt[p]); cudaFreeHost(t->h_obs[p]); cudaFreeHost(t->h_nobs[p]);
+        if (t->ev_up[p]) cudaEventDestroy(t->ev_up[p]);
+        if (t->ev_done[p]) cudaEventDestroy(t->ev_done[p]);
+        for (int i = 0; i <= dvfe_tracker::ST_COUNT; i++) if (t->ev[p][i]) cudaEventDestroy(t->ev[p][i]);
+    }
     cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_inv_in); cudaFree(t->d_exist);
     cudaFreeHost(t->h_exist);
     free_gftt_scratch(&t->gsc);
-    for (int p = 0; p < 2; p++) {
+    for (int p = 0; p < 6; p++) {
         for (int k = 0; k < 3; k++) cudaFree(t->d_groups[p][k]);
         for (int k = 0; k < 2; k++) cudaFree(t->d_jobs[p][k]);
     }
     t->free_instances();
-    for (int i = 0; i <= dvfe_tracker::ST_COUNT; i++) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->cs) cudaStreamDestroy(t->cs);
     if (t->st && t->own_stream) cudaStreamDestroy(t->st);
     delete t;
 }
 
-// The frame step with the images already on the device (dense or pitched, strided per stream).
-int dvfe_tracker::step_device(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
-                              const double* time0, bool semantic, bool level0_in_place, bool has_right) {
-    DVFE_CUDA(cudaSetDevice(cfg.device));
+// ---- the frame step --------------------------------------------------------------------------------------
+// submit() only enqueues: optional device-side copy into level 0, pyramids, LK, detection, post-processing and the
+// D2H of the records of step k, all on the compute stream; nothing blocks the host.  Two steps may be in flight,
+// so the H2D of step k+1 (upload stream) overlaps the kernels of step k.
+int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
+                         const double* time0, bool semantic, bool level0_in_place, bool has_right) {
+    const long k = frames;
+    const int ph = (int)(k % 6), par = (int)(k % 2);
     const bool stereo_now = cfg.stereo && (d_right != nullptr || (level0_in_place && has_right));
-    const int par = cur;
-    for (int s = 0; s < B; s++) h_dt[s] = time0[s] - prev_time[s];       // cur_time - prev_time
-    DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int s = 0; s < B; s++) h_dt[par][s] = time0[s] - prev_time[s];       // cur_time - prev_time
+    DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt[par], B * sizeof(double), cudaMemcpyHostToDevice, st));
+    prof_step[par] = prof;
+    auto mark = [&](int i) { if (prof) cudaEventRecord(ev[par][i], st); };
 
     mark(0);
     PyrImgSet set;
     set.src[0] = d_left; set.src[1] = d_right;
-    set.dst[0] = pyr[par]; set.dst[1] = pyr[2];
+    set.dst[0] = left_slot(k); set.dst[1] = right_slot(k);
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
     DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
-    if (frames > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
-        DVFE_CHECK(launch_lk(d_groups[par][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+    if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
+        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
     mark(ST_LK_TEMPORAL + 1);
-    if (frames > 0)   // ReduceVector x4 + track_cnt++
+    if (k > 0)   // ReduceVector x4 + track_cnt++
         DVFE_CHECK(launch_compact(bg, B, cap, st));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
-    DVFE_CHECK(launch_gftt(d_jobs[par][semantic ? 1 : 0], nullptr, B, W, H, cap, st));
+    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st));
     mark(ST_GFTT + 1);
     // UndistortedPts(cam0) + PtsVelocity
     DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
     mark(ST_LEFT_POST + 1);
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
-        DVFE_CHECK(launch_lk(d_groups[par][2], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st));
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs, d_nobs, st));
     mark(ST_PACK + 1);
-    DVFE_CUDA(cudaMemcpyAsync(h_nobs, d_nobs, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    DVFE_CUDA(cudaMemcpyAsync(h_obs, d_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, st));
+    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par], d_nobs, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DVFE_CUDA(cudaMemcpyAsync(h_obs[par], d_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, st));
     mark(ST_D2H + 1);
-    DVFE_CUDA(cudaStreamSynchronize(st));
-    if (prof) {
-        for (int i = 0; i < ST_COUNT; i++) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) prof_ms[i] += ms;
-        }
-        prof_steps++;
-    }
+    DVFE_CUDA(cudaEventRecord(ev_done[par], st));
     for (int s = 0; s < B; s++) prev_time[s] = time0[s];
     last_has_right = stereo_now;
-    cur = 1 - cur;
     frames++;
     return DVFE_OK;
 }
 
-// Host images -> level 0 of the pyramids, one pitched 3-D copy per camera (no staging buffer, no copy kernel).
+int dvfe_tracker::wait_one() {
+    if (completed >= frames) return DVFE_OK;
+    const int par = (int)(completed % 2);
+    DVFE_CUDA(cudaEventSynchronize(ev_done[par]));
+    if (prof_step[par]) {
+        for (int i = 0; i < ST_COUNT; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[par][i], ev[par][i + 1]) == cudaSuccess) prof_ms[i] += ms;
+        }
+        prof_steps++;
+    }
+    out_slot = par;
+    completed++;
+    return DVFE_OK;
+}
+
+int dvfe_tracker::wait_all() {
+    while (completed < frames) DVFE_CHECK(wait_one());
+    return DVFE_OK;
+}
+
+// Host images -> level 0 of the pyramids of the NEXT step, one pitched 3-D copy per camera on the upload stream
+// (no staging buffer, no copy kernel).  The target slots were last read two steps ago.
 int dvfe_tracker::upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
+    const long k = frames;
+    const int par = (int)(k % 2);
+    while (frames - completed >= 2) DVFE_CHECK(wait_one());      // slot reuse: step k-2 must be finished
     const PyrLevel& L0 = desc.lv[0];
     const size_t inner = L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
     for (int cam = 0; cam < 2; cam++) {
         const uint8_t* src = cam ? right : left;
         if (!src) continue;
-        uint8_t* dst = (cam ? pyr[2] : pyr[cur]) + inner;
+        uint8_t* dst = (cam ? right_slot(k) : left_slot(k)) + inner;
         if (stream_stride % (size_t)pitch == 0) {
             cudaMemcpy3DParms p;
             memset(&p, 0, sizeof(p));
@@ -314,13 +352,15 @@ int dvfe_tracker::upload_in_place(const uint8_t* left, const uint8_t* right, siz
             p.dstPtr = make_cudaPitchedPtr((void*)dst, (size_t)L0.pitch, (size_t)W, desc.bytes / (size_t)L0.pitch);
             p.extent = make_cudaExtent((size_t)W, (size_t)H, (size_t)B);
             p.kind = cudaMemcpyHostToDevice;
-            DVFE_CUDA(cudaMemcpy3DAsync(&p, st));
+            DVFE_CUDA(cudaMemcpy3DAsync(&p, cs));
         } else {
             for (int s = 0; s < B; s++)
                 DVFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)s * desc.bytes, L0.pitch, src + s * stream_stride, pitch, W,
-                                            (size_t)H, cudaMemcpyHostToDevice, st));
+                                            (size_t)H, cudaMemcpyHostToDevice, cs));
         }
     }
+    DVFE_CUDA(cudaEventRecord(ev_up[par], cs));
+    DVFE_CUDA(cudaStreamWaitEvent(st, ev_up[par], 0));
     return DVFE_OK;
 }
 
@@ -332,18 +372,33 @@ static int check_step_args(dvfe_tracker* t, const uint8_t* left, int pitch, cons
     return DVFE_OK;
 }
 
-extern "C" int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
-                                int pitch, const double* time0) {
+extern "C" int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
+                                      int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
-    return t->step_device(nullptr, nullptr, 0, 0, time0, false, true, right != nullptr);
+    return t->submit(nullptr, nullptr, 0, 0, time0, false, true, right != nullptr);
+}
+
+extern "C" int dvfe_wait(dvfe_tracker* t) {
+    if (!t) { dvfe_set_error("wait: null tracker"); return DVFE_ERR_INVALID; }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    return t->wait_one();
+}
+
+extern "C" int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
+                                int pitch, const double* time0) {
+    DVFE_CHECK(dvfe_track_image_async(t, left, right, stream_stride, pitch, time0));
+    return t->wait_all();
 }
 
 extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
                                        size_t stream_stride, int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, d_left, pitch, time0));
-    return t->step_device(d_left, d_right, stream_stride, pitch, time0, false);
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
+    DVFE_CHECK(t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr));
+    return t->wait_all();
 }
 
 extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right,
@@ -352,33 +407,32 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     if (!exist_inst) { dvfe_set_error("track_semantic_image: exist_inst is null"); return DVFE_ERR_INVALID; }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
     const size_t P = (size_t)t->W * t->H;
     DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
-    bool any = false;
     for (int s = 0; s < t->B; s++) {
         t->h_exist[s] = exist_inst[s] ? 1 : 0;
-        any |= exist_inst[s] != 0;
         if (exist_inst[s]) {
             if (!inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
             DVFE_CUDA(cudaMemcpy2DAsync(t->d_inv_in + s * P, t->W, inv_merge_mask + s * stream_stride, pitch, t->W,
                                         (size_t)t->H, cudaMemcpyHostToDevice, t->st));
         }
     }
-    (void)any;
     DVFE_CUDA(cudaMemcpyAsync(t->d_exist, t->h_exist, t->B * sizeof(int), cudaMemcpyHostToDevice, t->st));
     // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772)
     const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
     DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
                                  t->d_exist, t->st));
-    return t->step_device(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr);
+    DVFE_CHECK(t->submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr));
+    return t->wait_all();
 }
 
 extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out) {
     if (!t || stream < 0 || stream >= t->B || !n_out) { dvfe_set_error("get_features: bad argument"); return DVFE_ERR_INVALID; }
-    const int n = t->h_nobs[stream];
+    const int n = t->h_nobs[t->out_slot][stream];
     *n_out = n;
     if (n > cap) { dvfe_set_error("get_features: %d records, capacity %d", n, cap); return DVFE_ERR_CAPACITY; }
-    if (n > 0 && out) memcpy(out, t->h_obs + (size_t)stream * 2 * t->cap, (size_t)n * sizeof(dvfe_obs));
+    if (n > 0 && out) memcpy(out, t->h_obs[t->out_slot] + (size_t)stream * 2 * t->cap, (size_t)n * sizeof(dvfe_obs));
     return DVFE_OK;
 }
 
@@ -386,6 +440,7 @@ extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int
 extern "C" int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* stt, int cap) {
     if (!t || !stt || stream < 0 || stream >= t->B) { dvfe_set_error("get_state: bad argument"); return DVFE_ERR_INVALID; }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
     DVFE_CUDA(cudaStreamSynchronize(t->st));
     int n = 0;
     DVFE_CUDA(cudaMemcpy(&n, t->bg.n + stream, sizeof(int), cudaMemcpyDeviceToHost));
@@ -411,6 +466,7 @@ extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt
         return DVFE_ERR_INVALID;
     }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
     DVFE_CUDA(cudaStreamSynchronize(t->st));
     const int n = stt->n;
     const size_t o = (size_t)stream * t->cap;
@@ -431,6 +487,7 @@ extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt
 extern "C" int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream) {
     if (!t) { dvfe_set_error("set_stream: null tracker"); return DVFE_ERR_INVALID; }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
     DVFE_CUDA(cudaStreamSynchronize(t->st));
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     t->st = (cudaStream_t)cuda_stream;

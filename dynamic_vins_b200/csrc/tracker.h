@@ -26,43 +26,55 @@ struct InstanceState;   // instances.cu
 struct dvfe_tracker {
     dvfe_config cfg{};
     int B = 0, W = 0, H = 0, cap = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;                       // compute stream (caller-replaceable)
+    cudaStream_t cs = nullptr;                       // upload stream: H2D of step k+1 overlaps the kernels of step k
+    bool own_stream = true;
     PyrDesc desc{};
     CamParams cam0{}, cam1{};
-    uint8_t* pyr[3] = {nullptr, nullptr, nullptr};   // left (even frames), left (odd frames), right
-    int cur = 0;                                     // pyr[cur] receives the current left image
-    long frames = 0;
-    bool last_has_right = false;                     // the last uploaded frame had a right image
+    // Pyramids: 3 left slots (current / previous / being uploaded) and 2 right slots.  Step k uses
+    // left[k % 3] (previous = left[(k + 2) % 3]) and right[k % 2]; "phase" = k % 6 selects the descriptor set.
+    uint8_t* pyrL[3] = {nullptr, nullptr, nullptr};
+    uint8_t* pyrR[2] = {nullptr, nullptr};
+    long frames = 0;                                 // steps submitted
+    long completed = 0;                              // steps whose outputs have been waited for
+    bool last_has_right = false;                     // the last submitted frame had a right image
     PointSetArrays bg{};                             // background point sets, one per stream
     uint32_t* d_next_id = nullptr;                   // [B] InstFeat::global_id_count per stream
     double* d_dt = nullptr;
-    double* h_dt = nullptr;
+    double* h_dt[2] = {nullptr, nullptr};
     std::vector<double> prev_time;
     dvfe_obs* d_obs = nullptr;
-    dvfe_obs* h_obs = nullptr;
+    dvfe_obs* h_obs[2] = {nullptr, nullptr};         // pinned, one per in-flight step
     int* d_nobs = nullptr;
-    int* h_nobs = nullptr;
+    int* h_nobs[2] = {nullptr, nullptr};
+    int out_slot = 0;                                // which h_obs holds the newest completed step
+    cudaEvent_t ev_up[2] = {}, ev_done[2] = {};
     uint8_t *d_region = nullptr, *d_region_tmp = nullptr, *d_inv_in = nullptr;
     int* d_exist = nullptr;
     int* h_exist = nullptr;
     GfttScratch gsc{};
-    LkGroup* d_groups[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    GfttJob* d_jobs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    LkGroup* d_groups[6][3] = {};                    // [phase][temporal raw | temporal semantic | stereo]
+    GfttJob* d_jobs[6][2] = {};                      // [phase][raw | semantic]
     InstanceState* inst = nullptr;
-    bool own_stream = true;
 
-    // per-stage device timers
+    // per-stage device timers (one event set per in-flight step)
     enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT, ST_LEFT_POST, ST_LK_STEREO, ST_PACK, ST_D2H, ST_COUNT };
     bool prof = false;
-    cudaEvent_t ev[ST_COUNT + 1] = {};
+    bool prof_step[2] = {false, false};
+    cudaEvent_t ev[2][ST_COUNT + 1] = {};
     double prof_ms[ST_COUNT] = {};
     long prof_steps = 0;
-    void mark(int i) { if (prof) cudaEventRecord(ev[i], st); }
+
+    uint8_t* left_slot(long k) const { return pyrL[k % 3]; }
+    uint8_t* right_slot(long k) const { return pyrR[k % 2]; }
 
     int init();
-    int upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
-    int step_device(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
-                    bool semantic, bool level0_in_place = false, bool has_right = false);
     int init_instances();
     void free_instances();
+    int upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
+    // enqueue one frame step (no host synchronisation); at most two steps are in flight
+    int submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
+               bool semantic, bool level0_in_place, bool has_right);
+    int wait_one();                                  // oldest in-flight step -> outputs readable
+    int wait_all();
 };

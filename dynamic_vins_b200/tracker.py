@@ -110,6 +110,18 @@ class BatchTracker:
         t = self._times(time0)
         L.check(L.lib().dvfe_track_image(self._h, L.ptr(l), L.ptr(r), self.H * self.W, self.W, L.ptr(t)))
 
+    def track_image_async(self, left: np.ndarray, right: Optional[np.ndarray], time0) -> None:
+        """pipelined: enqueue the step and return; the arrays must stay alive until the matching wait()"""
+        l = self._batch(left, self.B, self.H, self.W)
+        r = self._batch(right, self.B, self.H, self.W)
+        t = self._times(time0)
+        self._keep = (l, r, t, getattr(self, "_keep", None) and self._keep[:3])
+        L.check(L.lib().dvfe_track_image_async(self._h, L.ptr(l), L.ptr(r), self.H * self.W, self.W, L.ptr(t)))
+
+    def wait(self) -> None:
+        """block until the oldest in-flight step is finished; features() then returns its records"""
+        L.check(L.lib().dvfe_wait(self._h))
+
     def track_image_device(self, d_left: int, d_right: int, stream_stride: int, pitch: int, time0) -> None:
         """d_left/d_right: device pointers (ints), e.g. torch tensor .data_ptr()."""
         t = self._times(time0)

@@ -131,6 +131,15 @@ int dvfe_profile_read(dvfe_tracker* t, const char** names, double* total_ms, lon
 int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch,
                      const double* time0);
 
+/* Pipelined form of dvfe_track_image: uploads and enqueues the step and returns without waiting.  Up to two steps
+ * may be in flight, so the host-to-device copy of frame k+1 overlaps the kernels of frame k (the call blocks only
+ * while two earlier steps are still unfinished).  dvfe_wait() blocks until the OLDEST unfinished step is done and
+ * makes its records the ones dvfe_get_features returns.  `left`/`right` must stay valid until that step is waited
+ * for.  dvfe_track_image == dvfe_track_image_async + dvfe_wait. */
+int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch,
+                           const double* time0);
+int dvfe_wait(dvfe_tracker* t);
+
 /* Same step with the images already resident in device memory (no H2D inside). */
 int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride,
                             int pitch, const double* time0);

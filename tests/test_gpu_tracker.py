@@ -339,3 +339,28 @@ def test_cpp_reference_shaped_api(tmp_path):
             vals = np.array([float(x) for x in tok[2:]])
             ref = np.concatenate([o[1] for o in obs])
             assert len(vals) == len(ref) and np.abs(vals[3:5] - ref[3:5]).max() <= POS_TOL
+
+
+def test_pipelined_async_equals_sync():
+    """dvfe_track_image_async / dvfe_wait (two steps in flight, upload overlapping compute) gives the same records
+    as the synchronous call, step by step"""
+    name, B, T = "c2_kitti_stereo", 2, 7
+    streams = [synth.make_stream(name, 10 + s) for s in range(B)]
+    frames = [[s.frame(k) for s in streams] for k in range(T)]
+    L = [np.stack([f.gray0 for f in fr]) for fr in frames]
+    R = [np.stack([f.gray1 for f in fr]) for fr in frames]
+    sync, pipe = BatchTracker(cfg_of(name, n_streams=B)), BatchTracker(cfg_of(name, n_streams=B))
+    want = []
+    for k in range(T):
+        sync.track_image(L[k], R[k], frames[k][0].time0)
+        want.append([sync.features(s).tobytes() for s in range(B)])
+    got = []
+    pipe.track_image_async(L[0], R[0], frames[0][0].time0)
+    for k in range(1, T):
+        pipe.track_image_async(L[k], R[k], frames[k][0].time0)
+        pipe.wait()                                     # step k-1
+        got.append([pipe.features(s).tobytes() for s in range(B)])
+    pipe.wait()
+    got.append([pipe.features(s).tobytes() for s in range(B)])
+    assert got == want
+    sync.close(); pipe.close()
