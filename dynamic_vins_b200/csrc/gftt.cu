@@ -326,7 +326,7 @@ __device__ __forceinline__ unsigned long long block_select_kth(const unsigned lo
     const int tid = threadIdx.x;
     if (tid == 0) { *s_prefix = 0ull; *s_remaining = k; }
     __syncthreads();
-    for (int pass = 0; pass < 8; pass++) {
+    for (int pass = 0; pass < 8 && *s_remaining > 0; pass++) {
         const int shift = 56 - 8 * pass;
         if (tid < 256) s_hist[tid] = 0;
         __syncthreads();
@@ -343,7 +343,8 @@ __device__ __forceinline__ unsigned long long block_select_kth(const unsigned lo
                 if (s_hist[b] >= rem) break;
                 rem -= s_hist[b];
             }
-            *s_remaining = rem;
+            // every key of the selected bucket is wanted: all keys >= this prefix are exactly the k largest
+            *s_remaining = (s_hist[b] == rem) ? 0 : rem;
             *s_prefix = prefix | ((unsigned long long)b << shift);
         }
         __syncthreads();
@@ -378,15 +379,21 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     const double maxVal = (mo == INT_MIN) ? 0.0 : (double)ord2f(mo);
     const float thr = (float)(maxVal * J.quality);
     const unsigned long long thr_key = ((unsigned long long)((unsigned)f2ord(thr) ^ 0x80000000u) << 32) | 0xffffffffull;
-    const unsigned long long* __restrict__ all = J.cand;
+    const unsigned long long* all = J.cand;
 
+    // candidates above the threshold, compacted into cand3 (unordered)
+    unsigned long long* __restrict__ valid = J.cand3;
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    {
-        int c = 0;
-        for (int i = tid; i < nc; i += NMS_THREADS) c += all[i] > thr_key ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    for (int i0 = 0; i0 < nc; i0 += NMS_THREADS) {
+        const int i = i0 + tid;
+        const unsigned long long key = i < nc ? all[i] : 0ull;
+        const bool keep = i < nc && key > thr_key;
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if ((tid & 31) == 0 && ballot) base = atomicAdd(&s_cnt, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) valid[base + __popc(ballot & ((1u << (tid & 31)) - 1))] = key;
     }
     __syncthreads();
     const int nv = s_cnt;                   // candidates above the threshold (cv: tmpCorners.size())
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     const bool use_nms = J.min_dist >= 1.f;
 
     unsigned long long* work = J.cand2;          // the M strongest candidates (unordered)
-    unsigned long long* cs = J.cand3;            // the same, grouped by cell, descending key inside a cell
+    unsigned long long* cs = J.cand;             // the same, grouped by cell (the pre-candidate list is dead by now)
     // Only the first K accepted corners in rank order are wanted, and whether a candidate is accepted depends only
     // on stronger candidates: the greedy result restricted to the M strongest candidates is a prefix of the full
     // result.  Start with a small M and grow it until K corners are accepted or every candidate is in.
@@ -412,17 +419,15 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     int n_acc = 0;
     volatile uint8_t* state = nullptr;
     for (;;) {
-        unsigned long long tkey = thr_key + 1ull;       // keep keys >= tkey
-        if (M < nv) {
-            tkey = block_select_kth(all, nc, M, [&](int, unsigned long long key) { return key > thr_key; }, s_hist,
-                                    &s_prefix, &s_remaining);
-        }
+        unsigned long long tkey = 0ull;                 // keep keys >= tkey
+        if (M < nv) tkey = block_select_kth(valid, nv, M, [&](int, unsigned long long) { return true; }, s_hist, &s_prefix,
+                                            &s_remaining);
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < nc; i0 += NMS_THREADS) {
+        for (int i0 = 0; i0 < nv; i0 += NMS_THREADS) {
             const int i = i0 + tid;
-            const unsigned long long key = i < nc ? all[i] : 0ull;
-            const bool keep = i < nc && key >= tkey && key > thr_key;
+            const unsigned long long key = i < nv ? valid[i] : 0ull;
+            const bool keep = i < nv && key >= tkey;
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
             int base = 0;
             if ((tid & 31) == 0 && ballot) base = atomicAdd(&s_cnt, __popc(ballot));
@@ -584,17 +589,21 @@ __global__ void k_gftt_assign_ids(const GfttJob* __restrict__ jobs, int n_jobs) 
 }
 
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
-                cudaStream_t st) {
+                cudaStream_t st, cudaEvent_t* marks) {
     (void)h_jobs;
     if (n_jobs <= 0) return DVFE_OK;
+    int mi = 0;
+#define GFTT_MARK() do { if (marks) cudaEventRecord(marks[mi++], st); } while (0)
     {
         dim3 blk(32, 8), grid(((max_w + 15) / 16 + 31) / 32, (max_h + 7) / 8, n_jobs);
         DVFE_LAUNCH(k_gftt_mask_fill, grid, blk, 0, st, d_jobs);
     }
+    GFTT_MARK();
     if (max_pts > 0) {
         dim3 grid((max_pts + 3) / 4, n_jobs);
         DVFE_LAUNCH(k_gftt_discs, grid, 128, 0, st, d_jobs);
     }
+    GFTT_MARK();
     if (h_jobs != nullptr && h_jobs[0].eig_in != nullptr) {     // seam op with an external response map
         dim3 blk(32, 8), grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
         DVFE_LAUNCH(k_gftt_max_ext, grid, blk, 0, st, d_jobs);
@@ -604,8 +613,10 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
             grid((max_w + RS_COLS * RS_WARPS - 1) / (RS_COLS * RS_WARPS), (max_h + RS_ROWS - 1) / RS_ROWS, n_jobs);
         DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
     }
+    GFTT_MARK();
     DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, 0, st, d_jobs);
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
+#undef GFTT_MARK
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

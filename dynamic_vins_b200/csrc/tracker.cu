@@ -292,8 +292,8 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
         DVFE_CHECK(launch_compact(bg, B, cap, st));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
-    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st));
-    mark(ST_GFTT + 1);
+    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, prof ? &ev[par][ST_GFTT_MASK + 1] : nullptr));
+    mark(ST_GFTT_SELECT + 1);
     // UndistortedPts(cam0) + PtsVelocity
     DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
     mark(ST_LEFT_POST + 1);
@@ -506,8 +506,9 @@ extern "C" int dvfe_profile(dvfe_tracker* t, int enable) {
 }
 
 extern "C" int dvfe_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps) {
-    static const char* kNames[dvfe_tracker::ST_COUNT] = {"pyramid", "lk_temporal", "compact", "gftt",
-                                                         "left_post", "lk_stereo", "pack", "d2h"};
+    static const char* kNames[dvfe_tracker::ST_COUNT] = {"pyramid", "lk_temporal", "compact", "gftt_mask_fill", "gftt_discs",
+                                                         "gftt_response", "gftt_select", "left_post", "lk_stereo", "pack",
+                                                         "d2h"};
     if (!t) { dvfe_set_error("profile_read: null tracker"); return DVFE_ERR_INVALID; }
     for (int i = 0; i < dvfe_tracker::ST_COUNT; i++) {
         if (names) names[i] = kNames[i];

@@ -58,7 +58,8 @@ struct dvfe_tracker {
     InstanceState* inst = nullptr;
 
     // per-stage device timers (one event set per in-flight step)
-    enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT, ST_LEFT_POST, ST_LK_STEREO, ST_PACK, ST_D2H, ST_COUNT };
+    enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT_MASK, ST_GFTT_DISCS, ST_GFTT_RESPONSE, ST_GFTT_SELECT, ST_LEFT_POST,
+           ST_LK_STEREO, ST_PACK, ST_D2H, ST_COUNT };
     bool prof = false;
     bool prof_step[2] = {false, false};
     cudaEvent_t ev[2][ST_COUNT + 1] = {};
