@@ -133,7 +133,7 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
     """Compulsory HBM bytes of one launch group, SURVEY.md §8(d) (P = W*H pixels per image):
        pyramid     read P + write the padded level 0 (P) + levels 1..3 (0.328 P), per image, 2 images per stream
        lk_*        both pyramids of the pair read once (2 * 1.328 P) + 17 B per point (8 in, 8 out, 1 status)
-       gftt        read P (image) + mask P written and read (the response map stays on chip) + 8 B per candidate
+       gftt_response  read P (image) + P (mask); the response map stays on chip; 8 B per pre-candidate written
     """
     P = float(W * H)
     pyr = sum(1.0 / 4 ** l for l in range(n_levels))
@@ -141,8 +141,10 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
         return S * 2 * (P + P * pyr)
     if stage in ("lk_temporal", "lk_stereo"):
         return S * 2 * P * pyr + 17.0 * n_pts_total
-    if stage == "gftt":
-        return S * (P + 2 * P) + 8.0 * 20000 * S
+    if stage == "gftt_response":
+        return S * (P + P) + 8.0 * 20000 * S       # image + mask read, ~20 k pre-candidates written per stream
+    if stage == "gftt_mask_fill":
+        return S * P
     return 0.0
 
 
@@ -259,6 +261,11 @@ def run_dvfe(args):
         dom = max(stage_ms, key=stage_ms.get)
         n_levels = 4
         ab = algorithmic_bytes(dom, S, W, H, n_left, n_levels)
+        traffic = None
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
         achieved = ab / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -274,7 +281,7 @@ def run_dvfe(args):
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom]},
         }
         if world == 1 and not args.no_cpu_baseline:
