@@ -9,7 +9,8 @@ streams per GPU, raw mode (TrackImage: temporal LK with forward-backward check, 
 points with min-distance 25, left->right LK, undistortion, velocity).  A "step" advances every stream of the
 rank by one frame.  Streams are independent, so N GPUs run N x 64 streams with no collective ("scaling": weak).
 
-  value  frames/s with the frames already resident in HBM (dvfe_track_image_device), outputs read back;
+  value  frames/s with the frames already resident in HBM (dvfe_track_image_device_async + dvfe_wait), every
+         step's records read back to the host;
   e2e    frames/s through the host-buffer C-ABI calls (dvfe_track_image_async + dvfe_wait, the pipelined form of
          dvfe_track_image): every step copies its pinned host images to the device and its FeatureFrame records
          back to the host inside the timed region; the H2D of frame k+1 overlaps the kernels of frame k.
@@ -41,8 +42,8 @@ WORKLOAD = "c5_zed_streams"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="dvfe", choices=["dvfe", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
@@ -202,9 +203,14 @@ def run_dvfe(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         n_pts = 0
-        for i in range(args.warmup, args.warmup + args.steps):
+        first = args.warmup
+        f = frames[order[first]]
+        trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr(), P, W, times[first])
+        for i in range(first + 1, first + args.steps):
             f = frames[order[i]]
-            trk.track_image_device(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+            trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+            trk.wait()                      # records of step i-1 are on the host
+        trk.wait()
         e1.record(stream)
         barrier()
         clock_info = clocks.stop()

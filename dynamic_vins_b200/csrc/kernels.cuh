@@ -39,7 +39,8 @@ int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cu
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);
 
 // lk.cu
-int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st);
+int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
+              int back_max_level = 1, double fb_threshold = 0.5);
 
 // gftt.cu
 struct GfttJob {                 // one detection problem (a stream's image, or one instance ROI)

@@ -154,7 +154,8 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
     }
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back) {
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back,
+                                                                                    int back_max_level, double fb_threshold) {
     __shared__ __align__(16) uint8_t s_win[LK_WARPS][LK_WIN_BYTES];
     const LkGroup& G = groups[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
         const uint8_t* __restrict__ pyrI = pass ? G.pyrB : G.pyrA;
         const uint8_t* __restrict__ pyrJ = pass ? G.pyrA : G.pyrB;
         const float2 src = pass ? p2 : p1;
-        const int lmax = pass ? (1 < top ? 1 : top) : (max_level < top ? max_level : top);
+        const int lmax = pass ? (back_max_level < top ? back_max_level : top) : (max_level < top ? max_level : top);
         float outx = pass ? p1.x : 0.f, outy = pass ? p1.y : 0.f;      // nextPts[ptidx]
         int st = 1;
 #pragma unroll 1
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
             rev = make_float2(outx, outy);
             const float ddx = p1.x - rev.x, ddy = p1.y - rev.y;
             const float dist = sqrtf(ddx * ddx + ddy * ddy);
-            status = (st && (double)dist <= 0.5) ? 1 : 0;
+            status = (st && (double)dist <= fb_threshold) ? 1 : 0;
         }
     }
     if (status) {
@@ -319,10 +320,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
     }
 }
 
-int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st) {
+int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
+              int back_max_level, double fb_threshold) {
     if (n_groups <= 0 || max_pts <= 0) return DVFE_OK;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, n_groups);
-    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back);
+    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back, back_max_level, fb_threshold);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

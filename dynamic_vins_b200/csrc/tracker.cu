@@ -286,7 +286,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
-        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
     mark(ST_LK_TEMPORAL + 1);
     if (k > 0)   // ReduceVector x4 + track_cnt++
         DVFE_CHECK(launch_compact(bg, B, cap, st));
@@ -298,7 +298,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
     mark(ST_LEFT_POST + 1);
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
-        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st));
+        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs, d_nobs, st));
     mark(ST_PACK + 1);
@@ -399,6 +399,24 @@ extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, c
     DVFE_CHECK(t->wait_all());
     DVFE_CHECK(t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr));
     return t->wait_all();
+}
+
+extern "C" int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
+                                             size_t stream_stride, int pitch, const double* time0) {
+    DVFE_CHECK(check_step_args(t, d_left, pitch, time0));
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    while (t->frames - t->completed >= 2) DVFE_CHECK(t->wait_one());
+    return t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr);
+}
+
+extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold) {
+    if (!t || back_max_level < 0 || back_max_level >= DVFE_MAX_PYR_LEVELS || !(fb_threshold > 0.0)) {
+        dvfe_set_error("set_lk_mode: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    t->lk_back_level = back_max_level;
+    t->lk_fb_thresh = fb_threshold;
+    return DVFE_OK;
 }
 
 extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right,

@@ -56,6 +56,8 @@ struct dvfe_tracker {
     LkGroup* d_groups[6][3] = {};                    // [phase][temporal raw | temporal semantic | stereo]
     GfttJob* d_jobs[6][2] = {};                      // [phase][raw | semantic]
     InstanceState* inst = nullptr;
+    int lk_back_level = 1;                           // backward LK maxLevel (feature_utils.cpp:51: 1; cv::cuda path: 3)
+    double lk_fb_thresh = 0.5;                       // forward-backward threshold in px (:57: 0.5; cv::cuda path: 1.0)
 
     // per-stage device timers (one event set per in-flight step)
     enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT_MASK, ST_GFTT_DISCS, ST_GFTT_RESPONSE, ST_GFTT_SELECT, ST_LEFT_POST,

@@ -92,3 +92,21 @@ def lift_projective(cam: dict, pts, off=(0.0, 0.0)):
     out = np.zeros_like(p)
     L.check(L.lib().dvfe_op_lift_projective(C.byref(c), L.ptr(p), len(p), float(off[0]), float(off[1]), L.ptr(out)))
     return out
+
+
+def bgr_to_gray(bgr):
+    """cv::cvtColor(color, gray, CV_BGR2GRAY)"""
+    b = np.ascontiguousarray(bgr, dtype=np.uint8)
+    h, w, _ = b.shape
+    out = np.zeros((h, w), np.uint8)
+    L.check(L.lib().dvfe_op_bgr_to_gray(L.ptr(b), w, h, b.strides[0], L.ptr(out)))
+    return out
+
+
+def merge_masks(masks):
+    """(n, h, w) instance masks -> (merge_mask 255 = object, inv_merge_mask)"""
+    m = np.ascontiguousarray(masks, dtype=np.uint8)
+    n, h, w = m.shape
+    merge, inv = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
+    L.check(L.lib().dvfe_op_merge_masks(L.ptr(m) if n else None, n, w, h, L.ptr(merge), L.ptr(inv)))
+    return merge, inv

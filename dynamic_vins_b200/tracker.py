@@ -128,6 +128,16 @@ class BatchTracker:
         L.check(L.lib().dvfe_track_image_device(self._h, C.c_void_p(d_left), C.c_void_p(d_right) if d_right else None,
                                                 stream_stride, pitch, L.ptr(t)))
 
+    def track_image_device_async(self, d_left: int, d_right: int, stream_stride: int, pitch: int, time0) -> None:
+        t = self._times(time0)
+        self._keep_t = (t, getattr(self, "_keep_t", (None,))[0])
+        L.check(L.lib().dvfe_track_image_device_async(self._h, C.c_void_p(d_left), C.c_void_p(d_right) if d_right else None,
+                                                      stream_stride, pitch, L.ptr(t)))
+
+    def set_lk_mode(self, back_max_level: int = 1, fb_threshold: float = 0.5) -> None:
+        """cv::cuda call pattern of FeatureTrackByLKGpu: back_max_level=3, fb_threshold=1.0"""
+        L.check(L.lib().dvfe_set_lk_mode(self._h, int(back_max_level), float(fb_threshold)))
+
     def track_semantic_image(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
         l = self._batch(left, self.B, self.H, self.W)
         r = self._batch(right, self.B, self.H, self.W)
@@ -222,3 +232,17 @@ def serialize_point_features(points: Dict[int, List[Tuple[int, np.ndarray]]]) ->
         else:
             lines.append(f"1 {fid} {vals} " + " ".join(repr(float(x)) for x in obs[1][1]))
     return "\n".join(lines) + ("\n" if lines else "")
+
+
+def deserialize_point_features(text: str) -> Dict[int, List[Tuple[int, np.ndarray]]]:
+    """DeserializePointFeature (dynamic_vins/src/utils/io/feature_serialization.cpp:45-70)."""
+    points: Dict[int, List[Tuple[int, np.ndarray]]] = {}
+    for line in text.splitlines():
+        tok = line.split()
+        if not tok:
+            continue
+        fid = int(tok[1])
+        points.setdefault(fid, []).append((0, np.array([float(x) for x in tok[2:9]])))
+        if tok[0] == "1":
+            points[fid].append((1, np.array([float(x) for x in tok[9:16]])))
+    return points

@@ -144,6 +144,18 @@ int dvfe_wait(dvfe_tracker* t);
 int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride,
                             int pitch, const double* time0);
 
+/* Pipelined form of dvfe_track_image_device (pair with dvfe_wait): the D2H of step k and the host turn-around overlap
+ * the kernels of step k+1.  The device images must stay unchanged until the step is waited for. */
+int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride,
+                                  int pitch, const double* time0);
+
+/* FeatureTracker::TrackImageNaive-style variant of the step (front_end/background_tracker.cpp:400-516): the
+ * cv::cuda LK call pattern of FeatureTrackByLKGpu (front_end/feature_utils.cpp:83-163) — backward pass over all
+ * `back_max_level`+1 levels (3) and a forward-backward threshold of `fb_threshold` px (1.0) — evaluated with this
+ * library's fixed-point LK arithmetic (cv::cuda's fp32 texture interpolation is not reproduced).  Applies to all later
+ * steps of the tracker; the defaults (1, 0.5) are the CPU FeatureTrackByLK. */
+int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold);
+
 /* FeatureTracker::TrackSemanticImage(SemanticImage&) (front_end/background_tracker.cpp:757-837).
  * inv_merge_mask: HOST, same layout as left (0 = object, 255 = background), may be NULL when no stream has
  * instances; exist_inst[s] = SemanticImage::exist_inst. */
@@ -211,6 +223,16 @@ int dvfe_op_erode_rect(const uint8_t* src, int w, int h, int pitch, int k, uint8
 /* InstFeat::UndistortedPts / UndistortedPointsWithAddOffset: PinholeCamera::liftProjective then (x/z, y/z)
  * narrowed to float (front_end/instance_feature.cpp:94-103,123-133). */
 int dvfe_op_lift_projective(const dvfe_camera* cam, const float* pts, int n, float off_x, float off_y, float* out);
+
+/* ---- upstream frame preparation ----------------------------------------------------- */
+
+/* SemanticImage::SetGrayImage: cv::cvtColor(color, gray, CV_BGR2GRAY) (basic/semantic_image.cpp:69-73).
+ * bgr: h rows of 3*w bytes (pitch bytes per row) -> gray_out: dense w x h. */
+int dvfe_op_bgr_to_gray(const uint8_t* bgr, int w, int h, int pitch, uint8_t* gray_out);
+
+/* SemanticImage::SetMaskAndRoi / SetBackgroundMask (basic/semantic_image.cpp:20-63,103-117): masks = n dense w x h
+ * instance masks (non-zero = object) -> merge_mask (255 = object) and inv_merge_mask (bitwise_not). */
+int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int h, uint8_t* merge_out, uint8_t* inv_out);
 
 #ifdef __cplusplus
 }

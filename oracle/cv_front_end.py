@@ -57,6 +57,8 @@ class FrontEndParams:
     mask_morphology_size: int = 5
     is_stereo: bool = True        # cfg::is_stereo (num_of_cam == 2)
     lk_max_level: int = 3         # cv::calcOpticalFlowPyrLK(..., Size(21,21), 3)
+    lk_back_max_level: int = 1    # backward call: maxLevel 1 (feature_utils.cpp:51); FeatureTrackByLKGpu: 3
+    fb_threshold: float = 0.5     # forward-backward distance (feature_utils.cpp:57); FeatureTrackByLKGpu: 1.0 (:117)
 
 
 class IdCounter:
@@ -152,7 +154,7 @@ LK_CRIT = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
 
 
 def feature_track_by_lk(img1: np.ndarray, img2: np.ndarray, pts1: np.ndarray,
-                        flow_back: bool = True, max_level: int = 3):
+                        flow_back: bool = True, max_level: int = 3, back_max_level: int = 1, fb_threshold: float = 0.5):
     """front_end/feature_utils.cpp:35-69.  Returns (pts2 float32 (N,2), status uint8 (N,)).
     Throws on empty input like the reference (:39-41)."""
     if img1 is None or img2 is None or img1.size == 0 or img2.size == 0 or len(pts1) == 0:
@@ -165,12 +167,12 @@ def feature_track_by_lk(img1: np.ndarray, img2: np.ndarray, pts1: np.ndarray,
     if flow_back:
         rev0 = p1.copy()
         rev, rst, _ = cv2.calcOpticalFlowPyrLK(img2, img1, p2.reshape(-1, 1, 2).copy(), rev0,
-                                               winSize=LK_WIN, maxLevel=1, criteria=LK_CRIT,
+                                               winSize=LK_WIN, maxLevel=back_max_level, criteria=LK_CRIT,
                                                flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
         rev = rev.reshape(-1, 2)
         rst = rst.reshape(-1)
         for i in range(len(status)):
-            ok = status[i] and rst[i] and point_distance(p1[i, 0], rev[i]) <= 0.5
+            ok = status[i] and rst[i] and point_distance(p1[i, 0], rev[i]) <= fb_threshold
             status[i] = 1 if ok else 0
     rows, cols = img2.shape[:2]
     for i in range(len(status)):
@@ -278,7 +280,8 @@ class InstFeat:
     def track_left(self, curr_img, last_img, P: FrontEndParams, mask=None):
         if len(self.last_points) == 0:
             return
-        pts2, status = feature_track_by_lk(last_img, curr_img, self.last_points, bool(P.flow_back), P.lk_max_level)
+        pts2, status = feature_track_by_lk(last_img, curr_img, self.last_points, bool(P.flow_back), P.lk_max_level,
+                                           P.lk_back_max_level, P.fb_threshold)
         self.curr_points = pts2
         if mask is not None:
             for i in range(len(status)):
@@ -299,7 +302,8 @@ class InstFeat:
         pts = self.curr_points
         if offset != (0.0, 0.0):
             pts = np.stack([pts[:, 0] + f32(offset[0]), pts[:, 1] + f32(offset[1])], axis=1).astype(f32)
-        rp, status = feature_track_by_lk(gray0, gray1, pts, bool(P.flow_back), P.lk_max_level)
+        rp, status = feature_track_by_lk(gray0, gray1, pts, bool(P.flow_back), P.lk_max_level, P.lk_back_max_level,
+                                         P.fb_threshold)
         self.right_points = _reduce(rp, status)
         self.right_ids = _reduce(list(self.ids), status)
 
@@ -388,7 +392,7 @@ class FeatureTracker:
         self.stage = {}
         if len(bg.last_points) > 0:                                                 # :61-68
             pts2, status = feature_track_by_lk(self.prev_gray0, gray0, bg.last_points, bool(P.flow_back),
-                                               P.lk_max_level)
+                                               P.lk_max_level, P.lk_back_max_level, P.fb_threshold)
             self.stage["lk_pts"], self.stage["lk_status"] = pts2.copy(), status.copy()
             bg.last_points = _reduce(bg.last_points, status)
             bg.curr_points = _reduce(pts2, status)

@@ -216,3 +216,20 @@ def test_full_size_properties():
     p2, s = ops.feature_track_by_lk(f0.gray0, f1.gray0, pts, True, 3)
     c2, cs = cvfe.feature_track_by_lk(f0.gray0, f1.gray0, pts, True, 3)
     assert np.array_equal(s, cs) and np.abs(p2 - c2)[cs == 1].max() <= POS_TOL and cs.mean() > 0.9
+
+
+def test_frame_prep_ops():
+    """BGR->gray and instance-mask merge, bit-exact vs cv2 / numpy"""
+    rng = np.random.default_rng(3)
+    for shape in [(123, 457), (720, 1280), (5, 7)]:
+        bgr = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+        assert np.array_equal(ops.bgr_to_gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    fr = synth.make_stream("c3_zed_dynamic", 0).frame(2)
+    full = np.zeros((len(fr.boxes), 720, 1280), np.uint8)
+    for i, b in enumerate(fr.boxes):
+        x, y, w, h = b["rect"]
+        full[i, y:y + h, x:x + w] = b["mask"] // 255         # 0/1 masks like the SOLOv2 tensor
+    merge, inv = ops.merge_masks(full)
+    assert np.array_equal(merge, fr.merge_mask) and np.array_equal(inv, fr.inv_merge_mask)
+    merge, inv = ops.merge_masks(np.zeros((0, 8, 9), np.uint8))
+    assert not merge.any() and (inv == 255).all()

@@ -94,3 +94,23 @@ def test_two_rank_gloo_sharding_and_max_reduce():
     for rank, gathered, ms in res:
         assert gathered == [[0, 1, 2, 3], [4, 5, 6, 7]]         # disjoint, every stream owned exactly once
         assert ms == [11.0, 5.0]
+
+
+def test_point_feature_wire_format_round_trip():
+    """SerializePointFeature / DeserializePointFeature text format (utils/io/feature_serialization.cpp:26-70)"""
+    rng = np.random.default_rng(0)
+    pts = {}
+    for fid in (3, 8, 21):
+        obs = [(0, np.r_[rng.standard_normal(2), 1.0, rng.uniform(0, 700, 2), rng.standard_normal(2)])]
+        if fid != 8:
+            obs.append((1, np.r_[rng.standard_normal(2), 1.0, rng.uniform(0, 700, 2), rng.standard_normal(2)]))
+        pts[fid] = obs
+    txt = dv.tracker.serialize_point_features(pts)
+    back = dv.tracker.deserialize_point_features(txt)
+    assert list(back) == [3, 8, 21]
+    for fid in pts:
+        assert [c for c, _ in back[fid]] == [c for c, _ in pts[fid]]
+        for (_, a), (_, b) in zip(back[fid], pts[fid]):
+            assert np.array_equal(a, b)          # repr() round-trips doubles exactly
+    from oracle import cv_front_end as cvfe
+    assert cvfe.serialize_point_features(pts) == txt
