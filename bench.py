@@ -292,6 +292,8 @@ def run_dvfe(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            out["parity"] = parity_sample(local)
+            out["single_stream"] = single_stream_latency(local)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -330,6 +332,51 @@ def cpu_baseline(budget_s: float) -> dict:
     return {"value": n / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "port",
             "sample": f"1 stream x {n} frames of {WORKLOAD} (1280x720 stereo, 400 pts), cv2 {cv2.__version__} "
                       f"with {cv2.getNumThreads()} threads, single process"}
+
+
+def parity_sample(device: int, n_frames: int = 6) -> dict:
+    """px error vs the reference CPU path (the metric's second half): stream 0 of the workload, GPU vs the cv2
+    oracle, free running from a cold start; outside every timed region."""
+    from dynamic_vins_b200 import BatchTracker, make_config, obs_to_map, synth
+    c = synth.CONFIGS[WORKLOAD]
+    st, fe = _oracle_frontend(0)
+    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True,
+                                   device=device))
+    worst, ids_equal, n_obs = 0.0, True, 0
+    for k in range(n_frames):
+        fr = st.frame(k)
+        want = fe.step(fr)["features"]
+        trk.track_image(fr.gray0, fr.gray1, fr.time0)
+        got = obs_to_map(trk.features(0))
+        ids_equal &= sorted(got) == sorted(want) and all([c0 for c0, _ in got[i]] == [c0 for c0, _ in want[i]] for i in want)
+        for i in set(got) & set(want):
+            for (_, a), (_, b) in zip(got[i], want[i]):
+                worst = max(worst, float(np.abs(a[3:5] - b[3:5]).max()))
+                n_obs += 1
+    trk.close()
+    return {"max_px_err_vs_ref_cpu": worst, "ids_and_stereo_bits_equal": bool(ids_equal), "frames": n_frames,
+            "observations": n_obs, "tolerance_px": 0.02}
+
+
+def single_stream_latency(device: int, n_frames: int = 40) -> dict:
+    """one camera (B = 1, the reference's deployment shape): ms per dvfe_track_image call, host buffers in and
+    records out, wall clock"""
+    from dynamic_vins_b200 import BatchTracker, make_config, synth
+    c = synth.CONFIGS[WORKLOAD]
+    st = synth.SynthStream(c["width"], c["height"], seed=77, stereo=True)
+    frames = [st.frame(k) for k in range(4)]
+    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True,
+                                   device=device))
+    order = __import__("dynamic_vins_b200").synth.pingpong_positions(4, n_frames + 5)
+    ts = []
+    for i, k in enumerate(order):
+        t0 = time.perf_counter()
+        trk.track_image(frames[k].gray0, frames[k].gray1, 0.05 * (i + 1))
+        ts.append((time.perf_counter() - t0) * 1e3)
+    trk.close()
+    ts = np.array(ts[5:])
+    return {"ms_per_frame_median": float(np.median(ts)), "ms_per_frame_p95": float(np.percentile(ts, 95)),
+            "frames_per_s": float(1e3 / np.median(ts)), "note": "B=1, pageable host images, synchronous call"}
 
 
 def _ref_worker(wid: int, T: int, conn):
