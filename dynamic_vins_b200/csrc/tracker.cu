@@ -147,9 +147,11 @@ extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
 int dvfe_tracker::init() {
     DVFE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     DVFE_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    DVFE_CUDA(cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking));
     for (int p = 0; p < 2; p++) {
         for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[p][i]));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_up[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_packed[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_done[p], cudaEventDisableTiming));
     }
     const size_t P = (size_t)W * H;
@@ -163,9 +165,9 @@ int dvfe_tracker::init() {
     }
     DVFE_CHECK(dmalloc(&d_dt, (size_t)B));
     prev_time.assign(B, 0.0);
-    DVFE_CHECK(dmalloc(&d_obs, (size_t)B * 2 * cap));
-    DVFE_CHECK(dmalloc(&d_nobs, (size_t)B));
     for (int p = 0; p < 2; p++) {
+        DVFE_CHECK(dmalloc(&d_obs[p], (size_t)B * 2 * cap));
+        DVFE_CHECK(dmalloc(&d_nobs[p], (size_t)B));
         DVFE_CUDA(cudaMallocHost((void**)&h_dt[p], B * sizeof(double)));
         DVFE_CUDA(cudaMallocHost((void**)&h_obs[p], (size_t)B * 2 * cap * sizeof(dvfe_obs)));
         DVFE_CUDA(cudaMallocHost((void**)&h_nobs[p], B * sizeof(int)));
@@ -240,12 +242,14 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     cudaSetDevice(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->cs) cudaStreamSynchronize(t->cs);
+    if (t->ds) cudaStreamSynchronize(t->ds);
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
     cudaFree(t->d_next_id); cudaFree(t->d_dt);
-    cudaFree(t->d_obs); cudaFree(t->d_nobs);
     for (int p = 0; p < 2; p++) {
+        cudaFree(t->d_obs[p]); cudaFree(t->d_nobs[p]);
+        if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
         cudaFreeHost(t->h_dt[p]); cudaFreeHost(t->h_obs[p]); cudaFreeHost(t->h_nobs[p]);
         if (t->ev_up[p]) cudaEventDestroy(t->ev_up[p]);
         if (t->ev_done[p]) cudaEventDestroy(t->ev_done[p]);
@@ -260,6 +264,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     }
     t->free_instances();
     if (t->cs) cudaStreamDestroy(t->cs);
+    if (t->ds) cudaStreamDestroy(t->ds);
     if (t->st && t->own_stream) cudaStreamDestroy(t->st);
     delete t;
 }
@@ -300,12 +305,15 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
         DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
     mark(ST_LK_STEREO + 1);
-    DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs, d_nobs, st));
+    DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs[par], d_nobs[par], st));
     mark(ST_PACK + 1);
-    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par], d_nobs, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    DVFE_CUDA(cudaMemcpyAsync(h_obs[par], d_obs, (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, st));
-    mark(ST_D2H + 1);
-    DVFE_CUDA(cudaEventRecord(ev_done[par], st));
+    // records go home on the download stream so that the next step's kernels do not queue behind the copy
+    DVFE_CUDA(cudaEventRecord(ev_packed[par], st));
+    DVFE_CUDA(cudaStreamWaitEvent(ds, ev_packed[par], 0));
+    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par], d_nobs[par], B * sizeof(int), cudaMemcpyDeviceToHost, ds));
+    DVFE_CUDA(cudaMemcpyAsync(h_obs[par], d_obs[par], (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, ds));
+    if (prof) cudaEventRecord(ev[par][ST_D2H + 1], ds);
+    DVFE_CUDA(cudaEventRecord(ev_done[par], ds));
     for (int s = 0; s < B; s++) prev_time[s] = time0[s];
     last_has_right = stereo_now;
     frames++;

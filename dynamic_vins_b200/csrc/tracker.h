@@ -28,6 +28,7 @@ struct dvfe_tracker {
     int B = 0, W = 0, H = 0, cap = 0;
     cudaStream_t st = nullptr;                       // compute stream (caller-replaceable)
     cudaStream_t cs = nullptr;                       // upload stream: H2D of step k+1 overlaps the kernels of step k
+    cudaStream_t ds = nullptr;                       // download stream: D2H of step k overlaps the kernels of step k+1
     bool own_stream = true;
     PyrDesc desc{};
     CamParams cam0{}, cam1{};
@@ -43,12 +44,12 @@ struct dvfe_tracker {
     double* d_dt = nullptr;
     double* h_dt[2] = {nullptr, nullptr};
     std::vector<double> prev_time;
-    dvfe_obs* d_obs = nullptr;
+    dvfe_obs* d_obs[2] = {nullptr, nullptr};         // one per in-flight step
     dvfe_obs* h_obs[2] = {nullptr, nullptr};         // pinned, one per in-flight step
-    int* d_nobs = nullptr;
+    int* d_nobs[2] = {nullptr, nullptr};
     int* h_nobs[2] = {nullptr, nullptr};
     int out_slot = 0;                                // which h_obs holds the newest completed step
-    cudaEvent_t ev_up[2] = {}, ev_done[2] = {};
+    cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {};
     uint8_t *d_region = nullptr, *d_region_tmp = nullptr, *d_inv_in = nullptr;
     int* d_exist = nullptr;
     int* h_exist = nullptr;
