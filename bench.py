@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="dvfe", choices=["dvfe", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["c1_euroc_mono", "c2_kitti_stereo", "c4_hd_stereo", "c5_zed_streams"],
+                    help="BASELINE.json config shape of every stream (default: configs[4], the metric's configuration)")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -170,17 +172,18 @@ def run_dvfe(args):
         torch.cuda.synchronize()
 
     c = synth.CONFIGS[WORKLOAD]
+    stereo = bool(c["stereo"])
     S, T, W, H = args.streams, args.frames, c["width"], c["height"]
     # ---- synthetic frames: S independent streams (distinct seeds per stream and rank), T unique frames each
     frames = torch.empty((T, 2, S, H, W), dtype=torch.uint8, device=dev)
     for s in range(S):
-        st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + rank * S + s, stereo=True)
+        st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + rank * S + s, stereo=stereo)
         frames[:, :, s] = gpu_frames(st, T, dev)
     torch.cuda.synchronize()
     order = synth.pingpong_positions(T, args.warmup + args.steps)
     times = [np.full(S, 0.05 * (i + 1)) for i in range(len(order))]
 
-    cfg = make_config(W, H, c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S, device=local)
+    cfg = make_config(W, H, c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=stereo, n_streams=S, device=local)
     stream = torch.cuda.Stream(device=dev)
     P = W * H
 
@@ -194,7 +197,7 @@ def run_dvfe(args):
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             f = frames[order[i]]
-            trk.track_image_device(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+            trk.track_image_device(f[0].data_ptr(), f[1].data_ptr() if stereo else 0, P, W, times[i])
         trk.profile(True)
         launches0 = lib().dvfe_kernel_launches()
         clocks = ClockSampler(local)
@@ -205,10 +208,10 @@ def run_dvfe(args):
         n_pts = 0
         first = args.warmup
         f = frames[order[first]]
-        trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr(), P, W, times[first])
+        trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr() if stereo else 0, P, W, times[first])
         for i in range(first + 1, first + args.steps):
             f = frames[order[i]]
-            trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr(), P, W, times[i])
+            trk.track_image_device_async(f[0].data_ptr(), f[1].data_ptr() if stereo else 0, P, W, times[i])
             trk.wait()                      # records of step i-1 are on the host
         trk.wait()
         e1.record(stream)
@@ -229,16 +232,16 @@ def run_dvfe(args):
     trk = make_tracker()
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
-            trk.track_image(host_np[order[i], 0], host_np[order[i], 1], times[i])
+            trk.track_image(host_np[order[i], 0], host_np[order[i], 1] if stereo else None, times[i])
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         # the public pipelined call: the H2D of frame k+1 overlaps the kernels of frame k; every step's records
         # are read back to the host (dvfe_wait) inside the timed region
         first = args.warmup
-        trk.track_image_async(host_np[order[first], 0], host_np[order[first], 1], times[first])
+        trk.track_image_async(host_np[order[first], 0], host_np[order[first], 1] if stereo else None, times[first])
         for i in range(first + 1, first + args.steps):
-            trk.track_image_async(host_np[order[i], 0], host_np[order[i], 1], times[i])
+            trk.track_image_async(host_np[order[i], 0], host_np[order[i], 1] if stereo else None, times[i])
             trk.wait()
         trk.wait()
         e1.record(stream)
@@ -277,13 +280,13 @@ def run_dvfe(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 images, int32/int64 patch sums, fp32 2x2 solve, fp64 undistortion", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": W, "height": H, "stereo": True,
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": W, "height": H, "stereo": stereo,
                        "max_cnt": c["max_cnt"], "min_dist": c["min_dist"], "lk": "21x21, maxLevel 3, fwd+bwd",
                        "unique_frames_per_stream": T, "l2": "inputs_larger_than_L2",
                        "tracked_points_per_step": n_left, "observations_per_step": n_obs},
             "clocks": clock_info,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(2 * S * P), "d2h_bytes_per_step": int(S * (2 * c["max_cnt"] * 64 + 4))},
+                    "h2d_bytes_per_step": int((2 if stereo else 1) * S * P), "d2h_bytes_per_step": int(S * (2 * c["max_cnt"] * 64 + 4))},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -300,12 +303,12 @@ def run_dvfe(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-def _oracle_frontend(stream_id: int):
+def _oracle_frontend(stream_id: int, workload: str = None):
     from dynamic_vins_b200 import synth
     from oracle import cv_front_end as cvfe
-    c = synth.CONFIGS[WORKLOAD]
-    st = synth.SynthStream(c["width"], c["height"], seed=1000 * c["config_id"] + stream_id, stereo=True)
-    fe = cvfe.FrontEnd(cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"], is_stereo=True),
+    c = synth.CONFIGS[workload or WORKLOAD]
+    st = synth.SynthStream(c["width"], c["height"], seed=1000 * c["config_id"] + stream_id, stereo=c["stereo"])
+    fe = cvfe.FrontEnd(cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"], is_stereo=c["stereo"]),
                        c["cam0"], c["cam1"], "raw")
     return st, fe
 
@@ -330,7 +333,7 @@ def cpu_baseline(budget_s: float) -> dict:
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "port",
-            "sample": f"1 stream x {n} frames of {WORKLOAD} (1280x720 stereo, 400 pts), cv2 {cv2.__version__} "
+            "sample": f"1 stream x {n} frames of {WORKLOAD}, cv2 {cv2.__version__} "
                       f"with {cv2.getNumThreads()} threads, single process"}
 
 
@@ -340,8 +343,8 @@ def parity_sample(device: int, n_frames: int = 6) -> dict:
     from dynamic_vins_b200 import BatchTracker, make_config, obs_to_map, synth
     c = synth.CONFIGS[WORKLOAD]
     st, fe = _oracle_frontend(0)
-    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True,
-                                   device=device))
+    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"],
+                                   stereo=c["stereo"], device=device))
     worst, ids_equal, n_obs = 0.0, True, 0
     for k in range(n_frames):
         fr = st.frame(k)
@@ -363,10 +366,10 @@ def single_stream_latency(device: int, n_frames: int = 40) -> dict:
     records out, wall clock"""
     from dynamic_vins_b200 import BatchTracker, make_config, synth
     c = synth.CONFIGS[WORKLOAD]
-    st = synth.SynthStream(c["width"], c["height"], seed=77, stereo=True)
+    st = synth.SynthStream(c["width"], c["height"], seed=77, stereo=c["stereo"])
     frames = [st.frame(k) for k in range(4)]
-    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True,
-                                   device=device))
+    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"],
+                                   stereo=c["stereo"], device=device))
     order = __import__("dynamic_vins_b200").synth.pingpong_positions(4, n_frames + 5)
     ts = []
     for i, k in enumerate(order):
@@ -379,10 +382,10 @@ def single_stream_latency(device: int, n_frames: int = 40) -> dict:
             "frames_per_s": float(1e3 / np.median(ts)), "note": "B=1, pageable host images, synchronous call"}
 
 
-def _ref_worker(wid: int, T: int, conn):
+def _ref_worker(wid: int, T: int, conn, workload: str):
     import cv2
     cv2.setNumThreads(1)
-    st, fe = _oracle_frontend(wid)
+    st, fe = _oracle_frontend(wid, workload)
     frames = [st.frame(k) for k in range(T)]
     from dynamic_vins_b200.synth import pingpong_positions
     i = 0
@@ -413,7 +416,7 @@ def run_reference(args):
     pipes, procs = [], []
     for w in range(n_workers):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(w, args.frames, b), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(w, args.frames, b, WORKLOAD), daemon=True)
         p.start()
         pipes.append(a); procs.append(p)
     for a in pipes:
@@ -440,7 +443,7 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8 images, int16 patches, fp32 (OpenCV CPU)", "data": "synthetic",
            "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "width": c["width"], "height": c["height"],
-                      "stereo": True, "max_cnt": c["max_cnt"], "min_dist": c["min_dist"],
+                      "stereo": bool(c["stereo"]), "max_cnt": c["max_cnt"], "min_dist": c["min_dist"],
                       "lk": "21x21, maxLevel 3, fwd+bwd", "unique_frames_per_stream": args.frames},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "port",
                             "sample": f"{n_workers} processes x {args.steps} frames, one {WORKLOAD} stream each "
@@ -451,6 +454,7 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    WORKLOAD = a.workload
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -179,6 +179,11 @@ int dvfe_tracker::init() {
     DVFE_CHECK(dmalloc(&d_exist, (size_t)B));
     DVFE_CUDA(cudaMallocHost((void**)&h_exist, B * sizeof(int)));
     DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
+    // pitched host->device DMA straight into the padded level 0 runs at full PCIe rate only for rows that are a
+    // multiple of 64 bytes; other widths go through a dense staging buffer (one linear copy) and the copy kernel
+    staged_upload = (W % 64) != 0;
+    if (staged_upload)
+        for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
     // LK groups: [phase][temporal raw | temporal semantic | stereo]
     std::vector<LkGroup> g(B);
@@ -255,6 +260,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
         if (t->ev_done[p]) cudaEventDestroy(t->ev_done[p]);
         for (int i = 0; i <= dvfe_tracker::ST_COUNT; i++) if (t->ev[p][i]) cudaEventDestroy(t->ev[p][i]);
     }
+    cudaFree(t->d_stage[0]); cudaFree(t->d_stage[1]);
     cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_inv_in); cudaFree(t->d_exist);
     cudaFreeHost(t->h_exist);
     free_gftt_scratch(&t->gsc);
@@ -372,6 +378,29 @@ int dvfe_tracker::upload_in_place(const uint8_t* left, const uint8_t* right, siz
     return DVFE_OK;
 }
 
+// Host images -> dense device staging of the NEXT step (upload stream); the copy kernel then builds level 0.
+int dvfe_tracker::upload_staged(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
+    const long k = frames;
+    const int par = (int)(k % 2);
+    while (frames - completed >= 2) DVFE_CHECK(wait_one());
+    const size_t P = (size_t)W * H;
+    for (int cam = 0; cam < 2; cam++) {
+        const uint8_t* src = cam ? right : left;
+        if (!src) continue;
+        uint8_t* dst = d_stage[par] + (size_t)cam * B * P;
+        if (pitch == W && stream_stride == P) {
+            DVFE_CUDA(cudaMemcpyAsync(dst, src, (size_t)B * P, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int s = 0; s < B; s++)
+                DVFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)s * P, W, src + s * stream_stride, pitch, W, (size_t)H,
+                                            cudaMemcpyHostToDevice, cs));
+        }
+    }
+    DVFE_CUDA(cudaEventRecord(ev_up[par], cs));
+    DVFE_CUDA(cudaStreamWaitEvent(st, ev_up[par], 0));
+    return DVFE_OK;
+}
+
 static int check_step_args(dvfe_tracker* t, const uint8_t* left, int pitch, const double* time0) {
     if (!t || !left || !time0 || pitch < t->W) {
         dvfe_set_error("track: input wrong, received at least one empty parameter");   // feature_utils.cpp:39-41
@@ -384,6 +413,13 @@ extern "C" int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, cons
                                       int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    if (t->staged_upload) {
+        const size_t P = (size_t)t->W * t->H;
+        const int par = (int)(t->frames % 2);
+        DVFE_CHECK(t->upload_staged(left, right, stream_stride, pitch));
+        return t->submit(t->d_stage[par], right ? t->d_stage[par] + t->B * P : nullptr, P, t->W, time0, false, false,
+                         right != nullptr);
+    }
     DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
     return t->submit(nullptr, nullptr, 0, 0, time0, false, true, right != nullptr);
 }
@@ -435,7 +471,9 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     const size_t P = (size_t)t->W * t->H;
-    DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
+    const int par = (int)(t->frames % 2);
+    if (t->staged_upload) DVFE_CHECK(t->upload_staged(left, right, stream_stride, pitch));
+    else DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
     for (int s = 0; s < t->B; s++) {
         t->h_exist[s] = exist_inst[s] ? 1 : 0;
         if (exist_inst[s]) {
@@ -449,7 +487,11 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
     DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
                                  t->d_exist, t->st));
-    DVFE_CHECK(t->submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr));
+    if (t->staged_upload)
+        DVFE_CHECK(t->submit(t->d_stage[par], right ? t->d_stage[par] + t->B * P : nullptr, P, t->W, time0, true, false,
+                             right != nullptr));
+    else
+        DVFE_CHECK(t->submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr));
     return t->wait_all();
 }
 

@@ -75,7 +75,10 @@ struct dvfe_tracker {
     int init();
     int init_instances();
     void free_instances();
+    uint8_t* d_stage[2] = {nullptr, nullptr};       // dense upload staging [2 cameras][B][H*W], one per in-flight step
+    bool staged_upload = false;                      // rows that are not a multiple of 64 B make pitched DMA slow
     int upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
+    int upload_staged(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
     // enqueue one frame step (no host synchronisation); at most two steps are in flight
     int submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
                bool semantic, bool level0_in_place, bool has_right);
