@@ -96,22 +96,3 @@ struct LkGroup {
     int mask_pitch;
     float offx, offy;        // added to pts1 first (InstFeat::TrackRightByPad)
 };
-
-// ---- per-stream point state (struct of arrays, capacity `cap` per stream) ------------------
-struct PointSet {
-    float2* pts;             // curr_points
-    float2* last;            // last_points
-    float2* un;              // curr_un_points
-    float2* prev_un;         // prev_id_pts[id] for tracked points
-    float2* vel;             // pts_velocity
-    uint32_t* ids;
-    int32_t* track_cnt;
-    float2* rpts;            // right_points (aligned with left index; valid where rstatus)
-    float2* run;             // right_un_points
-    float2* rvel;
-    float2* rprev_un;        // right_prev_id_pts[id]
-    uint8_t* rprev_valid;
-    uint8_t* rstatus;        // right match status of this frame
-    uint8_t* status;         // temporal LK status
-    int* n;                  // [n_sets]
-};

@@ -72,7 +72,6 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     int disc_radius;             // radius of the discs around existing points
     float min_dist;              // NMS distance
     double quality;              // 0.01
-    int id_order;                // jobs sharing next_id are serialised in this order (instances)
 };
 // marks (nullable): 3 events recorded after the mask fill, the discs and the response kernel
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
