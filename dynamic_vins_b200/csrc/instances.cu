@@ -112,7 +112,7 @@ int dvfe_tracker::init_instances() {
     inst = new InstanceState();
     InstanceState& I = *inst;
     I.MI = cfg.max_instances; I.cap = cfg.max_dynamic_cnt; I.P = (size_t)W * H;
-    I.full = make_pyr_desc(W, H, cfg.lk_max_level);
+    I.full = make_pyr_desc(W, H, cfg.lk_max_level > 3 ? cfg.lk_max_level : 3);
     const size_t NS = (size_t)B * I.MI;
     I.streams.resize(B);
     for (auto& s : I.streams)
@@ -263,7 +263,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             if (in.prev_w > 0) {
                 // InstanceImagePadding: both crops zero-padded to (max rows, max cols)
                 const int pw = std::max(in.prev_w, in.w), ph = std::max(in.prev_h, in.h);
-                const PyrDesc d = make_pyr_desc(pw, ph, t->cfg.lk_max_level);
+                const PyrDesc d = make_pyr_desc(pw, ph, t->cfg.lk_max_level > 1 ? t->cfg.lk_max_level : 1);
                 PyrJob& a = I.pyr.h[2 * n_track];
                 PyrJob& b = I.pyr.h[2 * n_track + 1];
                 a.src = I.roi_gray + (set * 2 + (1 - in.cur_buf)) * P; a.sw = in.prev_w; a.sh = in.prev_h; a.spitch = in.prev_w;

@@ -83,7 +83,8 @@ extern "C" int dvfe_op_lk(const uint8_t* img1, const uint8_t* img2, int w, int h
         return DVFE_ERR_INVALID;
     }
     DVFE_CHECK(ensure_device());
-    const PyrDesc desc = make_pyr_desc(w, h, max_level);
+    // the backward call always asks for maxLevel 1 (feature_utils.cpp:51), whatever the forward maxLevel is
+    const PyrDesc desc = make_pyr_desc(w, h, max_level > 1 ? max_level : 1);
     DevBuf d_img, d_pyr, d_p1, d_p2, d_rev, d_st, d_n, d_mask, d_grp;
     DVFE_CHECK(d_img.alloc((size_t)2 * w * h));
     DVFE_CUDA(cudaMemcpy2D(d_img.p, w, img1, pitch, w, h, cudaMemcpyHostToDevice));

@@ -135,7 +135,8 @@ extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
     if (!t) return DVFE_ERR_CAPACITY;
     t->cfg = *cfg;
     t->B = cfg->n_streams; t->W = cfg->width; t->H = cfg->height; t->cap = cfg->max_cnt;
-    t->desc = make_pyr_desc(t->W, t->H, cfg->lk_max_level);
+    // levels for the forward maxLevel, the backward call's maxLevel 1 and the cv::cuda call pattern's 3 (dvfe_set_lk_mode)
+    t->desc = make_pyr_desc(t->W, t->H, cfg->lk_max_level > 3 ? cfg->lk_max_level : 3);
     t->cam0 = make_cam(cfg->cam0);
     t->cam1 = make_cam(cfg->cam1);
     int rc = t->init();
