@@ -589,7 +589,7 @@ __global__ void k_gftt_assign_ids(const GfttJob* __restrict__ jobs, int n_jobs) 
 }
 
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
-                cudaStream_t st, cudaEvent_t* marks) {
+                cudaStream_t st, cudaEvent_t* marks, cudaEvent_t after_response) {
     (void)h_jobs;
     if (n_jobs <= 0) return DVFE_OK;
     int mi = 0;
@@ -614,6 +614,7 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
         DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
     }
     GFTT_MARK();
+    if (after_response) cudaEventRecord(after_response, st);
     DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, 0, st, d_jobs);
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
 #undef GFTT_MARK

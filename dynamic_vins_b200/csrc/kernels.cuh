@@ -73,9 +73,10 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     float min_dist;              // NMS distance
     double quality;              // 0.01
 };
-// marks (nullable): 3 events recorded after the mask fill, the discs and the response kernel
+// marks (nullable): 3 events recorded after the mask fill, the discs and the response kernel;
+// after_response (nullable): recorded between the response kernel and the (few-CTA) selection kernel
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
-                cudaStream_t st, cudaEvent_t* marks = nullptr);
+                cudaStream_t st, cudaEvent_t* marks = nullptr, cudaEvent_t after_response = nullptr);
 int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st);
 int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n, int max_pts, int radius,
                      cudaStream_t st);

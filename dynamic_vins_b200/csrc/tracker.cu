@@ -149,10 +149,13 @@ int dvfe_tracker::init() {
     DVFE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     DVFE_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     DVFE_CUDA(cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking));
+    DVFE_CUDA(cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking));
     for (int p = 0; p < 2; p++) {
         for (int i = 0; i <= ST_COUNT; i++) DVFE_CUDA(cudaEventCreate(&ev[p][i]));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_up[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_packed[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_resp[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_rpyr[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_done[p], cudaEventDisableTiming));
     }
     const size_t P = (size_t)W * H;
@@ -249,6 +252,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->cs) cudaStreamSynchronize(t->cs);
     if (t->ds) cudaStreamSynchronize(t->ds);
+    if (t->rs) cudaStreamSynchronize(t->rs);
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
@@ -256,6 +260,8 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     for (int p = 0; p < 2; p++) {
         cudaFree(t->d_obs[p]); cudaFree(t->d_nobs[p]);
         if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
+        if (t->ev_resp[p]) cudaEventDestroy(t->ev_resp[p]);
+        if (t->ev_rpyr[p]) cudaEventDestroy(t->ev_rpyr[p]);
         cudaFreeHost(t->h_dt[p]); cudaFreeHost(t->h_obs[p]); cudaFreeHost(t->h_nobs[p]);
         if (t->ev_up[p]) cudaEventDestroy(t->ev_up[p]);
         if (t->ev_done[p]) cudaEventDestroy(t->ev_done[p]);
@@ -272,6 +278,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     t->free_instances();
     if (t->cs) cudaStreamDestroy(t->cs);
     if (t->ds) cudaStreamDestroy(t->ds);
+    if (t->rs) cudaStreamDestroy(t->rs);
     if (t->st && t->own_stream) cudaStreamDestroy(t->st);
     delete t;
 }
@@ -291,11 +298,13 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     auto mark = [&](int i) { if (prof) cudaEventRecord(ev[par][i], st); };
 
     mark(0);
+    // left pyramid now; the right pyramid is built on its own stream while the selection kernel (one CTA per
+    // stream) leaves most SMs idle, and joins before the stereo LK
     PyrImgSet set;
-    set.src[0] = d_left; set.src[1] = d_right;
-    set.dst[0] = left_slot(k); set.dst[1] = right_slot(k);
+    set.src[0] = d_left; set.src[1] = nullptr;
+    set.dst[0] = left_slot(k); set.dst[1] = nullptr;
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
-    DVFE_CHECK(launch_build_pyramids(set, stereo_now ? 2 * B : B, desc, pitch, st, level0_in_place));
+    DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
         DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
@@ -304,11 +313,22 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
         DVFE_CHECK(launch_compact(bg, B, cap, st));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
-    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, prof ? &ev[par][ST_GFTT_MASK + 1] : nullptr));
+    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, prof ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
+                           stereo_now ? ev_resp[par] : nullptr));
+    if (stereo_now) {
+        PyrImgSet rset;
+        rset.src[0] = d_right; rset.src[1] = nullptr;
+        rset.dst[0] = right_slot(k); rset.dst[1] = nullptr;
+        rset.src_stride = stream_stride; rset.dst_stride = desc.bytes; rset.per_set = B;
+        DVFE_CUDA(cudaStreamWaitEvent(rs, ev_resp[par], 0));        // after the response kernel of this step (and so
+        DVFE_CHECK(launch_build_pyramids(rset, B, desc, pitch, rs, level0_in_place));   // after the upload it waited for)
+        DVFE_CUDA(cudaEventRecord(ev_rpyr[par], rs));
+    }
     mark(ST_GFTT_SELECT + 1);
     // UndistortedPts(cam0) + PtsVelocity
     DVFE_CHECK(launch_left_post(bg, B, cap, cam0, d_dt, nullptr, st));
     mark(ST_LEFT_POST + 1);
+    if (stereo_now) DVFE_CUDA(cudaStreamWaitEvent(st, ev_rpyr[par], 0));
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
         DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
     mark(ST_LK_STEREO + 1);

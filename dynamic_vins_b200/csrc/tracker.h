@@ -29,6 +29,7 @@ struct dvfe_tracker {
     cudaStream_t st = nullptr;                       // compute stream (caller-replaceable)
     cudaStream_t cs = nullptr;                       // upload stream: H2D of step k+1 overlaps the kernels of step k
     cudaStream_t ds = nullptr;                       // download stream: D2H of step k overlaps the kernels of step k+1
+    cudaStream_t rs = nullptr;                       // right-image pyramid stream: fills the SMs the selection kernel leaves idle
     bool own_stream = true;
     PyrDesc desc{};
     CamParams cam0{}, cam1{};
@@ -49,7 +50,7 @@ struct dvfe_tracker {
     int* d_nobs[2] = {nullptr, nullptr};
     int* h_nobs[2] = {nullptr, nullptr};
     int out_slot = 0;                                // which h_obs holds the newest completed step
-    cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {};
+    cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {}, ev_resp[2] = {}, ev_rpyr[2] = {};
     uint8_t *d_region = nullptr, *d_region_tmp = nullptr, *d_inv_in = nullptr;
     int* d_exist = nullptr;
     int* h_exist = nullptr;
