@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     if (K > NMS_MAX_K) K = NMS_MAX_K;
     int nc = J.counters[0];
     if (nc > J.cand_cap) nc = J.cand_cap;
+    if (tid == 0 && J.counters[2] && J.err) atomicOr(J.err, 1);      // more local maxima than the buffer holds
     if (nc <= 0) return;
 
     // quality threshold: keep lambda > (float)(maxVal * quality)   (cv::threshold THRESH_TOZERO, strict)

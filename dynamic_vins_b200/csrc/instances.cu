@@ -292,6 +292,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             J.n = I.pts.n + set; J.next_id = t->d_next_id + stream;
             J.max_cnt = t->cfg.max_dynamic_cnt; J.min_needed = 1;
             J.disc_radius = t->cfg.min_dynamic_dist; J.min_dist = (float)t->cfg.min_dynamic_dist; J.quality = 0.01;
+            J.err = t->d_err;
             // stereo job: TrackRightByPad — full images, points offset by rect.tl()
             LkGroup& R = I.lk_s.h[j];
             memset(&R, 0, sizeof(R));

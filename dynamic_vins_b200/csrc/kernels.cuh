@@ -61,6 +61,7 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     int* counters;               // [8]: 0 n_precand, 1 masked max (ordered int), 2 overflow flag, 3 n above threshold,
                                  //      4 n_new, 5 M examined, 6 n_accepted
     uint8_t* state;              // scratch [cand_cap]
+    int* err;                    // nullable: sticky error word (bit 0: candidate buffer overflow)
     // point set the discs come from and new corners are appended to
     float2* pts;
     uint32_t* ids;               // nullable

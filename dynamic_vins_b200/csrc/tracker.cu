@@ -168,14 +168,15 @@ int dvfe_tracker::init() {
         DVFE_CUDA(cudaMemcpy(d_next_id, ones.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     DVFE_CHECK(dmalloc(&d_dt, (size_t)B));
+    DVFE_CHECK(dmalloc(&d_err, (size_t)1));
     prev_time.assign(B, 0.0);
     for (int p = 0; p < 2; p++) {
         DVFE_CHECK(dmalloc(&d_obs[p], (size_t)B * 2 * cap));
         DVFE_CHECK(dmalloc(&d_nobs[p], (size_t)B));
         DVFE_CUDA(cudaMallocHost((void**)&h_dt[p], B * sizeof(double)));
         DVFE_CUDA(cudaMallocHost((void**)&h_obs[p], (size_t)B * 2 * cap * sizeof(dvfe_obs)));
-        DVFE_CUDA(cudaMallocHost((void**)&h_nobs[p], B * sizeof(int)));
-        memset(h_nobs[p], 0, B * sizeof(int));
+        DVFE_CUDA(cudaMallocHost((void**)&h_nobs[p], (B + 1) * sizeof(int)));
+        memset(h_nobs[p], 0, (B + 1) * sizeof(int));
     }
     DVFE_CHECK(dmalloc(&d_region, (size_t)B * P));
     DVFE_CHECK(dmalloc(&d_region_tmp, (size_t)B * P));
@@ -237,6 +238,7 @@ int dvfe_tracker::init() {
                 J.disc_radius = cfg.min_dist;
                 J.min_dist = (float)cfg.min_dist;
                 J.quality = 0.01;
+                J.err = d_err;
             }
             DVFE_CHECK(dmalloc(&d_jobs[ph][kind], (size_t)B));
             DVFE_CUDA(cudaMemcpy(d_jobs[ph][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
@@ -256,7 +258,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
-    cudaFree(t->d_next_id); cudaFree(t->d_dt);
+    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFree(t->d_err);
     for (int p = 0; p < 2; p++) {
         cudaFree(t->d_obs[p]); cudaFree(t->d_nobs[p]);
         if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
@@ -338,6 +340,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CUDA(cudaEventRecord(ev_packed[par], st));
     DVFE_CUDA(cudaStreamWaitEvent(ds, ev_packed[par], 0));
     DVFE_CUDA(cudaMemcpyAsync(h_nobs[par], d_nobs[par], B * sizeof(int), cudaMemcpyDeviceToHost, ds));
+    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par] + B, d_err, sizeof(int), cudaMemcpyDeviceToHost, ds));
     DVFE_CUDA(cudaMemcpyAsync(h_obs[par], d_obs[par], (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, ds));
     if (prof) cudaEventRecord(ev[par][ST_D2H + 1], ds);
     DVFE_CUDA(cudaEventRecord(ev_done[par], ds));
@@ -360,6 +363,11 @@ int dvfe_tracker::wait_one() {
     }
     out_slot = par;
     completed++;
+    if (h_nobs[par][B] != 0) {
+        dvfe_set_error("corner detection: more local maxima than the candidate buffer holds (W*H/4 + 4096); "
+                       "the selection of some frame was truncated");
+        return DVFE_ERR_CAPACITY;
+    }
     return DVFE_OK;
 }
 
