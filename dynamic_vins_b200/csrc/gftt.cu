@@ -337,15 +337,33 @@ __device__ __forceinline__ unsigned long long block_select_kth(const unsigned lo
             if ((key & himask) == prefix && pred(i, key)) atomicAdd(&s_hist[(int)((key >> shift) & 255)], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-            int rem = *s_remaining, b = 255;
-            for (; b > 0; b--) {
-                if (s_hist[b] >= rem) break;
-                rem -= s_hist[b];
+        if (tid < 32) {
+            // warp 0: lane l owns bins 255-8l .. 248-8l (descending); find the bin where the count from the top
+            // reaches the remaining rank
+            const int rem = *s_remaining;
+            int c[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { c[q] = s_hist[255 - (8 * tid + q)]; sum += c[q]; }
+            int incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (tid >= off) incl += v;
             }
-            // every key of the selected bucket is wanted: all keys >= this prefix are exactly the k largest
-            *s_remaining = (s_hist[b] == rem) ? 0 : rem;
-            *s_prefix = prefix | ((unsigned long long)b << shift);
+            const int before = incl - sum;
+            const bool mine = before < rem && incl >= rem;
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            if (who == 0) {
+                // fewer keys than the rank (cannot happen for k <= population); keep everything
+                if (tid == 0) { *s_remaining = 0; *s_prefix = prefix; }
+            } else if (mine) {
+                int r = rem - before, q = 0;
+                while (q < 7 && c[q] < r) { r -= c[q]; q++; }
+                const int b = 255 - (8 * tid + q);
+                // every key of the selected bucket is wanted: all keys >= this prefix are exactly the k largest
+                *s_remaining = (c[q] == r) ? 0 : r;
+                *s_prefix = prefix | ((unsigned long long)b << shift);
+            }
         }
         __syncthreads();
     }
@@ -353,6 +371,11 @@ __device__ __forceinline__ unsigned long long block_select_kth(const unsigned lo
 }
 
 #define NMS_SMEM_STATE 16384
+// The cell table and the working keys live in (dynamic) shared memory when they fit: every round of the parallel
+// greedy pass chases cell -> key -> state, and from global memory each hop is an L2 round trip.
+#define NMS_SMEM_CELLS 8192
+#define NMS_SMEM_KEYS 8192
+#define NMS_DYN_SMEM (2 * (NMS_SMEM_CELLS + 2) * 4 + NMS_SMEM_KEYS * 8)
 
 __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __restrict__ jobs) {
     __shared__ int s_part[64];
@@ -362,6 +385,9 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     __shared__ unsigned long long s_prefix;
     __shared__ int s_remaining;
     __shared__ uint8_t s_state[NMS_SMEM_STATE];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    int* const s_cells = reinterpret_cast<int*>(s_dyn);                                               // 2 x (cells + 1)
+    unsigned long long* const s_keys = reinterpret_cast<unsigned long long*>(s_dyn + 2 * (NMS_SMEM_CELLS + 2) * 4);
 
     const GfttJob& J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
@@ -406,8 +432,9 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     const int cell = (int)lrintf(J.min_dist) > 0 ? (int)lrintf(J.min_dist) : 1;
     const int gw = (J.w + cell - 1) / cell, gh = (J.h + cell - 1) / cell;
     const int ncell = gw * gh;
-    int* cstart = J.cell_count;                 // [ncell + 1]
-    int* ccur = J.cell_count + (ncell + 1);     // [ncell + 1]
+    const bool cells_in_smem = ncell + 1 <= NMS_SMEM_CELLS + 1;
+    int* cstart = cells_in_smem ? s_cells : J.cell_count;                  // [ncell + 1]
+    int* ccur = cstart + (ncell + 1);                                      // [ncell + 1]
     const double md2 = (double)J.min_dist * (double)J.min_dist;
     const bool use_nms = J.min_dist >= 1.f;
 
@@ -419,6 +446,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     int M = min(nv, max(512, 16 * K));
     int n_acc = 0;
     volatile uint8_t* state = nullptr;
+    const unsigned long long* fin = work;        // the examined candidates, indexed like `state`
     for (;;) {
         unsigned long long tkey = 0ull;                 // keep keys >= tkey
         if (M < nv) tkey = block_select_kth(valid, nv, M, [&](int, unsigned long long) { return true; }, s_hist, &s_prefix,
@@ -457,7 +485,8 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
                 cs[cstart[c] + pos] = key;
             }
             __syncthreads();
-            // rank-sort every cell (descending) from cs back into work, then swap roles
+            // rank-sort every cell (descending) from cs into the sorted array (shared memory when it fits)
+            unsigned long long* srt_w = (M <= NMS_SMEM_KEYS) ? s_keys : work;
             {
                 const int warp = tid >> 5, lane = tid & 31;
                 for (int c = warp; c < ncell; c += NMS_THREADS / 32) {
@@ -466,14 +495,18 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
                         const unsigned long long key = cs[b + e];
                         int rank = 0;
                         for (int o = 0; o < m; o++) rank += (cs[b + o] > key) ? 1 : 0;
-                        work[b + rank] = key;
+                        srt_w[b + rank] = key;
                     }
                 }
             }
             __syncthreads();
-            const unsigned long long* __restrict__ srt = work;
+            const unsigned long long* srt = srt_w;
+            fin = srt_w;
             for (int i = tid; i < M; i += NMS_THREADS) state[i] = 0;
             __syncthreads();
+            // Decisions are final once written, so no barrier is needed between rounds: every thread keeps sweeping
+            // its own undecided candidates until none is left (the strongest undecided candidate of the block can
+            // always be decided by its owner, so the sweep terminates).
             for (;;) {
                 int undecided = 0;
                 for (int i = tid; i < M; i += NMS_THREADS) {
@@ -506,9 +539,11 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
                     else if (!blocked) state[i] = 1;
                     else undecided = 1;
                 }
-                if (!__syncthreads_or(undecided)) break;
+                if (!__any_sync(0xffffffffu, undecided)) break;      // warp-level: lanes of a warp sweep together
             }
+            __syncthreads();
         } else {
+            fin = work;
             for (int i = tid; i < M; i += NMS_THREADS) state[i] = 1;
             __syncthreads();
         }
@@ -529,7 +564,6 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
     }
 
     // ---- the K strongest accepted keys (all of them if fewer), sorted descending ----
-    const unsigned long long* __restrict__ fin = work;
     int n_sel = n_acc;
     unsigned long long kth = 0ull;
     if (n_acc > K) {
@@ -616,7 +650,9 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
     }
     GFTT_MARK();
     if (after_response) cudaEventRecord(after_response, st);
-    DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, 0, st, d_jobs);
+    // per device attribute; setting it again is a no-op
+    DVFE_CUDA(cudaFuncSetAttribute(k_gftt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_DYN_SMEM));
+    DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, NMS_DYN_SMEM, st, d_jobs);
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
 #undef GFTT_MARK
     DVFE_CUDA(cudaGetLastError());
