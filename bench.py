@@ -279,9 +279,10 @@ def run_dvfe(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8 images, int32/int64 patch sums, fp32 2x2 solve, fp64 undistortion", "data": "synthetic",
+            "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": W, "height": H, "stereo": stereo,
                        "max_cnt": c["max_cnt"], "min_dist": c["min_dist"], "lk": "21x21, maxLevel 3, fwd+bwd",
+                       "arithmetic": "u8 pixels, int32/int64 patch sums, fp32 2x2 solve, fp64 box sums and undistortion",
                        "unique_frames_per_stream": T, "l2": "inputs_larger_than_L2",
                        "tracked_points_per_step": n_left, "observations_per_step": n_obs},
             "clocks": clock_info,
@@ -441,7 +442,7 @@ def run_reference(args):
     c = __import__("dynamic_vins_b200").synth.CONFIGS[WORKLOAD]
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "u8 images, int16 patches, fp32 (OpenCV CPU)", "data": "synthetic",
+           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "width": c["width"], "height": c["height"],
                       "stereo": bool(c["stereo"]), "max_cnt": c["max_cnt"], "min_dist": c["min_dist"],
                       "lk": "21x21, maxLevel 3, fwd+bwd", "unique_frames_per_stream": args.frames},

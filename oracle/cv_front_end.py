@@ -6,7 +6,12 @@ CPU restatement of the reference's point-feature front-end, line by line, over
 legs of `bench.py` may import this module.  The product path
 (`dynamic_vins_b200/`) never does.
 
-Pinning: the reference C++ cannot be built here (ROS, OpenCV-C++ 3.4.16+CUDA, Eigen,
+PARITY UNPINNED against the reference binary: the reference ships no tests, golden vectors or fixtures for this
+path and cannot be built or run here, so nothing produced by the reference itself anchors this oracle.  What IS
+pinned: the OpenCV stages are executed by the third-party library itself (cv2) at the reference's call sites, and
+the plain-C arithmetic spec (oracle/spec.c) is checked against that library.
+
+Pinning details: the reference C++ cannot be built here (ROS, OpenCV-C++ 3.4.16+CUDA, Eigen,
 libtorch, TensorRT, PCL, Ceres are absent) and it ships no tests or golden vectors
 for this path.  The arithmetic lives in a third-party
 dependency, OpenCV (pinned 3.4.16, dynamic_vins/CMakeLists.txt:36; un-vendored).

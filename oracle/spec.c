@@ -1,5 +1,8 @@
 /* ORACLE (test infrastructure, NOT product code).
  *
+ * PARITY UNPINNED against the reference binary (it ships no golden vectors for this path and cannot run here);
+ * pinned against the third-party library that holds the arithmetic (cv2 4.13.0), see below.
+ *
  * Plain-C arithmetic restatement of the OpenCV stages the reference's CPU front-end
  * calls.  The arithmetic lives in a third-party dependency that is NOT under
  * /root/reference: OpenCV, pinned 3.4.16 by dynamic_vins/CMakeLists.txt:36.  The
