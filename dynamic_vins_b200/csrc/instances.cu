@@ -37,6 +37,7 @@ struct InstHost {
     int prev_w = 0, prev_h = 0;    // size of roi->prev_roi_gray (0 = empty)
     int cur_buf = 0;               // which of the two ROI buffers holds roi_gray
     int roi_w = 0, roi_h = 0;      // size of roi->roi_gray
+    long long mask_off = -1;       // offset of this frame's ROI mask in the packed staging (-1: in the slot buffer)
 };
 
 struct InstStream {
@@ -53,20 +54,33 @@ int dmalloc(T** p, size_t count) {
     return DVFE_OK;
 }
 
-// pinned host staging + device copy of a small per-call descriptor array
+// a per-call descriptor array: a view into the tracker's descriptor arena (one pinned blob, one device blob, ONE
+// host-to-device copy per call)
 template <typename T>
 struct Staged {
     T* h = nullptr;
     T* d = nullptr;
-    int cap = 0;
-    int alloc(int n) {
-        cap = n;
-        DVFE_CUDA(cudaMallocHost((void**)&h, sizeof(T) * n));
-        DVFE_CUDA(cudaMalloc((void**)&d, sizeof(T) * n));
+};
+
+struct Arena {
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    size_t cap = 0, used = 0;
+    int alloc(size_t bytes) {
+        cap = bytes;
+        DVFE_CUDA(cudaMallocHost((void**)&h, bytes));
+        DVFE_CUDA(cudaMalloc((void**)&d, bytes));
         return DVFE_OK;
     }
-    int push(int n, cudaStream_t st) {
-        if (n > 0) DVFE_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+    template <typename T>
+    void take(Staged<T>& s, int n) {
+        used = (used + 15) & ~(size_t)15;
+        s.h = reinterpret_cast<T*>(h + used);
+        s.d = reinterpret_cast<T*>(d + used);
+        used += sizeof(T) * (size_t)n;
+    }
+    int push(cudaStream_t st) {
+        DVFE_CUDA(cudaMemcpyAsync(d, h, used, cudaMemcpyHostToDevice, st));
         return DVFE_OK;
     }
     void release() {
@@ -90,7 +104,10 @@ struct InstanceState {
     dvfe_inst_obs* d_out = nullptr;      // [B*MI*cap]
     dvfe_inst_obs* h_out = nullptr;      // pinned
     int* h_n = nullptr;                  // pinned [B*MI]
-    // per-call descriptors (MI entries; one stream per call)
+    // per-call descriptors (MI entries; one stream per call), all inside `arena`
+    Arena arena;
+    uint8_t *h_mask_stage = nullptr, *d_mask_stage = nullptr;    // packed ROI masks of one call (pinned / device)
+    size_t mask_stage_cap = 0;
     Staged<CropJob> crop;
     Staged<PyrJob> pyr;                  // 2*MI
     Staged<LkGroup> lk_t, lk_s;
@@ -128,18 +145,23 @@ int dvfe_tracker::init_instances() {
     DVFE_CHECK(dmalloc(&I.d_out, NS * I.cap));
     DVFE_CUDA(cudaMallocHost((void**)&I.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
     DVFE_CUDA(cudaMallocHost((void**)&I.h_n, NS * sizeof(int)));
-    DVFE_CHECK(I.crop.alloc(I.MI));
-    DVFE_CHECK(I.pyr.alloc(2 * I.MI));
-    DVFE_CHECK(I.lk_t.alloc(I.MI));
-    DVFE_CHECK(I.lk_s.alloc(I.MI));
-    DVFE_CHECK(I.erode.alloc(I.MI));
-    DVFE_CHECK(I.gftt.alloc(I.MI));
-    DVFE_CHECK(I.act_track.alloc(I.MI));
-    DVFE_CHECK(I.act_vis.alloc(I.MI));
-    DVFE_CHECK(I.clear_flags.alloc(I.MI));
-    DVFE_CHECK(I.dt.alloc(I.MI));
-    DVFE_CHECK(I.offs.alloc(I.MI));
-    DVFE_CHECK(I.inst_id.alloc(I.MI));
+    DVFE_CHECK(I.arena.alloc((size_t)I.MI * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
+                                             sizeof(GfttJob) + 3 + sizeof(double) + sizeof(float2) + sizeof(uint32_t)) + 4096));
+    I.arena.take(I.crop, I.MI);
+    I.arena.take(I.pyr, 2 * I.MI);
+    I.arena.take(I.lk_t, I.MI);
+    I.arena.take(I.lk_s, I.MI);
+    I.arena.take(I.erode, I.MI);
+    I.arena.take(I.gftt, I.MI);
+    I.arena.take(I.act_track, I.MI);
+    I.arena.take(I.act_vis, I.MI);
+    I.arena.take(I.clear_flags, I.MI);
+    I.arena.take(I.dt, I.MI);
+    I.arena.take(I.offs, I.MI);
+    I.arena.take(I.inst_id, I.MI);
+    I.mask_stage_cap = 4 * I.P;
+    DVFE_CUDA(cudaMallocHost((void**)&I.h_mask_stage, I.mask_stage_cap));
+    DVFE_CHECK(dmalloc(&I.d_mask_stage, I.mask_stage_cap));
     return DVFE_OK;
 }
 
@@ -151,9 +173,9 @@ void dvfe_tracker::free_instances() {
     cudaFree(I.pyr_prev); cudaFree(I.pyr_cur);
     free_gftt_scratch(&I.gsc);
     cudaFree(I.d_out); cudaFreeHost(I.h_out); cudaFreeHost(I.h_n);
-    I.crop.release(); I.pyr.release(); I.lk_t.release(); I.lk_s.release(); I.erode.release(); I.gftt.release();
-    I.act_track.release(); I.act_vis.release(); I.clear_flags.release(); I.dt.release(); I.offs.release();
-    I.inst_id.release();
+    I.arena.release();
+    if (I.h_mask_stage) cudaFreeHost(I.h_mask_stage);
+    cudaFree(I.d_mask_stage);
     delete inst;
     inst = nullptr;
 }
@@ -201,6 +223,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
 
     // ---- caller's per-frame reset (system/main.cpp:198-202) + AddViodeInstances (dynamic_tracker.cpp:585-605) ----
     for (auto& kv : S.insts) { kv.second.visible = false; kv.second.has_box = false; }
+    size_t mask_used = 0;
     for (int b = 0; b < n_boxes; b++) {
         const dvfe_inst_in& bx = boxes[b];
         if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
@@ -226,10 +249,19 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
         InstHost& in = it->second;
         in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
         in.visible = true; in.has_box = true;
-        // inst.roi->mask_cv = det_box->roi->mask_cv
-        DVFE_CUDA(cudaMemcpy2DAsync(I.roi_mask + (base_set + in.slot) * P, bx.w, bx.mask, bx.mask_pitch, bx.w, bx.h,
-                                    cudaMemcpyHostToDevice, st));
+        // inst.roi->mask_cv = det_box->roi->mask_cv : packed into the pinned staging, uploaded with one copy below
+        const size_t bytes = (size_t)bx.w * bx.h;
+        if (mask_used + bytes <= I.mask_stage_cap) {
+            for (int r = 0; r < bx.h; r++) memcpy(I.h_mask_stage + mask_used + (size_t)r * bx.w, bx.mask + (size_t)r * bx.mask_pitch, bx.w);
+            in.mask_off = (long long)mask_used;
+            mask_used += (bytes + 15) & ~(size_t)15;
+        } else {
+            in.mask_off = -1;      // does not fit the staging area: direct (pageable) copy into the slot buffer
+            DVFE_CUDA(cudaMemcpy2DAsync(I.roi_mask + (base_set + in.slot) * P, bx.w, bx.mask, bx.mask_pitch, bx.w, bx.h,
+                                        cudaMemcpyHostToDevice, st));
+        }
     }
+    if (mask_used > 0) DVFE_CUDA(cudaMemcpyAsync(I.d_mask_stage, I.h_mask_stage, mask_used, cudaMemcpyHostToDevice, st));
     // ---- lost_num bookkeeping (:355-362) ----
     for (auto& kv : S.insts) {
         if (!kv.second.visible) kv.second.lost_num++;
@@ -281,7 +313,8 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             }
             // detection job (:418-446)
             ErodeJob& e = I.erode.h[j];
-            e.src = I.roi_mask + set * P; e.tmp = I.roi_mask_tmp + set * P; e.dst = I.roi_mask_er + set * P;
+            e.src = in.mask_off >= 0 ? I.d_mask_stage + in.mask_off : I.roi_mask + set * P;
+            e.tmp = I.roi_mask_tmp + set * P; e.dst = I.roi_mask_er + set * P;
             e.w = in.w; e.h = in.h; e.k = 5;
             GfttJob& J = I.gftt.h[j];
             memset(&J, 0, sizeof(J));
@@ -300,10 +333,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             R.ptsA = I.pts.pts + set * cap; R.ptsB = I.pts.rpts + set * cap; R.status = I.pts.rstatus + set * cap;
             R.n = I.pts.n + set; R.offx = (float)in.x; R.offy = (float)in.y;
         }
-        DVFE_CHECK(I.crop.push(nv, st)); DVFE_CHECK(I.pyr.push(2 * n_track, st)); DVFE_CHECK(I.lk_t.push(n_track, st));
-        DVFE_CHECK(I.lk_s.push(nv, st)); DVFE_CHECK(I.erode.push(nv, st)); DVFE_CHECK(I.gftt.push(nv, st));
-        DVFE_CHECK(I.act_track.push(MI, st)); DVFE_CHECK(I.act_vis.push(MI, st)); DVFE_CHECK(I.dt.push(MI, st));
-        DVFE_CHECK(I.offs.push(MI, st)); DVFE_CHECK(I.inst_id.push(MI, st));
+        DVFE_CHECK(I.arena.push(st));          // every descriptor array of this call in one copy
 
         // per-stream views of the point sets (MI sets)
         PointSetArrays V = I.pts;
@@ -353,7 +383,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
         for (auto& kv : S.insts)
             if (kv.second.lost_num == 0) { I.clear_flags.h[kv.second.slot] = 1; any = true; }
         if (any) {
-            DVFE_CHECK(I.clear_flags.push(MI, st));
+            DVFE_CHECK(I.arena.push(st));
             DVFE_CHECK(launch_clear_sets(I.pts.n + base_set, I.clear_flags.d, MI, st));
             DVFE_CUDA(cudaStreamSynchronize(st));
         }
