@@ -102,6 +102,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(gpu_index: int) -> str:
+    """Best effort: run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers the
+    e2e leg uploads from live on that GPU's NUMA node (matters when 8 ranks upload at once)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wv in enumerate(words) for b in range(64) if (int(wv) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} GPU-local CPUs"
+    except Exception as e:      # no NVML, no permission, ... : keep the default placement
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def gpu_frames(stream, T: int, device):
     """The `T` unique stereo frames of one synthetic stream, rendered on the GPU with the same formulas as
     dynamic_vins_b200.synth.SynthStream._view (float64).  Returns uint8 tensor [T][2][H][W]."""
@@ -164,6 +183,8 @@ def run_dvfe(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = bind_to_gpu_cpus(local)      # pinned host buffers are then first-touched on the GPU's NUMA node
 
     def barrier():
         torch.cuda.synchronize()
@@ -294,7 +315,9 @@ def run_dvfe(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom]},
         }
+        out["config"]["host_placement"] = numa_note
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every host core
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
             out["parity"] = parity_sample(local)
             out["single_stream"] = single_stream_latency(local)
