@@ -145,21 +145,21 @@ int dvfe_tracker::init_instances() {
     DVFE_CHECK(dmalloc(&I.d_out, NS * I.cap));
     DVFE_CUDA(cudaMallocHost((void**)&I.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
     DVFE_CUDA(cudaMallocHost((void**)&I.h_n, NS * sizeof(int)));
-    DVFE_CHECK(I.arena.alloc((size_t)I.MI * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
+    DVFE_CHECK(I.arena.alloc(NS * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
                                              sizeof(GfttJob) + 3 + sizeof(double) + sizeof(float2) + sizeof(uint32_t)) + 4096));
-    I.arena.take(I.crop, I.MI);
-    I.arena.take(I.pyr, 2 * I.MI);
-    I.arena.take(I.lk_t, I.MI);
-    I.arena.take(I.lk_s, I.MI);
-    I.arena.take(I.erode, I.MI);
-    I.arena.take(I.gftt, I.MI);
-    I.arena.take(I.act_track, I.MI);
-    I.arena.take(I.act_vis, I.MI);
-    I.arena.take(I.clear_flags, I.MI);
-    I.arena.take(I.dt, I.MI);
-    I.arena.take(I.offs, I.MI);
-    I.arena.take(I.inst_id, I.MI);
-    I.mask_stage_cap = 4 * I.P;
+    I.arena.take(I.crop, (int)NS);
+    I.arena.take(I.pyr, 2 * (int)NS);
+    I.arena.take(I.lk_t, (int)NS);
+    I.arena.take(I.lk_s, (int)NS);
+    I.arena.take(I.erode, (int)NS);
+    I.arena.take(I.gftt, (int)NS);
+    I.arena.take(I.act_track, (int)NS);
+    I.arena.take(I.act_vis, (int)NS);
+    I.arena.take(I.clear_flags, (int)NS);
+    I.arena.take(I.dt, (int)NS);
+    I.arena.take(I.offs, (int)NS);
+    I.arena.take(I.inst_id, (int)NS);
+    I.mask_stage_cap = (size_t)(B < 4 ? 4 : B) * I.P;      // ROI masks of one call, packed
     DVFE_CUDA(cudaMallocHost((void**)&I.h_mask_stage, I.mask_stage_cap));
     DVFE_CHECK(dmalloc(&I.d_mask_stage, I.mask_stage_cap));
     return DVFE_OK;
@@ -197,90 +197,98 @@ static void manage_instances(InstStream& S) {
     }
 }
 
-extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n_boxes, double time0) {
-    if (!t || !t->inst || stream < 0 || stream >= t->B || n_boxes < 0 || (n_boxes > 0 && !boxes)) {
-        dvfe_set_error("insts_track: bad argument (max_instances must be > 0 at create)");
-        return DVFE_ERR_INVALID;
-    }
-    if (t->frames == 0) {
-        dvfe_set_error("insts_track: no frame has been uploaded yet (call dvfe_track_semantic_image first)");
-        return DVFE_ERR_INVALID;
-    }
+// InstsTrack for the streams [s0, s1): boxes_of[s - s0] / n_of[s - s0] / time_of[s - s0].  Every visible instance of
+// every stream is one job of each batched launch; one descriptor upload, one mask upload, one synchronisation.
+static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of,
+                               const double* time_of) {
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     InstanceState& I = *t->inst;
-    InstStream& S = I.streams[stream];
     cudaStream_t st = t->st;
-    const int W = t->W, H = t->H, MI = I.MI, cap = I.cap;
+    const int W = t->W, H = t->H, MI = I.MI, cap = I.cap, B = t->B;
     const size_t P = I.P;
-    const size_t base_set = (size_t)stream * MI;
+    const int NS = B * MI;
     // the frame uploaded by the last background step
     const PyrLevel& L0 = t->desc.lv[0];
-    const uint8_t* left_pyr = t->left_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
-    const uint8_t* right_pyr = t->right_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
-    const uint8_t* left_px = left_pyr + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
     const bool stereo_now = t->cfg.stereo && t->last_has_right;
 
-    // ---- caller's per-frame reset (system/main.cpp:198-202) + AddViodeInstances (dynamic_tracker.cpp:585-605) ----
-    for (auto& kv : S.insts) { kv.second.visible = false; kv.second.has_box = false; }
+    memset(I.act_track.h, 0, NS); memset(I.act_vis.h, 0, NS); memset(I.clear_flags.h, 0, NS);
     size_t mask_used = 0;
-    for (int b = 0; b < n_boxes; b++) {
-        const dvfe_inst_in& bx = boxes[b];
-        if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
-            bx.mask_pitch < bx.w) {
-            dvfe_set_error("insts_track: box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask", b, bx.x, bx.y,
-                           bx.w, bx.h, W, H);
-            return DVFE_ERR_INVALID;
-        }
-        auto it = S.insts.find(bx.track_id);
-        if (it == S.insts.end()) {
-            if (S.free_slots.empty()) {
-                dvfe_set_error("insts_track: more than max_instances=%d live instances in stream %d", MI, stream);
-                return DVFE_ERR_CAPACITY;
-            }
-            InstHost in;
-            in.track_id = bx.track_id;
-            in.slot = S.free_slots.back();
-            S.free_slots.pop_back();
-            const int zero = 0;
-            DVFE_CUDA(cudaMemcpyAsync(I.pts.n + base_set + in.slot, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
-            it = S.insts.emplace(bx.track_id, in).first;
-        }
-        InstHost& in = it->second;
-        in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
-        in.visible = true; in.has_box = true;
-        // inst.roi->mask_cv = det_box->roi->mask_cv : packed into the pinned staging, uploaded with one copy below
-        const size_t bytes = (size_t)bx.w * bx.h;
-        if (mask_used + bytes <= I.mask_stage_cap) {
-            for (int r = 0; r < bx.h; r++) memcpy(I.h_mask_stage + mask_used + (size_t)r * bx.w, bx.mask + (size_t)r * bx.mask_pitch, bx.w);
-            in.mask_off = (long long)mask_used;
-            mask_used += (bytes + 15) & ~(size_t)15;
-        } else {
-            in.mask_off = -1;      // does not fit the staging area: direct (pageable) copy into the slot buffer
-            DVFE_CUDA(cudaMemcpy2DAsync(I.roi_mask + (base_set + in.slot) * P, bx.w, bx.mask, bx.mask_pitch, bx.w, bx.h,
-                                        cudaMemcpyHostToDevice, st));
-        }
-    }
-    if (mask_used > 0) DVFE_CUDA(cudaMemcpyAsync(I.d_mask_stage, I.h_mask_stage, mask_used, cudaMemcpyHostToDevice, st));
-    // ---- lost_num bookkeeping (:355-362) ----
-    for (auto& kv : S.insts) {
-        if (!kv.second.visible) kv.second.lost_num++;
-        else kv.second.lost_num = 0;
-    }
-    const bool exist_inst = n_boxes > 0;
-    S.out.clear();
+    int nv = 0, n_track = 0, max_rw = 1, max_rh = 1, max_pw = 1, max_ph = 1, max_lv = 1;
+    bool any_clear = false;
+    std::vector<char> exist(s1 - s0, 0);
 
-    if (exist_inst) {
+    for (int stream = s0; stream < s1; stream++) {
+        InstStream& S = I.streams[stream];
+        const dvfe_inst_in* boxes = boxes_of[stream - s0];
+        const int n_boxes = n_of[stream - s0];
+        const double time0 = time_of[stream - s0];
+        const size_t base_set = (size_t)stream * MI;
+        const uint8_t* left_pyr = t->left_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
+        const uint8_t* right_pyr = t->right_slot(t->frames - 1) + (size_t)stream * t->desc.bytes;
+        const uint8_t* left_px = left_pyr + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+
+        // ---- caller's per-frame reset (system/main.cpp:198-202) + AddViodeInstances (dynamic_tracker.cpp:585-605) ----
+        for (auto& kv : S.insts) { kv.second.visible = false; kv.second.has_box = false; }
+        for (int b = 0; b < n_boxes; b++) {
+            const dvfe_inst_in& bx = boxes[b];
+            if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
+                bx.mask_pitch < bx.w) {
+                dvfe_set_error("insts_track: stream %d box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask",
+                               stream, b, bx.x, bx.y, bx.w, bx.h, W, H);
+                return DVFE_ERR_INVALID;
+            }
+            auto it = S.insts.find(bx.track_id);
+            if (it == S.insts.end()) {
+                if (S.free_slots.empty()) {
+                    dvfe_set_error("insts_track: more than max_instances=%d live instances in stream %d", MI, stream);
+                    return DVFE_ERR_CAPACITY;
+                }
+                InstHost in;
+                in.track_id = bx.track_id;
+                in.slot = S.free_slots.back();
+                S.free_slots.pop_back();
+                const int zero = 0;
+                DVFE_CUDA(cudaMemcpyAsync(I.pts.n + base_set + in.slot, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+                it = S.insts.emplace(bx.track_id, in).first;
+            }
+            InstHost& in = it->second;
+            in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
+            in.visible = true; in.has_box = true;
+            // inst.roi->mask_cv = det_box->roi->mask_cv : packed into the pinned staging, uploaded with one copy below
+            const size_t bytes = (size_t)bx.w * bx.h;
+            if (mask_used + bytes <= I.mask_stage_cap) {
+                for (int r = 0; r < bx.h; r++)
+                    memcpy(I.h_mask_stage + mask_used + (size_t)r * bx.w, bx.mask + (size_t)r * bx.mask_pitch, bx.w);
+                in.mask_off = (long long)mask_used;
+                mask_used += (bytes + 15) & ~(size_t)15;
+            } else {
+                in.mask_off = -1;      // does not fit the staging area: direct (pageable) copy into the slot buffer
+                DVFE_CUDA(cudaMemcpy2DAsync(I.roi_mask + (base_set + in.slot) * P, bx.w, bx.mask, bx.mask_pitch, bx.w, bx.h,
+                                            cudaMemcpyHostToDevice, st));
+            }
+        }
+        // ---- lost_num bookkeeping (:355-362) ----
+        for (auto& kv : S.insts) {
+            if (!kv.second.visible) kv.second.lost_num++;
+            else kv.second.lost_num = 0;
+        }
+        S.out.clear();
+        exist[stream - s0] = n_boxes > 0;
+        if (!exist[stream - s0]) {
+            manage_instances(S);
+            // ClearState (:41-58) for the instances ExecInst still visits (lost_num == 0)
+            for (auto& kv : S.insts)
+                if (kv.second.lost_num == 0) { I.clear_flags.h[base_set + kv.second.slot] = 1; any_clear = true; }
+            S.last_time = time0;
+            continue;
+        }
         // jobs in ascending instance id; every job is a visible instance (lost_num == 0)
-        std::vector<InstHost*> vis;
-        for (auto& kv : S.insts)
-            if (kv.second.lost_num == 0) vis.push_back(&kv.second);
-        const int nv = (int)vis.size();
-        memset(I.act_track.h, 0, MI); memset(I.act_vis.h, 0, MI);
-        int n_track = 0, max_rw = 1, max_rh = 1, max_pw = 1, max_ph = 1, max_lv = 1;
-        for (int j = 0; j < nv; j++) {
-            InstHost& in = *vis[j];
+        for (auto& kv : S.insts) {
+            InstHost& in = kv.second;
+            if (in.lost_num != 0) continue;
             const size_t set = base_set + in.slot;
+            const int j = nv++;
             // roi_gray = gray0(rect): crop into the buffer that does not hold prev_roi_gray
             in.cur_buf = in.prev_w > 0 ? 1 - in.cur_buf : in.cur_buf;
             in.roi_w = in.w; in.roi_h = in.h;
@@ -288,10 +296,10 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             c.src = left_px; c.spitch = L0.pitch; c.x = in.x; c.y = in.y; c.w = in.w; c.h = in.h;
             c.dst = I.roi_gray + (set * 2 + in.cur_buf) * P;
             max_rw = std::max(max_rw, in.w); max_rh = std::max(max_rh, in.h);
-            I.act_vis.h[in.slot] = 1;
-            I.dt.h[in.slot] = time0 - S.last_time;                      // curr_time - last_time
-            I.offs.h[in.slot] = make_float2((float)in.x, (float)in.y);    // box2d->rect.tl()
-            I.inst_id.h[in.slot] = in.track_id;
+            I.act_vis.h[set] = 1;
+            I.dt.h[set] = time0 - S.last_time;                         // curr_time - last_time
+            I.offs.h[set] = make_float2((float)in.x, (float)in.y);       // box2d->rect.tl()
+            I.inst_id.h[set] = in.track_id;
             if (in.prev_w > 0) {
                 // InstanceImagePadding: both crops zero-padded to (max rows, max cols)
                 const int pw = std::max(in.prev_w, in.w), ph = std::max(in.prev_h, in.h);
@@ -307,7 +315,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
                 G.pyrA = a.dst; G.pyrB = b.dst; G.desc = d;
                 G.ptsA = I.pts.pts + set * cap; G.ptsB = I.pts.lk_out + set * cap; G.status = I.pts.status + set * cap;
                 G.n = I.pts.n + set;
-                I.act_track.h[in.slot] = 1;
+                I.act_track.h[set] = 1;
                 max_pw = std::max(max_pw, pw); max_ph = std::max(max_ph, ph); max_lv = std::max(max_lv, d.n_levels);
                 n_track++;
             }
@@ -333,33 +341,44 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             R.ptsA = I.pts.pts + set * cap; R.ptsB = I.pts.rpts + set * cap; R.status = I.pts.rstatus + set * cap;
             R.n = I.pts.n + set; R.offx = (float)in.x; R.offy = (float)in.y;
         }
-        DVFE_CHECK(I.arena.push(st));          // every descriptor array of this call in one copy
+    }
 
-        // per-stream views of the point sets (MI sets)
+    if (mask_used > 0) DVFE_CUDA(cudaMemcpyAsync(I.d_mask_stage, I.h_mask_stage, mask_used, cudaMemcpyHostToDevice, st));
+    if (nv > 0 || any_clear) DVFE_CHECK(I.arena.push(st));          // every descriptor array of this call in one copy
+    const size_t set0 = (size_t)s0 * MI;
+    const int n_sets = (s1 - s0) * MI;
+    if (nv > 0) {
+        // views of the point sets of streams [s0, s1)
         PointSetArrays V = I.pts;
-        const size_t o = base_set * cap;
+        const size_t o = set0 * cap;
         V.pts += o; V.lk_out += o; V.un += o; V.vel += o; V.ids += o; V.track_cnt += o; V.status += o; V.rpts += o;
-        V.rstatus += o; V.rprev_un += o; V.rprev_valid += o; V.n += base_set;
+        V.rstatus += o; V.rprev_un += o; V.rprev_valid += o; V.n += set0;
 
         DVFE_CHECK(launch_crop_jobs(I.crop.d, nv, max_rw, max_rh, st));
         // inst.TrackLeft(roi_gray_padded, prev_roi_gray_padded): previous-box crop -> current-box crop (:381-413)
         DVFE_CHECK(launch_build_pyramids_jobs(I.pyr.d, 2 * n_track, max_pw, max_ph, max_lv, st));
         DVFE_CHECK(launch_lk(I.lk_t.d, n_track, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
-        DVFE_CHECK(launch_compact(V, MI, cap, st, I.act_track.d));
+        DVFE_CHECK(launch_compact(V, n_sets, cap, st, I.act_track.d + set0));
         // ErodeMask(roi mask, 5) + discs(min_dynamic_dist) + goodFeaturesToTrack on the ROI + ids (:418-446)
         DVFE_CHECK(launch_erode_jobs(I.erode.d, nv, max_rw, max_rh, st));
         DVFE_CHECK(launch_gftt(I.gftt.d, nullptr, nv, max_rw, max_rh, cap, st));
         // UndistortedPointsWithAddOffset(cam0) + PtsVelocity(curr_time - last_time) (:448-457)
-        DVFE_CHECK(launch_left_post(V, MI, cap, t->cam0, I.dt.d, I.offs.d, st, I.act_vis.d));
+        DVFE_CHECK(launch_left_post(V, n_sets, cap, t->cam0, I.dt.d + set0, I.offs.d + set0, st, I.act_vis.d + set0));
         // TrackRightByPad + RightUndistortedPts + RightPtsVelocity (:462-471), then the Output() records
         if (stereo_now) DVFE_CHECK(launch_lk(I.lk_s.d, nv, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
-        DVFE_CHECK(launch_inst_post_pack(V, MI, cap, t->cam1, I.dt.d, I.act_vis.d, stereo_now ? 1 : 0, I.inst_id.d,
-                                         I.d_out + o, st));
-        DVFE_CUDA(cudaMemcpyAsync(I.h_n + base_set, I.pts.n + base_set, MI * sizeof(int), cudaMemcpyDeviceToHost, st));
-        DVFE_CUDA(cudaMemcpyAsync(I.h_out + o, I.d_out + o, (size_t)MI * cap * sizeof(dvfe_inst_obs), cudaMemcpyDeviceToHost,
-                                  st));
-        DVFE_CUDA(cudaStreamSynchronize(st));
+        DVFE_CHECK(launch_inst_post_pack(V, n_sets, cap, t->cam1, I.dt.d + set0, I.act_vis.d + set0, stereo_now ? 1 : 0,
+                                         I.inst_id.d + set0, I.d_out + o, st));
+        DVFE_CUDA(cudaMemcpyAsync(I.h_n + set0, I.pts.n + set0, n_sets * sizeof(int), cudaMemcpyDeviceToHost, st));
+        DVFE_CUDA(cudaMemcpyAsync(I.h_out + o, I.d_out + o, (size_t)n_sets * cap * sizeof(dvfe_inst_obs),
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    if (any_clear) DVFE_CHECK(launch_clear_sets(I.pts.n + set0, I.clear_flags.d + set0, n_sets, st));
+    if (nv > 0 || any_clear || mask_used > 0) DVFE_CUDA(cudaStreamSynchronize(st));
 
+    for (int stream = s0; stream < s1; stream++) {
+        if (!exist[stream - s0]) continue;
+        InstStream& S = I.streams[stream];
+        const size_t base_set = (size_t)stream * MI;
         manage_instances(S);                                                      // :474
         // PostProcess for every instance that is still live and not lost (:479-481): prev_roi_gray = roi_gray
         for (auto& kv : S.insts) {
@@ -375,21 +394,43 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
             const int n = I.h_n[set];
             S.out.insert(S.out.end(), I.h_out + set * cap, I.h_out + set * cap + n);
         }
-    } else {
-        manage_instances(S);
-        // ClearState (:41-58) for the instances ExecInst still visits (lost_num == 0)
-        memset(I.clear_flags.h, 0, MI);
-        bool any = false;
-        for (auto& kv : S.insts)
-            if (kv.second.lost_num == 0) { I.clear_flags.h[kv.second.slot] = 1; any = true; }
-        if (any) {
-            DVFE_CHECK(I.arena.push(st));
-            DVFE_CHECK(launch_clear_sets(I.pts.n + base_set, I.clear_flags.d, MI, st));
-            DVFE_CUDA(cudaStreamSynchronize(st));
-        }
+        S.last_time = time_of[stream - s0];
     }
-    S.last_time = time0;
     return DVFE_OK;
+}
+
+static int insts_check(dvfe_tracker* t) {
+    if (!t || !t->inst) {
+        dvfe_set_error("insts_track: bad argument (max_instances must be > 0 at create)");
+        return DVFE_ERR_INVALID;
+    }
+    if (t->frames == 0) {
+        dvfe_set_error("insts_track: no frame has been uploaded yet (call dvfe_track_semantic_image first)");
+        return DVFE_ERR_INVALID;
+    }
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n_boxes, double time0) {
+    DVFE_CHECK(insts_check(t));
+    if (stream < 0 || stream >= t->B || n_boxes < 0 || (n_boxes > 0 && !boxes)) {
+        dvfe_set_error("insts_track: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    return insts_track_streams(t, stream, stream + 1, &boxes, &n_boxes, &time0);
+}
+
+extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0) {
+    DVFE_CHECK(insts_check(t));
+    if (!n_boxes || !time0) { dvfe_set_error("insts_track_batch: null argument"); return DVFE_ERR_INVALID; }
+    std::vector<const dvfe_inst_in*> of(t->B);
+    size_t off = 0;
+    for (int s = 0; s < t->B; s++) {
+        if (n_boxes[s] < 0 || (n_boxes[s] > 0 && !boxes)) { dvfe_set_error("insts_track_batch: bad box count"); return DVFE_ERR_INVALID; }
+        of[s] = boxes + off;
+        off += (size_t)n_boxes[s];
+    }
+    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0);
 }
 
 extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out) {

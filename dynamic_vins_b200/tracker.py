@@ -159,6 +159,22 @@ class BatchTracker:
             arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
         L.check(L.lib().dvfe_insts_track(self._h, stream, arr, len(boxes), float(time0)))
 
+    def insts_track_batch(self, boxes_per_stream: Sequence[Sequence[dict]], time0) -> None:
+        """InstsTrack for all B streams in one set of launches"""
+        flat = [b for bs in boxes_per_stream for b in bs]
+        arr = (L.InstIn * max(1, len(flat)))()
+        keep = []
+        for i, b in enumerate(flat):
+            m = np.ascontiguousarray(b["mask"], np.uint8)
+            keep.append(m)
+            x, y, w, h = b["rect"]
+            arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
+            arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
+        counts = np.asarray([len(bs) for bs in boxes_per_stream], np.int32)
+        assert len(counts) == self.B
+        t = self._times(time0)
+        L.check(L.lib().dvfe_insts_track_batch(self._h, arr, L.ptr(counts), L.ptr(t)))
+
     # ---- outputs -------------------------------------------------------------------------------
     def features(self, stream: int = 0) -> np.ndarray:
         """dvfe_obs records (structured array: id, cam, v[7]) sorted by (id, cam)."""

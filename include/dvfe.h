@@ -168,6 +168,10 @@ int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_
  * Uses the gray0/gray1 uploaded by the last dvfe_track_semantic_image call of that stream. */
 int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* insts, int n_insts, double time0);
 
+/* The same for ALL streams of the tracker in one set of launches: `insts` holds the boxes stream by stream
+ * (n_insts[0] boxes of stream 0, then n_insts[1] of stream 1, ...), time0[s] per stream. */
+int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* insts, const int* n_insts, const double* time0);
+
 /* FeatureBackground of stream s of the last step: n_out records, sorted by (id, cam). */
 int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out);
 /* InstsFeatManager::Output() (front_end/dynamic_tracker.cpp:521-577), sorted by (inst_id, id). */

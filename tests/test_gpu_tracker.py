@@ -450,3 +450,33 @@ def test_lk_mode_cuda_call_pattern_vs_oracle():
     with pytest.raises(dv.DvfeError):
         trk.set_lk_mode(9, 1.0)
     trk.close()
+
+
+def test_dynamic_mode_batched_streams_equal_single():
+    """dvfe_insts_track_batch over B streams == per-stream dvfe_insts_track on single-stream trackers, bit for bit
+    (including a stream that has no detections in one frame)"""
+    name, B, T = "c3_zed_dynamic", 2, 5
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    batch = BatchTracker(cfg_of(name, n_streams=B, max_instances=8))
+    singles = [BatchTracker(cfg_of(name, max_instances=8)) for _ in range(B)]
+    for k in range(T):
+        frs = [s.frame(k) for s in streams]
+        if k == 2:                                   # stream 1 loses all detections for one frame
+            frs[1].boxes, frs[1].exist_inst = [], False
+            frs[1].inv_merge_mask = np.full_like(frs[1].inv_merge_mask, 255)
+        L = np.stack([f.gray0 for f in frs]); R = np.stack([f.gray1 for f in frs])
+        M = np.stack([f.inv_merge_mask for f in frs])
+        batch.track_semantic_image(L, R, M, [int(f.exist_inst) for f in frs], [f.time0 for f in frs])
+        batch.insts_track_batch([f.boxes for f in frs], [f.time0 for f in frs])
+        for s in range(B):
+            singles[s].track_semantic_image(frs[s].gray0, frs[s].gray1, frs[s].inv_merge_mask, int(frs[s].exist_inst), frs[s].time0)
+            singles[s].insts_track(0, frs[s].boxes, frs[s].time0)
+            assert batch.features(s).tobytes() == singles[s].features(0).tobytes()
+            a, b = batch.insts_output(s), singles[s].insts_output(0)
+            assert a.tobytes() == b.tobytes()
+            if k == 2 and s == 1:
+                assert len(a) == 0
+            else:
+                assert len(a) > 300
+    batch.close()
+    [s.close() for s in singles]
