@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="dvfe", choices=["dvfe", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU")
-    ap.add_argument("--workload", default=WORKLOAD, choices=["c1_euroc_mono", "c2_kitti_stereo", "c4_hd_stereo", "c5_zed_streams"],
+    ap.add_argument("--workload", default=WORKLOAD, choices=["c1_euroc_mono", "c2_kitti_stereo", "c3_zed_dynamic", "c4_hd_stereo", "c5_zed_streams"],
                     help="BASELINE.json config shape of every stream (default: configs[4], the metric's configuration)")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -326,11 +326,77 @@ def run_dvfe(args):
         dist.destroy_process_group()
 
 
+def run_dvfe_dynamic(args):
+    """BASELINE.json configs[2]: dynamic mode (TrackSemanticImage + InstsTrack + Output) on S streams of 1280x720
+    stereo with 8 instance masks each.  Host buffers in, records out, every call synchronous: the number reported is
+    end to end (there is no device-resident variant of the instance interface).  8 distinct synthetic streams are
+    replicated to S streams (the numpy scene generator is slow); single GPU only."""
+    import torch
+    from dynamic_vins_b200 import BatchTracker, lib, make_config, synth
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    c = dict(synth.CONFIGS[WORKLOAD])
+    S, T = args.streams, min(args.frames, 6)
+    base = [synth.make_stream(WORKLOAD, s) for s in range(min(8, S))]
+    frames = [[st.frame(k) for st in base] for k in range(T)]
+    def stack(k, attr):     # pinned host memory, like the headline workload's e2e leg
+        a = np.stack([getattr(frames[k][s % len(base)], attr) for s in range(S)])
+        return torch.from_numpy(a).pin_memory().numpy()
+    Ls = [stack(k, "gray0") for k in range(T)]; Rs = [stack(k, "gray1") for k in range(T)]
+    Ms = [stack(k, "inv_merge_mask") for k in range(T)]
+    boxes = [[frames[k][s % len(base)].boxes for s in range(S)] for k in range(T)]
+    cfg = make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S,
+                      max_dynamic_cnt=c["max_dynamic_cnt"], min_dynamic_dist=c["min_dynamic_dist"],
+                      use_mask_morphology=c["use_mask_morphology"], mask_morphology_size=c["mask_morphology_size"],
+                      max_instances=8, device=local)
+    trk = BatchTracker(cfg)
+    order = synth.pingpong_positions(T, args.warmup + args.steps)
+    def step(i):
+        k = order[i]
+        t = 0.05 * (i + 1)
+        trk.track_semantic_image(Ls[k], Rs[k], Ms[k], [1] * S, t)
+        trk.insts_track_batch(boxes[k], t)
+    for i in range(args.warmup):
+        step(i)
+    launches0 = lib().dvfe_kernel_launches()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_inst = sum(len(trk.insts_output(s)) for s in range(S))
+    n_bg = sum(int((trk.features(s)["cam"] == 0).sum()) for s in range(S))
+    value = S * args.steps / dt
+    mask_bytes = sum(b["mask"].size for b in boxes[0][0]) * S
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": c["width"], "height": c["height"], "stereo": True,
+                      "mode": "dynamic: TrackSemanticImage + InstsTrack(8 instances) + Output", "max_cnt": c["max_cnt"],
+                      "max_dynamic_cnt": c["max_dynamic_cnt"], "background_points_per_step": n_bg,
+                      "instance_points_per_step": n_inst, "timing": "wall clock, synchronous host-buffer calls"},
+           "e2e": {"value": value, "unit": UNIT, "ms_per_step": dt / args.steps * 1e3,
+                   "h2d_bytes_per_step": int(3 * S * c["width"] * c["height"] + mask_bytes), "d2h_bytes_per_step": None},
+           "gpu_launches": int(lib().dvfe_kernel_launches() - launches0)}
+    trk.close()
+    print(json.dumps(out), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------------
 def _oracle_frontend(stream_id: int, workload: str = None):
     from dynamic_vins_b200 import synth
     from oracle import cv_front_end as cvfe
-    c = synth.CONFIGS[workload or WORKLOAD]
+    wl = workload or WORKLOAD
+    c = synth.CONFIGS[wl]
+    if wl == "c3_zed_dynamic":
+        st = synth.make_stream(wl, stream_id % 8)
+        P = cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"], max_dynamic_cnt=c["max_dynamic_cnt"],
+                                min_dynamic_dist=c["min_dynamic_dist"], use_mask_morphology=c["use_mask_morphology"],
+                                mask_morphology_size=c["mask_morphology_size"], is_stereo=True)
+        return st, cvfe.FrontEnd(P, c["cam0"], c["cam1"], "dynamic")
     st = synth.SynthStream(c["width"], c["height"], seed=1000 * c["config_id"] + stream_id, stereo=c["stereo"])
     fe = cvfe.FrontEnd(cvfe.FrontEndParams(max_cnt=c["max_cnt"], min_dist=c["min_dist"], is_stereo=c["stereo"]),
                        c["cam0"], c["cam1"], "raw")
@@ -421,7 +487,11 @@ def _ref_worker(wid: int, T: int, conn, workload: str):
         order = pingpong_positions(T, i + msg + 1)
         for _ in range(msg):
             fr = frames[order[i]]
-            fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
+            if fe.mode == "dynamic":
+                fr.time0 = 0.05 * (i + 1)
+                fe.step(fr)
+            else:
+                fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
             i += 1
         conn.send(i)
 
@@ -481,5 +551,7 @@ if __name__ == "__main__":
     WORKLOAD = a.workload
     if a.impl == "reference":
         run_reference(a)
+    elif WORKLOAD == "c3_zed_dynamic":
+        run_dvfe_dynamic(a)
     else:
         run_dvfe(a)
