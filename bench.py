@@ -182,6 +182,8 @@ def run_dvfe(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries one JSON line
         dist.init_process_group("nccl", device_id=dev)
     all_cpus = os.sched_getaffinity(0)
     numa_note = bind_to_gpu_cpus(local)      # pinned host buffers are then first-touched on the GPU's NUMA node
