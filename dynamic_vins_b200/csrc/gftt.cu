@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 // Nothing but the pre-candidates (local maxima with mask != 0) and the masked maximum leaves the chip; the
 // quality threshold needs the global maximum and is applied by the selection kernel.
 #define RS_COLS 28
+#ifndef RS_ROWS
 #define RS_ROWS 48
+#endif
 #define RS_WARPS 8
 
 template <bool WRITE_EIG, bool EMIT>
