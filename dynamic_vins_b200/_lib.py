@@ -32,7 +32,7 @@ class Config(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("width", "height", "n_streams", "stereo", "max_cnt", "min_dist",
                                        "max_dynamic_cnt", "min_dynamic_dist", "flow_back", "use_mask_morphology",
                                        "mask_morphology_size", "lk_max_level", "max_instances", "device")] + \
-               [("cam0", Camera), ("cam1", Camera)]
+               [("cam0", Camera), ("cam1", Camera), ("n_groups", C.c_int), ("reserved", C.c_int)]
 
 
 class Obs(C.Structure):

@@ -399,6 +399,10 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
     return DVFE_OK;
 }
 
+int grp_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n, double time0);
+int grp_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0);
+int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
+
 static int insts_check(dvfe_tracker* t) {
     if (!t || !t->inst) {
         dvfe_set_error("insts_track: bad argument (max_instances must be > 0 at create)");
@@ -412,6 +416,7 @@ static int insts_check(dvfe_tracker* t) {
 }
 
 extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n_boxes, double time0) {
+    if (t && !t->groups.empty()) return grp_insts_track(t, stream, boxes, n_boxes, time0);
     DVFE_CHECK(insts_check(t));
     if (stream < 0 || stream >= t->B || n_boxes < 0 || (n_boxes > 0 && !boxes)) {
         dvfe_set_error("insts_track: bad argument");
@@ -421,6 +426,10 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
 }
 
 extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0) {
+    if (t && !t->groups.empty()) {
+        if (!n_boxes || !time0) { dvfe_set_error("insts_track_batch: null argument"); return DVFE_ERR_INVALID; }
+        return grp_insts_track_batch(t, boxes, n_boxes, time0);
+    }
     DVFE_CHECK(insts_check(t));
     if (!n_boxes || !time0) { dvfe_set_error("insts_track_batch: null argument"); return DVFE_ERR_INVALID; }
     std::vector<const dvfe_inst_in*> of(t->B);
@@ -434,6 +443,11 @@ extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes
 }
 
 extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out) {
+    if (t && !t->groups.empty()) {
+        dvfe_tracker* leaf; int local;
+        DVFE_CHECK(grp_route(t, stream, &leaf, &local));
+        return dvfe_insts_output(leaf, local, out, cap, n_out);
+    }
     if (!t || !t->inst || stream < 0 || stream >= t->B || !n_out) {
         dvfe_set_error("insts_output: bad argument");
         return DVFE_ERR_INVALID;

@@ -28,6 +28,21 @@ void dvfe_set_error(const char* fmt, ...) {
         if (rc__ != DVFE_OK) return rc__; \
     } while (0)
 
+// groups.cu
+int grp_create(const dvfe_config* cfg, dvfe_tracker** out);
+void grp_destroy(dvfe_tracker* t);
+int grp_track_image_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stride, int pitch,
+                          const double* time0, bool device);
+int grp_wait(dvfe_tracker* t);
+int grp_wait_all(dvfe_tracker* t);
+int grp_track_semantic(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv, size_t stride, int pitch,
+                       const int* exist, const double* time0);
+int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
+int grp_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb);
+int grp_profile(dvfe_tracker* t, int enable);
+int grp_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps);
+#define IS_GROUP(t) ((t) != nullptr && !(t)->groups.empty())
+
 template <typename T>
 static int dmalloc(T** p, size_t count) {
     DVFE_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
@@ -131,6 +146,7 @@ extern "C" int dvfe_create(const dvfe_config* cfg, dvfe_tracker** out) {
         return DVFE_ERR_CONFIG;
     }
     DVFE_CHECK(check_device(cfg->device));
+    if (cfg->n_groups > 1 && cfg->n_streams > 1) return grp_create(cfg, out);
     dvfe_tracker* t = new (std::nothrow) dvfe_tracker();
     if (!t) return DVFE_ERR_CAPACITY;
     t->cfg = *cfg;
@@ -250,6 +266,7 @@ int dvfe_tracker::init() {
 
 extern "C" void dvfe_destroy(dvfe_tracker* t) {
     if (!t) return;
+    if (IS_GROUP(t)) { grp_destroy(t); return; }
     cudaSetDevice(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->cs) cudaStreamSynchronize(t->cs);
@@ -441,6 +458,7 @@ static int check_step_args(dvfe_tracker* t, const uint8_t* left, int pitch, cons
 extern "C" int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
                                       int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
+    if (IS_GROUP(t)) return grp_track_image_async(t, left, right, stream_stride, pitch, time0, false);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     if (t->staged_upload) {
         const size_t P = (size_t)t->W * t->H;
@@ -455,6 +473,7 @@ extern "C" int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, cons
 
 extern "C" int dvfe_wait(dvfe_tracker* t) {
     if (!t) { dvfe_set_error("wait: null tracker"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_wait(t);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     return t->wait_one();
 }
@@ -462,12 +481,17 @@ extern "C" int dvfe_wait(dvfe_tracker* t) {
 extern "C" int dvfe_track_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, size_t stream_stride,
                                 int pitch, const double* time0) {
     DVFE_CHECK(dvfe_track_image_async(t, left, right, stream_stride, pitch, time0));
-    return t->wait_all();
+    return IS_GROUP(t) ? grp_wait_all(t) : t->wait_all();
 }
 
 extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
                                        size_t stream_stride, int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, d_left, pitch, time0));
+    if (IS_GROUP(t)) {
+        DVFE_CHECK(grp_wait_all(t));
+        DVFE_CHECK(grp_track_image_async(t, d_left, d_right, stream_stride, pitch, time0, true));
+        return grp_wait_all(t);
+    }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     DVFE_CHECK(t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr));
@@ -477,6 +501,7 @@ extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, c
 extern "C" int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right,
                                              size_t stream_stride, int pitch, const double* time0) {
     DVFE_CHECK(check_step_args(t, d_left, pitch, time0));
+    if (IS_GROUP(t)) return grp_track_image_async(t, d_left, d_right, stream_stride, pitch, time0, true);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     while (t->frames - t->completed >= 2) DVFE_CHECK(t->wait_one());
     return t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr);
@@ -487,6 +512,7 @@ extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_t
         dvfe_set_error("set_lk_mode: bad argument");
         return DVFE_ERR_INVALID;
     }
+    if (IS_GROUP(t)) return grp_set_lk_mode(t, back_max_level, fb_threshold);
     t->lk_back_level = back_max_level;
     t->lk_fb_thresh = fb_threshold;
     return DVFE_OK;
@@ -497,6 +523,7 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
                                          const int* exist_inst, const double* time0) {
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     if (!exist_inst) { dvfe_set_error("track_semantic_image: exist_inst is null"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_track_semantic(t, left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     const size_t P = (size_t)t->W * t->H;
@@ -525,6 +552,11 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
 }
 
 extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out) {
+    if (IS_GROUP(t)) {
+        dvfe_tracker* leaf; int local;
+        DVFE_CHECK(grp_route(t, stream, &leaf, &local));
+        return dvfe_get_features(leaf, local, out, cap, n_out);
+    }
     if (!t || stream < 0 || stream >= t->B || !n_out) { dvfe_set_error("get_features: bad argument"); return DVFE_ERR_INVALID; }
     const int n = t->h_nobs[t->out_slot][stream];
     *n_out = n;
@@ -535,6 +567,11 @@ extern "C" int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int
 
 // ---- state get/set (teacher-forced parity tests, checkpointing) ---------------------------------------
 extern "C" int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* stt, int cap) {
+    if (IS_GROUP(t)) {
+        dvfe_tracker* leaf; int local;
+        DVFE_CHECK(grp_route(t, stream, &leaf, &local));
+        return dvfe_get_state(leaf, local, stt, cap);
+    }
     if (!t || !stt || stream < 0 || stream >= t->B) { dvfe_set_error("get_state: bad argument"); return DVFE_ERR_INVALID; }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
@@ -558,6 +595,11 @@ extern "C" int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* stt, int 
 }
 
 extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt) {
+    if (IS_GROUP(t)) {
+        dvfe_tracker* leaf; int local;
+        DVFE_CHECK(grp_route(t, stream, &leaf, &local));
+        return dvfe_set_state(leaf, local, stt);
+    }
     if (!t || !stt || stream < 0 || stream >= t->B || stt->n < 0 || stt->n > t->cap) {
         dvfe_set_error("set_state: bad argument");
         return DVFE_ERR_INVALID;
@@ -583,6 +625,7 @@ extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt
 
 extern "C" int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream) {
     if (!t) { dvfe_set_error("set_stream: null tracker"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return dvfe_set_stream(t->groups[0], cuda_stream);      // the other groups keep private streams
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     DVFE_CUDA(cudaStreamSynchronize(t->st));
@@ -594,6 +637,7 @@ extern "C" int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream) {
 
 extern "C" int dvfe_profile(dvfe_tracker* t, int enable) {
     if (!t) { dvfe_set_error("profile: null tracker"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_profile(t, enable);
     t->prof = enable != 0;
     if (enable) {
         for (int i = 0; i < dvfe_tracker::ST_COUNT; i++) t->prof_ms[i] = 0.0;
@@ -607,6 +651,7 @@ extern "C" int dvfe_profile_read(dvfe_tracker* t, const char** names, double* to
                                                          "gftt_response", "gftt_select", "left_post", "lk_stereo", "pack",
                                                          "d2h"};
     if (!t) { dvfe_set_error("profile_read: null tracker"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_profile_read(t, names, total_ms, steps);
     for (int i = 0; i < dvfe_tracker::ST_COUNT; i++) {
         if (names) names[i] = kNames[i];
         if (total_ms) total_ms[i] = t->prof_ms[i];

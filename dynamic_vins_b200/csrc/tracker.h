@@ -24,6 +24,10 @@ int gftt_cells(int w, int h, float min_dist);
 struct InstanceState;   // instances.cu
 
 struct dvfe_tracker {
+    // A tracker is either a leaf (owns device state for its B streams) or a container of G leaf trackers
+    // ("stream groups", dvfe_config::n_groups) that splits every call by stream range.
+    std::vector<dvfe_tracker*> groups;
+    std::vector<int> group_first;                    // first stream of each group (size G + 1)
     dvfe_config cfg{};
     int B = 0, W = 0, H = 0, cap = 0;
     cudaStream_t st = nullptr;                       // compute stream (caller-replaceable)

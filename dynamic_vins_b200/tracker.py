@@ -20,7 +20,8 @@ from . import _lib as L
 def make_config(width: int, height: int, max_cnt: int, min_dist: int, cam0: dict, cam1: Optional[dict] = None,
                 stereo: bool = True, n_streams: int = 1, max_dynamic_cnt: int = 50, min_dynamic_dist: int = 5,
                 flow_back: int = 1, use_mask_morphology: int = 0, mask_morphology_size: int = 5,
-                lk_max_level: int = 3, max_instances: int = 0, device: int = 0, **_ignored) -> L.Config:
+                lk_max_level: int = 3, max_instances: int = 0, device: int = 0, n_groups: int = 1,
+                **_ignored) -> L.Config:
     c = L.Config()
     c.width, c.height, c.n_streams, c.stereo = width, height, n_streams, int(bool(stereo))
     c.max_cnt, c.min_dist = max_cnt, min_dist
@@ -28,6 +29,7 @@ def make_config(width: int, height: int, max_cnt: int, min_dist: int, cam0: dict
     c.flow_back = flow_back
     c.use_mask_morphology, c.mask_morphology_size = use_mask_morphology, mask_morphology_size
     c.lk_max_level, c.max_instances, c.device = lk_max_level, max_instances, device
+    c.n_groups = n_groups
     cam1 = cam1 if cam1 is not None else cam0
     for dst, src in ((c.cam0, cam0), (c.cam1, cam1)):
         for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2"):

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     assert C.sizeof(L.Obs) == 64 and L.OBS_DTYPE.itemsize == 64
     assert C.sizeof(L.Camera) == 64
-    assert C.sizeof(L.Config) == 14 * 4 + 2 * 64
+    assert C.sizeof(L.Config) == 14 * 4 + 2 * 64 + 8
     assert C.sizeof(L.InstObs) == L.INST_OBS_DTYPE.itemsize == 16 + 13 * 8
 
 

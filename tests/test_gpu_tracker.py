@@ -480,3 +480,61 @@ def test_dynamic_mode_batched_streams_equal_single():
                 assert len(a) > 300
     batch.close()
     [s.close() for s in singles]
+
+
+def test_stream_groups_equal_ungrouped():
+    """dvfe_config::n_groups splits the streams over G leaf trackers on their own CUDA streams; every record is the
+    same as without groups, through the synchronous, pipelined, state and lk-mode entry points"""
+    name, B, T = "c2_kitti_stereo", 5, 5
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    plain, grouped = BatchTracker(cfg_of(name, n_streams=B)), BatchTracker(cfg_of(name, n_streams=B, n_groups=2))
+    outs = {0: [], 1: []}
+    for k in range(T):
+        frs = [s.frame(k) for s in streams]
+        L = np.stack([f.gray0 for f in frs]); R = np.stack([f.gray1 for f in frs])
+        tm = [f.time0 + 0.001 * i for i, f in enumerate(frs)]
+        if k < 2:
+            plain.track_image(L, R, tm); grouped.track_image(L, R, tm)
+            for s in range(B):
+                assert plain.features(s).tobytes() == grouped.features(s).tobytes()
+        else:                                              # pipelined: results of step k-1 after wait()
+            for j, t in enumerate((plain, grouped)):
+                t.track_image_async(L, R, tm)
+                if k > 2:
+                    t.wait()
+                    outs[j].append([t.features(s).tobytes() for s in range(B)])
+    for j, t in enumerate((plain, grouped)):
+        t.wait()
+        outs[j].append([t.features(s).tobytes() for s in range(B)])
+    assert outs[0] == outs[1] and len(outs[0]) == T - 2
+    st = plain.get_state(3)
+    sg = grouped.get_state(3)                              # stream 3 = group 1, local stream 0
+    assert all(np.array_equal(st[k], sg[k]) for k in st)
+    grouped.set_state(4, st)
+    assert all(np.array_equal(grouped.get_state(4)[k], st[k]) for k in st)
+    with pytest.raises(Exception):
+        grouped.features(B)
+    plain.close(); grouped.close()
+
+
+def test_stream_groups_dynamic_mode():
+    name, B, T = "c3_zed_dynamic", 3, 3
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    plain = BatchTracker(cfg_of(name, n_streams=B, max_instances=8))
+    grouped = BatchTracker(cfg_of(name, n_streams=B, max_instances=8, n_groups=2))
+    for k in range(T):
+        frs = [s.frame(k) for s in streams]
+        L = np.stack([f.gray0 for f in frs]); R = np.stack([f.gray1 for f in frs])
+        M = np.stack([f.inv_merge_mask for f in frs])
+        for t in (plain, grouped):
+            t.track_semantic_image(L, R, M, [int(f.exist_inst) for f in frs], [f.time0 for f in frs])
+            if k == 1:
+                for s in range(B):
+                    t.insts_track(s, frs[s].boxes, frs[s].time0)
+            else:
+                t.insts_track_batch([f.boxes for f in frs], [f.time0 for f in frs])
+        for s in range(B):
+            assert plain.features(s).tobytes() == grouped.features(s).tobytes()
+            a, b = plain.insts_output(s), grouped.insts_output(s)
+            assert len(a) > 300 and a.tobytes() == b.tobytes()
+    plain.close(); grouped.close()
