@@ -72,7 +72,8 @@ int grp_track_semantic(dvfe_tracker* t, const uint8_t* left, const uint8_t* righ
     for (size_t g = 0; g < t->groups.size(); g++) {
         const int f = t->group_first[g];
         const size_t off = (size_t)f * stride;
-        DVFE_CHECK(dvfe_track_semantic_image(t->groups[g], left + off, right ? right + off : nullptr, inv ? inv + off : nullptr,
+        const size_t moff = off / (size_t)(t->groups[g]->prep_active() ? t->groups[g]->in_ch : 1);
+        DVFE_CHECK(dvfe_track_semantic_image(t->groups[g], left + off, right ? right + off : nullptr, inv ? inv + moff : nullptr,
                                              stride, pitch, exist + f, time0 + f));
     }
     return DVFE_OK;
@@ -99,6 +100,16 @@ int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local) {
     const int g = t ? grp_of(t, stream, local) : -1;
     if (g < 0) { dvfe_set_error("bad stream index %d", stream); return DVFE_ERR_INVALID; }
     *leaf = t->groups[g];
+    return DVFE_OK;
+}
+
+int grp_set_input(dvfe_tracker* t, int channels) {
+    for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_set_input(g, channels));
+    return DVFE_OK;
+}
+
+int grp_set_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* map2) {
+    for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_set_undistort_maps(g, cam, map1, map2));
     return DVFE_OK;
 }
 

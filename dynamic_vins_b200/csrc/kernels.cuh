@@ -34,6 +34,23 @@ struct ErodeJob {
 // pyramid.cu
 int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
                           bool level0_in_place = false);
+// Frame ingest (prep.cu): optional fixed-point cv::remap (undistortion maps) + optional BGR -> gray, B images per launch,
+// written at dst_pitch (straight into level 0 of a padded pyramid, or dense).
+struct IngestArgs {
+    const uint8_t* src;          // [B] images of `ch` interleaved channels
+    size_t src_stride;           // bytes between images
+    int src_pitch;
+    int ch;                      // 1 (gray) | 3 (BGR)
+    const short* map1;           // CV_16SC2 (x, y) per output pixel, dense w x h, or null = identity
+    const unsigned short* map2;  // CV_16UC1 interpolation-table index (fy * 32 + fx), dense w x h
+    uint8_t* dst;                // [B] gray images (ch_out = 1) or remapped `ch`-channel images (keep_channels)
+    size_t dst_stride;
+    int dst_pitch;
+    int w, h, n_img;
+    int keep_channels;           // 1: plain cv::remap of all channels (seam op); 0: output gray
+};
+int launch_ingest(const IngestArgs& a, cudaStream_t st);
+
 int launch_build_pyramids_jobs(const PyrJob* d_jobs, int n_jobs, int max_w, int max_h, int max_levels, cudaStream_t st);
 int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st);
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);

@@ -46,6 +46,187 @@ __global__ void __launch_bounds__(256) k_merge_masks(const uint8_t* __restrict__
     inv[(size_t)y * dpitch + x] = (uint8_t)~m;
 }
 
+// ---- cv::remap (INTER_LINEAR, BORDER_CONSTANT 0) with fixed-point maps + BGR2GRAY: the frame ingest ------------------
+// ImageProcessor::Run (image_process/image_process.cpp:105-126): un = cv::remap(color, left_undist_map1, left_undist_map2,
+// INTER_LINEAR) with the CV_16SC2 / CV_16UC1 maps of cv::initUndistortRectifyMap (utils/camera_model.cpp:479-501), then
+// cvtColor(BGR2GRAY).  OpenCV's fixed-point bilinear remap: (sx, sy) = map1, fx = map2 & 31, fy = (map2 >> 5) & 31, weights
+// w = {(32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx fy} * 32 (exact shorts, sum 2^15), taps outside the source = 0,
+// dst = (sum w * tap + 2^14) >> 15 per channel == (sum (w/32) * tap + 512) >> 10.  One thread = 4 consecutive output
+// pixels of up to INGEST_SPT streams: the map entries are loaded once and reused across streams (the maps are shared
+// by all streams and stay in L2), the source taps are gathers served by L1/L2.
+#define INGEST_SPT 8
+
+// taps of one output pixel whose 2 x 2 footprint is not fully inside the source (border pixels only)
+template <int CH>
+__device__ __noinline__ void remap_taps_border(const uint8_t* __restrict__ img, int pitch, int w, int h, int sx, int sy,
+                                               int w00, int w01, int w10, int w11, unsigned out[CH]) {
+    const bool x0 = (unsigned)sx < (unsigned)w, x1 = (unsigned)(sx + 1) < (unsigned)w;
+    const bool y0 = (unsigned)sy < (unsigned)h, y1 = (unsigned)(sy + 1) < (unsigned)h;
+    for (int c = 0; c < CH; c++) {
+        int acc = 512;
+        if (x0 && y0) acc += w00 * __ldg(img + (size_t)sy * pitch + sx * CH + c);
+        if (x1 && y0) acc += w01 * __ldg(img + (size_t)sy * pitch + (sx + 1) * CH + c);
+        if (x0 && y1) acc += w10 * __ldg(img + (size_t)(sy + 1) * pitch + sx * CH + c);
+        if (x1 && y1) acc += w11 * __ldg(img + (size_t)(sy + 1) * pitch + (sx + 1) * CH + c);
+        out[c] = (unsigned)acc >> 10;
+    }
+}
+
+__device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r) {
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+// Unmapped images (gray copy / BGR -> gray): 4 consecutive output pixels per thread, word loads, one 32-bit store.
+template <int CH, bool KEEP>
+__global__ void __launch_bounds__(256) k_ingest_rows(IngestArgs a) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= a.w || y >= a.h) return;
+    const int n = min(4, a.w - x0);
+    const int s_end = min(a.n_img, (int)(blockIdx.z + 1) * INGEST_SPT);
+    for (int s = blockIdx.z * INGEST_SPT; s < s_end; s++) {
+        const uint8_t* __restrict__ row = a.src + (size_t)s * a.src_stride + (size_t)y * a.src_pitch + x0 * CH;
+        uint8_t* d = a.dst + (size_t)s * a.dst_stride + (size_t)y * a.dst_pitch + x0 * (KEEP ? CH : 1);
+        if (KEEP) {
+            for (int i = 0; i < n * CH; i++) d[i] = __ldg(row + i);
+            continue;
+        }
+        unsigned packed = 0;
+        if (n == 4 && ((uintptr_t)row & 3) == 0) {
+            const unsigned* p = reinterpret_cast<const unsigned*>(row);
+            if (CH == 3) {
+                const unsigned w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);   // B G R B | G R B G | R B G R
+                packed = gray_of(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255) |
+                         gray_of(w0 >> 24, w1 & 255, (w1 >> 8) & 255) << 8 |
+                         gray_of((w1 >> 16) & 255, w1 >> 24, w2 & 255) << 16 |
+                         gray_of((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24) << 24;
+            } else {
+                packed = __ldg(p);
+            }
+        } else {
+            for (int i = 0; i < n; i++)
+                packed |= (CH == 3 ? gray_of(__ldg(row + 3 * i), __ldg(row + 3 * i + 1), __ldg(row + 3 * i + 2)) : __ldg(row + i)) << (8 * i);
+        }
+        if (n == 4 && ((uintptr_t)d & 3) == 0) *reinterpret_cast<unsigned*>(d) = packed;
+        else for (int i = 0; i < n; i++) d[i] = (uint8_t)(packed >> (8 * i));
+    }
+}
+
+// Remapped images: lane l owns the output pixels x = 128 * blockIdx.x + 32 * i + l (i < 4), so that each warp-wide
+// gather touches the taps of 32 ADJACENT pixels (undistortion maps are smooth: one or two cache lines per load; with 4
+// consecutive pixels per lane every load spans four lines and the kernel is bound by L1 wavefronts).  Everything that
+// depends only on the maps (tap offset, the four weights, inside/outside) is decoded once and reused for the INGEST_SPT
+// streams the thread loops over; all source reads are ld.global.nc, so the loads of the next stream are not ordered
+// behind the stores of this one.
+template <int CH, bool KEEP>
+__global__ void __launch_bounds__(256) k_ingest_remap(IngestArgs a) {
+    const int xb = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (xb >= a.w || y >= a.h) return;
+    int off[4], wa[4], wb[4];          // byte offset of tap (0,0); weights packed w00 | w01 << 16, w10 | w11 << 16
+    short sxs[4], sys[4];
+    unsigned inside = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = xb + 32 * i;
+        off[i] = 0; wa[i] = 0; wb[i] = 0; sxs[i] = 0; sys[i] = 0;
+        if (x < a.w) {
+            const size_t m = (size_t)y * a.w + x;
+            const unsigned xy = __ldg(reinterpret_cast<const unsigned*>(a.map1) + m);
+            const unsigned f = __ldg(a.map2 + m);
+            const int sx = (short)(xy & 0xffff), sy = (short)(xy >> 16);
+            const int fx = f & 31, fy = (f >> 5) & 31;
+            sxs[i] = (short)sx; sys[i] = (short)sy;
+            wa[i] = ((32 - fx) * (32 - fy)) | (fx * (32 - fy)) << 16;
+            wb[i] = ((32 - fx) * fy) | (fx * fy) << 16;
+            if ((unsigned)sx < (unsigned)(a.w - 1) && (unsigned)sy < (unsigned)(a.h - 1)) {
+                inside |= 1u << i;
+                off[i] = sy * a.src_pitch + sx * CH;
+            }
+        }
+    }
+    const int s_end = min(a.n_img, (int)(blockIdx.z + 1) * INGEST_SPT);
+    for (int s = blockIdx.z * INGEST_SPT; s < s_end; s++) {
+        const uint8_t* __restrict__ img = a.src + (size_t)s * a.src_stride;
+        uint8_t* drow = a.dst + (size_t)s * a.dst_stride + (size_t)y * a.dst_pitch;
+        unsigned res[4][CH];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (xb + 32 * i >= a.w) break;
+            const int w00 = wa[i] & 0xffff, w01 = wa[i] >> 16, w10 = wb[i] & 0xffff, w11 = wb[i] >> 16;
+            if (inside >> i & 1) {
+                const uint8_t* p = img + off[i];
+#pragma unroll
+                for (int c = 0; c < CH; c++)
+                    res[i][c] = (unsigned)(w00 * __ldg(p + c) + w01 * __ldg(p + CH + c) + w10 * __ldg(p + a.src_pitch + c) +
+                                           w11 * __ldg(p + a.src_pitch + CH + c) + 512) >> 10;
+            } else {
+                remap_taps_border<CH>(img, a.src_pitch, a.w, a.h, sxs[i], sys[i], w00, w01, w10, w11, res[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = xb + 32 * i;
+            if (x >= a.w) break;
+            if (KEEP) {
+#pragma unroll
+                for (int c = 0; c < CH; c++) drow[x * CH + c] = (uint8_t)res[i][c];
+            } else {
+                drow[x] = (uint8_t)(CH == 3 ? gray_of(res[i][0], res[i][1], res[i][2]) : res[i][0]);
+            }
+        }
+    }
+}
+
+int launch_ingest(const IngestArgs& a, cudaStream_t st) {
+    if (a.n_img <= 0) return DVFE_OK;
+    const int nz = (a.n_img + INGEST_SPT - 1) / INGEST_SPT;
+    dim3 blk(32, 8), grid((a.w + 127) / 128, (a.h + 7) / 8, nz);
+    if (a.map1) {
+        if (a.ch == 3 && a.keep_channels) DVFE_LAUNCH((k_ingest_remap<3, true>), grid, blk, 0, st, a);
+        else if (a.ch == 3) DVFE_LAUNCH((k_ingest_remap<3, false>), grid, blk, 0, st, a);
+        else DVFE_LAUNCH((k_ingest_remap<1, false>), grid, blk, 0, st, a);
+    } else {
+        if (a.ch == 3 && a.keep_channels) DVFE_LAUNCH((k_ingest_rows<3, true>), grid, blk, 0, st, a);
+        else if (a.ch == 3) DVFE_LAUNCH((k_ingest_rows<3, false>), grid, blk, 0, st, a);
+        else DVFE_LAUNCH((k_ingest_rows<1, false>), grid, blk, 0, st, a);
+    }
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_op_remap(const uint8_t* src, int w, int h, int channels, int pitch, const int16_t* map1,
+                             const uint16_t* map2, int to_gray, uint8_t* dst) {
+    if (!src || !dst || w < 1 || h < 1 || (channels != 1 && channels != 3) || pitch < channels * w || (map1 != nullptr) != (map2 != nullptr)) {
+        dvfe_set_error("op_remap: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { dvfe_set_error("no CUDA device available: libdvfe has no CPU fallback"); return DVFE_ERR_NO_DEVICE; }
+    const size_t P = (size_t)w * h;
+    const int och = (channels == 3 && !to_gray) ? 3 : 1;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    short* d_m1 = nullptr;
+    unsigned short* d_m2 = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_src, P * channels);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_dst, P * och);
+    if (e == cudaSuccess && map1) e = cudaMalloc((void**)&d_m1, P * 4);
+    if (e == cudaSuccess && map1) e = cudaMalloc((void**)&d_m2, P * 2);
+    if (e == cudaSuccess) e = cudaMemcpy2D(d_src, (size_t)channels * w, src, pitch, (size_t)channels * w, h, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && map1) e = cudaMemcpy(d_m1, map1, P * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && map1) e = cudaMemcpy(d_m2, map2, P * 2, cudaMemcpyHostToDevice);
+    int rc = DVFE_OK;
+    if (e == cudaSuccess) {
+        IngestArgs a{d_src, P * channels, channels * w, channels, d_m1, d_m2, d_dst, P * och, och * w, w, h, 1, och == 3 ? 1 : 0};
+        rc = launch_ingest(a, 0);
+        if (rc == DVFE_OK) e = cudaDeviceSynchronize();
+        if (rc == DVFE_OK && e == cudaSuccess) e = cudaMemcpy(dst, d_dst, P * och, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_m1); cudaFree(d_m2);
+    if (rc != DVFE_OK) return rc;
+    if (e != cudaSuccess) { dvfe_set_error("op_remap: %s", cudaGetErrorString(e)); return DVFE_ERR_CUDA; }
+    return DVFE_OK;
+}
+
 extern "C" int dvfe_op_bgr_to_gray(const uint8_t* bgr, int w, int h, int pitch, uint8_t* gray_out) {
     if (!bgr || !gray_out || w < 1 || h < 1 || pitch < 3 * w) { dvfe_set_error("op_bgr_to_gray: bad argument"); return DVFE_ERR_INVALID; }
     int count = 0;

@@ -287,6 +287,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
         for (int i = 0; i <= dvfe_tracker::ST_COUNT; i++) if (t->ev[p][i]) cudaEventDestroy(t->ev[p][i]);
     }
     cudaFree(t->d_stage[0]); cudaFree(t->d_stage[1]);
+    for (int i = 0; i < 2; i++) { cudaFree(t->d_raw[i]); cudaFree(t->d_map1[i]); cudaFree(t->d_map2[i]); }
     cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_inv_in); cudaFree(t->d_exist);
     cudaFreeHost(t->h_exist);
     free_gftt_scratch(&t->gsc);
@@ -447,8 +448,89 @@ int dvfe_tracker::upload_staged(const uint8_t* left, const uint8_t* right, size_
     return DVFE_OK;
 }
 
+// ---- frame ingest: BGR and/or distorted input -> level 0 on the device ---------------------------------------------
+int dvfe_tracker::ensure_raw() {
+    const size_t need = (size_t)2 * B * W * H * in_ch;
+    for (int p = 0; p < 2; p++) {
+        if (d_raw[p]) continue;
+        DVFE_CUDA(cudaMalloc((void**)&d_raw[p], need));
+    }
+    return DVFE_OK;
+}
+
+// remap (if camera `cam` has maps) + gray conversion of B device images into level 0 of this step's pyramid slot
+int dvfe_tracker::ingest(const uint8_t* d_src, size_t stream_stride, int pitch, int cam, cudaStream_t s) {
+    const PyrLevel& L0 = desc.lv[0];
+    IngestArgs a;
+    a.src = d_src; a.src_stride = stream_stride; a.src_pitch = pitch; a.ch = in_ch;
+    a.map1 = d_map1[cam]; a.map2 = d_map2[cam];
+    a.dst = (cam ? right_slot(frames) : left_slot(frames)) + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
+    a.dst_stride = desc.bytes; a.dst_pitch = L0.pitch;
+    a.w = W; a.h = H; a.n_img = B; a.keep_channels = 0;
+    return launch_ingest(a, s);
+}
+
+// Host images (gray or BGR) -> dense device staging -> ingest kernel on the upload stream -> level 0 of the NEXT step
+int dvfe_tracker::upload_prepared(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch) {
+    const long k = frames;
+    const int par = (int)(k % 2);
+    while (frames - completed >= 2) DVFE_CHECK(wait_one());
+    DVFE_CHECK(ensure_raw());
+    const size_t row = (size_t)W * in_ch, img = row * H;
+    for (int cam = 0; cam < 2; cam++) {
+        const uint8_t* src = cam ? right : left;
+        if (!src) continue;
+        uint8_t* dst = d_raw[par] + (size_t)cam * B * img;
+        if ((size_t)pitch == row && stream_stride == img) {
+            DVFE_CUDA(cudaMemcpyAsync(dst, src, (size_t)B * img, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int s = 0; s < B; s++)
+                DVFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)s * img, row, src + s * stream_stride, pitch, row, (size_t)H,
+                                            cudaMemcpyHostToDevice, cs));
+        }
+        DVFE_CHECK(ingest(dst, img, (int)row, cam, cs));
+    }
+    DVFE_CUDA(cudaEventRecord(ev_up[par], cs));
+    DVFE_CUDA(cudaStreamWaitEvent(st, ev_up[par], 0));
+    return DVFE_OK;
+}
+
+int grp_set_input(dvfe_tracker* t, int channels);
+int grp_set_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* map2);
+
+extern "C" int dvfe_set_input(dvfe_tracker* t, int channels) {
+    if (!t || (channels != 1 && channels != 3)) { dvfe_set_error("set_input: channels must be 1 (gray) or 3 (BGR)"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_set_input(t, channels);
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
+    if (channels != t->in_ch) {
+        DVFE_CUDA(cudaStreamSynchronize(t->cs));
+        for (int p = 0; p < 2; p++) { cudaFree(t->d_raw[p]); t->d_raw[p] = nullptr; }
+    }
+    t->in_ch = channels;
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_set_undistort_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* map2) {
+    if (!t || cam < 0 || cam > 1 || (map1 != nullptr) != (map2 != nullptr)) { dvfe_set_error("set_undistort_maps: bad argument"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_set_maps(t, cam, map1, map2);
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->wait_all());
+    DVFE_CUDA(cudaStreamSynchronize(t->cs));
+    cudaFree(t->d_map1[cam]); cudaFree(t->d_map2[cam]);
+    t->d_map1[cam] = nullptr; t->d_map2[cam] = nullptr;
+    if (!map1) return DVFE_OK;
+    const size_t P = (size_t)t->W * t->H;
+    DVFE_CUDA(cudaMalloc((void**)&t->d_map1[cam], P * 4));
+    DVFE_CUDA(cudaMalloc((void**)&t->d_map2[cam], P * 2));
+    DVFE_CUDA(cudaMemcpy(t->d_map1[cam], map1, P * 4, cudaMemcpyHostToDevice));
+    DVFE_CUDA(cudaMemcpy(t->d_map2[cam], map2, P * 2, cudaMemcpyHostToDevice));
+    return DVFE_OK;
+}
+
 static int check_step_args(dvfe_tracker* t, const uint8_t* left, int pitch, const double* time0) {
-    if (!t || !left || !time0 || pitch < t->W) {
+    const int in_ch = !t ? 1 : (t->groups.empty() ? t->in_ch : t->groups[0]->in_ch);
+    if (!t || !left || !time0 || pitch < t->W * in_ch) {
         dvfe_set_error("track: input wrong, received at least one empty parameter");   // feature_utils.cpp:39-41
         return DVFE_ERR_INVALID;
     }
@@ -460,6 +542,10 @@ extern "C" int dvfe_track_image_async(dvfe_tracker* t, const uint8_t* left, cons
     DVFE_CHECK(check_step_args(t, left, pitch, time0));
     if (IS_GROUP(t)) return grp_track_image_async(t, left, right, stream_stride, pitch, time0, false);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    if (t->prep_active()) {
+        DVFE_CHECK(t->upload_prepared(left, right, stream_stride, pitch));
+        return t->submit(nullptr, nullptr, 0, 0, time0, false, true, right != nullptr);
+    }
     if (t->staged_upload) {
         const size_t P = (size_t)t->W * t->H;
         const int par = (int)(t->frames % 2);
@@ -494,6 +580,12 @@ extern "C" int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, c
     }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
+    if (t->prep_active()) {
+        DVFE_CHECK(t->ingest(d_left, stream_stride, pitch, 0, t->st));
+        if (d_right) DVFE_CHECK(t->ingest(d_right, stream_stride, pitch, 1, t->st));
+        DVFE_CHECK(t->submit(nullptr, nullptr, 0, 0, time0, false, true, d_right != nullptr));
+        return t->wait_all();
+    }
     DVFE_CHECK(t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr));
     return t->wait_all();
 }
@@ -504,6 +596,11 @@ extern "C" int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_l
     if (IS_GROUP(t)) return grp_track_image_async(t, d_left, d_right, stream_stride, pitch, time0, true);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     while (t->frames - t->completed >= 2) DVFE_CHECK(t->wait_one());
+    if (t->prep_active()) {
+        DVFE_CHECK(t->ingest(d_left, stream_stride, pitch, 0, t->st));
+        if (d_right) DVFE_CHECK(t->ingest(d_right, stream_stride, pitch, 1, t->st));
+        return t->submit(nullptr, nullptr, 0, 0, time0, false, true, d_right != nullptr);
+    }
     return t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr);
 }
 
@@ -528,13 +625,18 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     DVFE_CHECK(t->wait_all());
     const size_t P = (size_t)t->W * t->H;
     const int par = (int)(t->frames % 2);
-    if (t->staged_upload) DVFE_CHECK(t->upload_staged(left, right, stream_stride, pitch));
+    const bool prep = t->prep_active();
+    if (prep) DVFE_CHECK(t->upload_prepared(left, right, stream_stride, pitch));
+    else if (t->staged_upload) DVFE_CHECK(t->upload_staged(left, right, stream_stride, pitch));
     else DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
+    // the region mask is one byte per pixel whatever the image format
+    const size_t mask_stride = prep ? stream_stride / (size_t)t->in_ch : stream_stride;
+    const int mask_pitch = prep ? pitch / t->in_ch : pitch;
     for (int s = 0; s < t->B; s++) {
         t->h_exist[s] = exist_inst[s] ? 1 : 0;
         if (exist_inst[s]) {
             if (!inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
-            DVFE_CUDA(cudaMemcpy2DAsync(t->d_inv_in + s * P, t->W, inv_merge_mask + s * stream_stride, pitch, t->W,
+            DVFE_CUDA(cudaMemcpy2DAsync(t->d_inv_in + s * P, t->W, inv_merge_mask + s * mask_stride, mask_pitch, t->W,
                                         (size_t)t->H, cudaMemcpyHostToDevice, t->st));
         }
     }
@@ -543,7 +645,7 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
     DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
                                  t->d_exist, t->st));
-    if (t->staged_upload)
+    if (!prep && t->staged_upload)
         DVFE_CHECK(t->submit(t->d_stage[par], right ? t->d_stage[par] + t->B * P : nullptr, P, t->W, time0, true, false,
                              right != nullptr));
     else

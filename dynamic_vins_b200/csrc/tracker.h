@@ -83,6 +83,16 @@ struct dvfe_tracker {
     void free_instances();
     uint8_t* d_stage[2] = {nullptr, nullptr};       // dense upload staging [2 cameras][B][H*W], one per in-flight step
     bool staged_upload = false;                      // rows that are not a multiple of 64 B make pitched DMA slow
+    // frame ingest (dvfe_set_input / dvfe_set_undistort_maps): BGR and/or remapped input goes through a device staging
+    // buffer and the ingest kernel, which writes level 0 in place
+    int in_ch = 1;
+    short* d_map1[2] = {nullptr, nullptr};
+    unsigned short* d_map2[2] = {nullptr, nullptr};
+    uint8_t* d_raw[2] = {nullptr, nullptr};          // [2 cameras][B][H*W*in_ch] per in-flight step
+    bool prep_active() const { return in_ch != 1 || d_map1[0] || d_map1[1]; }
+    int ensure_raw();
+    int ingest(const uint8_t* d_src, size_t stream_stride, int pitch, int cam, cudaStream_t s);
+    int upload_prepared(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
     int upload_in_place(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
     int upload_staged(const uint8_t* left, const uint8_t* right, size_t stream_stride, int pitch);
     // enqueue one frame step (no host synchronisation); at most two steps are in flight

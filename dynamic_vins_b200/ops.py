@@ -103,6 +103,20 @@ def bgr_to_gray(bgr):
     return out
 
 
+def remap(src, map1=None, map2=None, to_gray=False):
+    """cv::remap(src, map1, map2, INTER_LINEAR) with CV_16SC2 / CV_16UC1 maps (+ cvtColor(BGR2GRAY) if to_gray)"""
+    a = np.ascontiguousarray(src, dtype=np.uint8)
+    h, w = a.shape[:2]
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    m1 = None if map1 is None else np.ascontiguousarray(map1, np.int16)
+    m2 = None if map2 is None else np.ascontiguousarray(map2, np.uint16)
+    if m1 is not None:
+        assert m1.shape == (h, w, 2) and m2.shape == (h, w)
+    out = np.zeros((h, w) if (ch == 1 or to_gray) else (h, w, ch), np.uint8)
+    L.check(L.lib().dvfe_op_remap(L.ptr(a), w, h, ch, a.strides[0], L.ptr(m1), L.ptr(m2), int(bool(to_gray)), L.ptr(out)))
+    return out
+
+
 def merge_masks(masks):
     """(n, h, w) instance masks -> (merge_mask 255 = object, inv_merge_mask)"""
     m = np.ascontiguousarray(masks, dtype=np.uint8)

@@ -282,3 +282,24 @@ def make_stream(config: str, stream_id: int = 0) -> SynthStream:
     c = CONFIGS[config]
     return SynthStream(c["width"], c["height"], seed=1000 * c["config_id"] + stream_id,
                        stereo=c["stereo"], n_objects=c["n_objects"])
+
+
+def colorize(gray: np.ndarray) -> np.ndarray:
+    """deterministic BGR rendition of a gray frame (distinct per-channel gains/offsets, integer arithmetic) for the
+    colour-input tests: SemanticImage::color0/color1 are 8UC3 BGR"""
+    g = gray.astype(np.int32)
+    b = g
+    gr = (g * 235 + 3072) >> 8
+    r = np.minimum(255, (g * 271) >> 8)
+    return np.stack([b, gr, r], axis=-1).astype(np.uint8)
+
+
+def random_maps(width: int, height: int, seed: int, outside: float = 3.0):
+    """random float sampling maps (some of them outside the image) in cv::remap's fixed-point form:
+    map1 int16 (h, w, 2) = floor(x), floor(y) ; map2 uint16 (h, w) = (fy << 5) | fx in 1/32 px"""
+    rng = np.random.default_rng(seed)
+    ix = np.rint(rng.uniform(-outside, width - 1 + outside, (height, width)) * 32).astype(np.int64)
+    iy = np.rint(rng.uniform(-outside, height - 1 + outside, (height, width)) * 32).astype(np.int64)
+    map1 = np.stack([ix >> 5, iy >> 5], axis=-1).astype(np.int16)
+    map2 = (((iy & 31) << 5) | (ix & 31)).astype(np.uint16)
+    return map1, map2

@@ -57,6 +57,7 @@ class BatchTracker:
     def __init__(self, cfg: L.Config):
         self.cfg = cfg
         self.B, self.W, self.H = cfg.n_streams, cfg.width, cfg.height
+        self.ch = 1
         self._h = C.c_void_p()
         L.check(L.lib().dvfe_create(C.byref(cfg), C.byref(self._h)))
         self._obs = np.zeros(2 * cfg.max_cnt, dtype=L.OBS_DTYPE)
@@ -96,29 +97,43 @@ class BatchTracker:
         return t
 
     @staticmethod
-    def _batch(a: Optional[np.ndarray], B: int, H: int, W: int) -> Optional[np.ndarray]:
+    def _batch(a: Optional[np.ndarray], B: int, H: int, W: int, ch: int = 1) -> Optional[np.ndarray]:
         if a is None:
             return None
         a = np.asarray(a)
-        if a.ndim == 2:
+        if a.ndim == (2 if ch == 1 else 3):
             a = a[None]
-        assert a.shape == (B, H, W) and a.dtype == np.uint8, (a.shape, a.dtype)
+        assert a.shape == ((B, H, W) if ch == 1 else (B, H, W, ch)) and a.dtype == np.uint8, (a.shape, a.dtype)
         return a if a.flags["C_CONTIGUOUS"] else np.ascontiguousarray(a)
+
+    # ---- frame ingest --------------------------------------------------------------------------
+    def set_input(self, channels: int) -> None:
+        """1: gray images (default); 3: BGR images (SemanticImage::color0/color1), converted on the device"""
+        L.check(L.lib().dvfe_set_input(self._h, channels))
+        self.ch = channels
+
+    def set_undistort_maps(self, cam: int, map1: Optional[np.ndarray], map2: Optional[np.ndarray]) -> None:
+        """cfg::is_undistort_input: cv::initUndistortRectifyMap(..., CV_16SC2) maps of camera cam (None, None clears)"""
+        m1 = None if map1 is None else np.ascontiguousarray(map1, np.int16)
+        m2 = None if map2 is None else np.ascontiguousarray(map2, np.uint16)
+        if m1 is not None:
+            assert m1.shape == (self.H, self.W, 2) and m2.shape == (self.H, self.W)
+        L.check(L.lib().dvfe_set_undistort_maps(self._h, cam, L.ptr(m1), L.ptr(m2)))
 
     def track_image(self, left: np.ndarray, right: Optional[np.ndarray], time0) -> None:
         """left/right: (B,H,W) or (H,W) uint8 host arrays."""
-        l = self._batch(left, self.B, self.H, self.W)
-        r = self._batch(right, self.B, self.H, self.W)
+        l = self._batch(left, self.B, self.H, self.W, self.ch)
+        r = self._batch(right, self.B, self.H, self.W, self.ch)
         t = self._times(time0)
-        L.check(L.lib().dvfe_track_image(self._h, L.ptr(l), L.ptr(r), self.H * self.W, self.W, L.ptr(t)))
+        L.check(L.lib().dvfe_track_image(self._h, L.ptr(l), L.ptr(r), self.H * self.W * self.ch, self.W * self.ch, L.ptr(t)))
 
     def track_image_async(self, left: np.ndarray, right: Optional[np.ndarray], time0) -> None:
         """pipelined: enqueue the step and return; the arrays must stay alive until the matching wait()"""
-        l = self._batch(left, self.B, self.H, self.W)
-        r = self._batch(right, self.B, self.H, self.W)
+        l = self._batch(left, self.B, self.H, self.W, self.ch)
+        r = self._batch(right, self.B, self.H, self.W, self.ch)
         t = self._times(time0)
         self._keep = (l, r, t, getattr(self, "_keep", None) and self._keep[:3])
-        L.check(L.lib().dvfe_track_image_async(self._h, L.ptr(l), L.ptr(r), self.H * self.W, self.W, L.ptr(t)))
+        L.check(L.lib().dvfe_track_image_async(self._h, L.ptr(l), L.ptr(r), self.H * self.W * self.ch, self.W * self.ch, L.ptr(t)))
 
     def wait(self) -> None:
         """block until the oldest in-flight step is finished; features() then returns its records"""
@@ -141,13 +156,13 @@ class BatchTracker:
         L.check(L.lib().dvfe_set_lk_mode(self._h, int(back_max_level), float(fb_threshold)))
 
     def track_semantic_image(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
-        l = self._batch(left, self.B, self.H, self.W)
-        r = self._batch(right, self.B, self.H, self.W)
+        l = self._batch(left, self.B, self.H, self.W, self.ch)
+        r = self._batch(right, self.B, self.H, self.W, self.ch)
         m = self._batch(inv_merge_mask, self.B, self.H, self.W)
         e = np.ascontiguousarray(np.broadcast_to(np.asarray(exist_inst, np.int32), (self.B,)))
         t = self._times(time0)
-        L.check(L.lib().dvfe_track_semantic_image(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W, self.W,
-                                                  L.ptr(e), L.ptr(t)))
+        L.check(L.lib().dvfe_track_semantic_image(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W * self.ch,
+                                                  self.W * self.ch, L.ptr(e), L.ptr(t)))
 
     def insts_track(self, stream: int, boxes: Sequence[dict], time0: float) -> None:
         """boxes: [{track_id, rect=(x,y,w,h), mask (h,w) uint8}] (SemanticImage::boxes2d)."""

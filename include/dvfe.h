@@ -243,6 +243,26 @@ int dvfe_op_bgr_to_gray(const uint8_t* bgr, int w, int h, int pitch, uint8_t* gr
  * instance masks (non-zero = object) -> merge_mask (255 = object) and inv_merge_mask (bitwise_not). */
 int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int h, uint8_t* merge_out, uint8_t* inv_out);
 
+/* ImageProcessor::Run undistortion (image_process/image_process.cpp:109-122): cv::remap(src, dst, map1, map2, INTER_LINEAR)
+ * with the fixed-point maps of cv::initUndistortRectifyMap(..., CV_16SC2, map1, map2) (utils/camera_model.cpp:483-497):
+ * map1 = w*h (x, y) int16 pairs, map2 = w*h uint16 table indices; BORDER_CONSTANT 0; dst has the size of src.
+ * channels 1 | 3.  to_gray != 0 with 3 channels additionally applies cvtColor(BGR2GRAY) (dst = dense w x h);
+ * otherwise dst = dense w x h x channels.  map1 == map2 == NULL: identity (only the gray conversion runs). */
+int dvfe_op_remap(const uint8_t* src, int w, int h, int channels, int pitch, const int16_t* map1, const uint16_t* map2,
+                  int to_gray, uint8_t* dst);
+
+/* ---- frame ingest inside the tracker (SURVEY.md §8f N1 + N2) ---------------------------------------------
+ * dvfe_set_input: the images handed to dvfe_track_image[_async|_device*] / dvfe_track_semantic_image are `channels`
+ * interleaved bytes per pixel: 1 = gray (default), 3 = BGR as in SemanticImage::color0/color1; pitch >= channels * width.
+ * dvfe_set_undistort_maps: cfg::is_undistort_input — every image of camera `cam` (0 left, 1 right) is first remapped
+ * through (map1, map2) as cv::remap does (see dvfe_op_remap); the maps are copied to the device and shared by all
+ * streams; (NULL, NULL) clears them.  Both run on the device, fused into one pass that writes pyramid level 0:
+ * gray0 = cvtColor(remap(color0)) is never materialised on the host.  The region mask of
+ * dvfe_track_semantic_image is NOT remapped (the caller passes SetBackgroundMask's result, basic/semantic_image.cpp:103-117)
+ * and stays one byte per pixel: with a 3-channel input its row pitch is pitch / 3 and its stream stride stream_stride / 3. */
+int dvfe_set_input(dvfe_tracker* t, int channels);
+int dvfe_set_undistort_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* map2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,7 +90,7 @@ public:
         check_input(img);
         const bool right = cfg_.stereo && !img.gray1.empty();
         const int exist = img.exist_inst ? 1 : 0;
-        if (img.exist_inst && (img.inv_merge_mask.empty() || img.inv_merge_mask.step != img.gray0.step))
+        if (img.exist_inst && (img.inv_merge_mask.empty() || img.inv_merge_mask.step != img.gray0.step / channels_))
             throw std::runtime_error("TrackSemanticImage: inv_merge_mask must have the layout of gray0");
         if (dvfe_track_semantic_image(h_, img.gray0.data, right ? img.gray1.data : nullptr,
                                       img.exist_inst ? img.inv_merge_mask.data : nullptr,
@@ -98,6 +98,17 @@ public:
                                       &img.time0) != DVFE_OK)
             throw std::runtime_error(dvfe_last_error(h_));
         return SetOutputFeats();
+    }
+    // ImageProcessor::Run moved onto the device (image_process/image_process.cpp:105-126): with SetColorInput(true) the
+    // gray0/gray1 views of SemanticImage carry color0/color1 (BGR, step >= 3 * cols; inv_merge_mask stays 1 byte/px
+    // with step = color step / 3); SetUndistortMaps hands over cam_s.left/right_undist_map1/2 (CV_16SC2 + CV_16UC1,
+    // utils/camera_model.cpp:483-497) and every image of that camera is remapped before the gray conversion.
+    void SetColorInput(bool bgr) {
+        if (dvfe_set_input(h_, bgr ? 3 : 1) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
+        channels_ = bgr ? 3 : 1;
+    }
+    void SetUndistortMaps(int cam, const int16_t* map1, const uint16_t* map2) {
+        if (dvfe_set_undistort_maps(h_, cam, map1, map2) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
     }
     dvfe_tracker* handle() { return h_; }
     const dvfe_config& config() const { return cfg_; }
@@ -122,6 +133,7 @@ private:
     }
     dvfe_config cfg_{};
     dvfe_tracker* h_ = nullptr;
+    int channels_ = 1;
 };
 
 // The reference builds InstsFeatManager from the config path and shares the process-global feature-id counter with

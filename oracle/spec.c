@@ -499,3 +499,35 @@ void spec_lift(const double* cam /* fx fy cx cy k1 k2 p1 p2 */, const float* pts
         out[2 * i] = (float)(mxu / 1.0); out[2 * i + 1] = (float)(myu / 1.0);
     }
 }
+
+/* cv::remap(src, dst, map1 CV_16SC2, map2 CV_16UC1, INTER_LINEAR, BORDER_CONSTANT 0) as ImageProcessor::Run calls it
+ * (image_process/image_process.cpp:109-122) [OpenCV imgwarp.cpp remapBilinear, fixed-point path]: weights from the
+ * 32 x 32 bilinear table scaled by 2^15, taps outside the source read 0, rounding (v + 2^14) >> 15.  ch interleaved
+ * channels; dst has the size of the maps = the size of src. */
+void spec_remap(const uint8_t* src, int w, int h, int ch, int sstride, const int16_t* map1, const uint16_t* map2,
+                uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const size_t m = (size_t)y * w + x;
+            const int sx = map1[2 * m], sy = map1[2 * m + 1];
+            const int fx = map2[m] & 31, fy = (map2[m] >> 5) & 31;
+            const int wt[4] = {(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+            for (int c = 0; c < ch; c++) {
+                int acc = 1 << 14;
+                for (int k = 0; k < 4; k++) {
+                    const int xx = sx + (k & 1), yy = sy + (k >> 1);
+                    if (xx >= 0 && xx < w && yy >= 0 && yy < h) acc += wt[k] * src[(size_t)yy * sstride + xx * ch + c];
+                }
+                dst[(size_t)y * dstride + x * ch + c] = (uint8_t)(acc >> 15);
+            }
+        }
+}
+
+/* cv::cvtColor(BGR2GRAY) with the 15-bit coefficients of cv2 4.13 (SemanticImage::SetGrayImage, basic/semantic_image.cpp:69-73) */
+void spec_bgr_to_gray(const uint8_t* bgr, int w, int h, int sstride, uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = bgr + (size_t)y * sstride + 3 * x;
+            dst[(size_t)y * dstride + x] = (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+        }
+}

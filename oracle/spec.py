@@ -135,3 +135,22 @@ def lift(cam, pts, off=(0.0, 0.0)):
     lib().spec_lift(_p(c, C.c_double), _p(p, C.c_float), len(p), C.c_float(off[0]), C.c_float(off[1]),
                     _p(out, C.c_float))
     return out
+
+
+def remap(src, map1, map2):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    m1 = np.ascontiguousarray(map1, np.int16)
+    m2 = np.ascontiguousarray(map2, np.uint16)
+    out = np.zeros_like(src)
+    lib().spec_remap(_p(src, C.c_uint8), w, h, ch, w * ch, _p(m1, C.c_int16), _p(m2, C.c_uint16), _p(out, C.c_uint8), w * ch)
+    return out
+
+
+def bgr_to_gray(bgr):
+    bgr = _u8(bgr)
+    h, w, _ = bgr.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().spec_bgr_to_gray(_p(bgr, C.c_uint8), w, h, 3 * w, _p(out, C.c_uint8), w)
+    return out

@@ -92,8 +92,32 @@ def stage_golden():
     print("stages: lk ok", int(st_.sum()), "stereo ok", int(rst.sum()))
 
 
+def prep_golden():
+    """cv2.remap (fixed-point maps, INTER_LINEAR) and cvtColor(BGR2GRAY) known answers on a small random image"""
+    rng = np.random.default_rng(77)
+    h, w = 64, 96
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    map1, map2 = synth.random_maps(w, h, 78)
+    out = {"bgr": bgr, "map1": map1, "map2": map2,
+           "remap_bgr": cv2.remap(bgr, map1, map2, cv2.INTER_LINEAR),
+           "remap_gray": cv2.remap(bgr[..., 1].copy(), map1, map2, cv2.INTER_LINEAR),
+           "gray": cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)}
+    out["remap_then_gray"] = cv2.cvtColor(out["remap_bgr"], cv2.COLOR_BGR2GRAY)
+    # the EuRoC undistortion maps as utils/camera_model.cpp:479-501 builds them: keep their checksums and the new intrinsics
+    from oracle import image_process as ip
+    c = synth.CONFIGS["c1_euroc_mono"]
+    m1, m2, cam = ip.undistort_maps(c["cam0"], c["width"], c["height"])
+    out["euroc_map1_crc"], out["euroc_map2_crc"] = np.uint32(crc(m1)), np.uint32(crc(m2))
+    out["euroc_new_k"] = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]])
+    g = synth.make_stream("c1_euroc_mono", 0).frame(0).gray0
+    out["euroc_undist_gray_crc"] = np.uint32(crc(ip.run(synth.colorize(g), None, (m1, m2))[0]))
+    np.savez_compressed(os.path.join(OUT, "prep.npz"), **out)
+    print("prep golden written")
+
+
 if __name__ == "__main__":
     stage_golden()
+    prep_golden()
     tracker_golden("c1_euroc_mono", 6)
     tracker_golden("c2_kitti_stereo", 6)
     if "--dynamic" in sys.argv or True:

@@ -233,3 +233,31 @@ def test_frame_prep_ops():
     assert np.array_equal(merge, fr.merge_mask) and np.array_equal(inv, fr.inv_merge_mask)
     merge, inv = ops.merge_masks(np.zeros((0, 8, 9), np.uint8))
     assert not merge.any() and (inv == 255).all()
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (37, 131), (1, 5), (480, 752)])
+def test_remap_bit_exact(shape):
+    """dvfe_op_remap == cv2.remap(INTER_LINEAR) with fixed-point maps, taps outside the image included; 1 and 3 channels,
+    with and without the fused gray conversion; NULL maps = identity"""
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    m1, m2 = synth.random_maps(w, h, 11 + h, outside=5.0)
+    ref = cv2.remap(bgr, m1, m2, cv2.INTER_LINEAR)
+    assert np.array_equal(ops.remap(bgr, m1, m2), ref)
+    assert np.array_equal(ops.remap(bgr, m1, m2, to_gray=True), cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
+    g = bgr[..., 2].copy()
+    assert np.array_equal(ops.remap(g, m1, m2), cv2.remap(g, m1, m2, cv2.INTER_LINEAR))
+    assert np.array_equal(ops.remap(bgr, None, None, to_gray=True), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(ops.remap(g, None, None), g)
+
+
+def test_remap_golden_and_euroc_undistortion():
+    from oracle import image_process as ip
+    g = load_golden("prep.npz")
+    assert np.array_equal(ops.remap(g["bgr"], g["map1"], g["map2"]), g["remap_bgr"])
+    assert np.array_equal(ops.remap(g["bgr"], g["map1"], g["map2"], to_gray=True), g["remap_then_gray"])
+    c = synth.CONFIGS["c1_euroc_mono"]
+    m1, m2, _ = ip.undistort_maps(c["cam0"], c["width"], c["height"])
+    gray = synth.make_stream("c1_euroc_mono", 0).frame(0).gray0
+    assert crc(ops.remap(synth.colorize(gray), m1, m2, to_gray=True)) == int(g["euroc_undist_gray_crc"])

@@ -2,6 +2,7 @@
 golden fixtures and the cv2 oracle run live on the same seeded frames (SURVEY.md Appendix D protocol)."""
 import os
 
+import cv2
 import numpy as np
 import pytest
 
@@ -538,3 +539,73 @@ def test_stream_groups_dynamic_mode():
             a, b = plain.insts_output(s), grouped.insts_output(s)
             assert len(a) > 300 and a.tobytes() == b.tobytes()
     plain.close(); grouped.close()
+
+
+@pytest.mark.parametrize("name,B,groups", [("c1_euroc_mono", 1, 1), ("c2_kitti_stereo", 3, 1), ("c2_kitti_stereo", 4, 2)])
+def test_color_and_undistort_ingest_equals_prepared_gray(name, B, groups):
+    """dvfe_set_input(3) + dvfe_set_undistort_maps: BGR frames remapped + converted on the device give byte-identical
+    records to a tracker fed with ImageProcessor::Run's host result (cv2.remap + cvtColor), through the synchronous,
+    pipelined and device-pointer entry points"""
+    from oracle import image_process as ip
+    c = synth.CONFIGS[name]
+    W, H, stereo = c["width"], c["height"], bool(c["stereo"])
+    maps0 = ip.undistort_maps(c["cam0"] if name == "c1_euroc_mono" else synth.EUROC_CAM0 | {"cx": W / 2, "cy": H / 2}, W, H)
+    maps1 = ip.undistort_maps(synth.EUROC_CAM0 | {"cx": W / 2 + 3, "cy": H / 2 - 2, "k1": -0.2}, W, H) if stereo else None
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    ref = BatchTracker(cfg_of(name, n_streams=B))
+    trk = BatchTracker(cfg_of(name, n_streams=B, n_groups=groups))
+    trk.set_input(3)
+    trk.set_undistort_maps(0, maps0[0], maps0[1])
+    if stereo:
+        trk.set_undistort_maps(1, maps1[0], maps1[1])
+    import torch
+    for k in range(5):
+        frs = [s.frame(k) for s in streams]
+        c0 = np.stack([synth.colorize(f.gray0) for f in frs])
+        c1 = np.stack([synth.colorize(f.gray1) for f in frs]) if stereo else None
+        prepared = [ip.run(c0[s], c1[s] if stereo else None, maps0[:2], maps1[:2] if stereo else None) for s in range(B)]
+        g0 = np.stack([p[0] for p in prepared])
+        g1 = np.stack([p[1] for p in prepared]) if stereo else None
+        tm = [f.time0 for f in frs]
+        ref.track_image(g0, g1, tm)
+        if k < 2:
+            trk.track_image(c0, c1, tm)
+        elif k < 4:
+            trk.track_image_async(c0, c1, tm); trk.wait()
+        else:
+            d0 = torch.from_numpy(c0).cuda()
+            d1 = torch.from_numpy(c1).cuda() if stereo else None
+            trk.track_image_device(d0.data_ptr(), d1.data_ptr() if stereo else 0, H * W * 3, W * 3, tm)
+        for s in range(B):
+            a, b = trk.features(s), ref.features(s)
+            assert len(a) > 50 and a.tobytes() == b.tobytes(), (k, s)
+    # switching back to gray input, maps cleared: plain path again
+    trk.set_input(1)
+    trk.set_undistort_maps(0, None, None)
+    trk.set_undistort_maps(1, None, None)
+    frs = [s.frame(5) for s in streams]
+    g0 = np.stack([f.gray0 for f in frs]); g1 = np.stack([f.gray1 for f in frs]) if stereo else None
+    ref.track_image(g0, g1, [f.time0 for f in frs]); trk.track_image(g0, g1, [f.time0 for f in frs])
+    assert all(trk.features(s).tobytes() == ref.features(s).tobytes() for s in range(B))
+    ref.close(); trk.close()
+
+
+def test_color_ingest_semantic_path():
+    """BGR input through dvfe_track_semantic_image (the region mask stays one byte per pixel) + instances"""
+    name = "c3_zed_dynamic"
+    st = synth.make_stream(name, 0)
+    ref = BatchTracker(cfg_of(name, max_instances=8))
+    trk = BatchTracker(cfg_of(name, max_instances=8))
+    trk.set_input(3)
+    for k in range(3):
+        f = st.frame(k)
+        ref.track_semantic_image(f.gray0, f.gray1, f.inv_merge_mask, int(f.exist_inst), f.time0)
+        ref.insts_track(0, f.boxes, f.time0)
+        # colorize() keeps B = gray; use a colour image whose BGR2GRAY is exactly the gray frame: B = G = R = gray
+        c0, c1 = np.repeat(f.gray0[..., None], 3, -1), np.repeat(f.gray1[..., None], 3, -1)
+        assert np.array_equal(cv2.cvtColor(c0, cv2.COLOR_BGR2GRAY), f.gray0)
+        trk.track_semantic_image(c0, c1, f.inv_merge_mask, int(f.exist_inst), f.time0)
+        trk.insts_track(0, f.boxes, f.time0)
+        assert trk.features(0).tobytes() == ref.features(0).tobytes()
+        assert trk.insts_output(0).tobytes() == ref.insts_output(0).tobytes()
+    ref.close(); trk.close()

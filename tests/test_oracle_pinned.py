@@ -163,3 +163,36 @@ def test_feature_track_by_lk_throws_on_empty():
     img = np.zeros((64, 64), np.uint8)
     with pytest.raises(RuntimeError):
         cvfe.feature_track_by_lk(img, img, np.zeros((0, 2), np.float32))
+
+
+def test_remap_and_gray_spec_vs_cv2_and_golden():
+    """§8f N1/N2 frame preparation: the C restatement of cv::remap (CV_16SC2 maps, INTER_LINEAR, constant border) and of
+    cvtColor(BGR2GRAY) equals cv2 bit for bit, incl. taps outside the image, and reproduces the committed golden"""
+    g = load_golden("prep.npz")
+    assert np.array_equal(spec.remap(g["bgr"], g["map1"], g["map2"]), g["remap_bgr"])
+    assert np.array_equal(spec.remap(g["bgr"][..., 1].copy(), g["map1"], g["map2"]), g["remap_gray"])
+    assert np.array_equal(spec.bgr_to_gray(g["bgr"]), g["gray"])
+    assert np.array_equal(spec.bgr_to_gray(spec.remap(g["bgr"], g["map1"], g["map2"])), g["remap_then_gray"])
+    rng = np.random.default_rng(5)
+    for (h, w) in [(33, 47), (1, 9), (120, 64)]:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        m1, m2 = synth.random_maps(w, h, 100 + h, outside=4.0)
+        assert np.array_equal(spec.remap(src, m1, m2), cv2.remap(src, m1, m2, cv2.INTER_LINEAR))
+        # float maps through cv2.convertMaps give the same fixed-point maps as the generator's rule
+        fx = (m1[..., 0].astype(np.float32) + (m2 & 31).astype(np.float32) / 32)
+        fy = (m1[..., 1].astype(np.float32) + (m2 >> 5).astype(np.float32) / 32)
+        c1, c2 = cv2.convertMaps(fx, fy, cv2.CV_16SC2)
+        assert np.array_equal(c1, m1) and np.array_equal(c2, m2)
+
+
+def test_undistort_maps_golden():
+    from oracle import image_process as ip
+    g = load_golden("prep.npz")
+    c = synth.CONFIGS["c1_euroc_mono"]
+    m1, m2, cam = ip.undistort_maps(c["cam0"], c["width"], c["height"])
+    assert crc(m1) == int(g["euroc_map1_crc"]) and crc(m2) == int(g["euroc_map2_crc"])
+    assert np.allclose([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], g["euroc_new_k"], rtol=0, atol=1e-9)
+    gray = synth.make_stream("c1_euroc_mono", 0).frame(0).gray0
+    und = ip.run(synth.colorize(gray), None, (m1, m2))[0]
+    assert crc(und) == int(g["euroc_undist_gray_crc"])
+    assert np.array_equal(und, spec.bgr_to_gray(spec.remap(synth.colorize(gray), m1, m2)))
