@@ -95,4 +95,11 @@ struct LkGroup {
     const uint8_t* mask;     // nullable: status &= mask[cvRound(pts2)] != 0
     int mask_pitch;
     float offx, offy;        // added to pts1 first (InstFeat::TrackRightByPad)
+    unsigned* tcache;        // nullable: forward-pass template cache, LK_TCACHE_WORDS words per (point, level)
 };
+// Template cache block of one (point, level): lane-major words, word j of lane l at [j * 32 + l]:
+//   0..13  (Ix, Iy) int16 pairs of the lane's 14 window pixels;  14, 15  the lane's sum I*Ix, sum I*Iy;
+//   16     lanes 0..2: A11, A12, A22 (float bits)
+#define LK_TCACHE_WORDS (17 * 32)
+#define LK_TCACHE_WRITE 1    // forward pass stores its templates (stereo call: template = current left image at the current points)
+#define LK_TCACHE_READ 2     // forward pass loads them (next temporal call: same image, same points)

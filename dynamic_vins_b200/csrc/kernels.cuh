@@ -57,7 +57,7 @@ int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cuda
 
 // lk.cu
 int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
-              int back_max_level = 1, double fb_threshold = 0.5);
+              int back_max_level = 1, double fb_threshold = 0.5, int tcache_flags = 0);
 
 // gftt.cu
 struct GfttJob {                 // one detection problem (a stream's image, or one instance ROI)

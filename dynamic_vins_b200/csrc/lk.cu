@@ -155,7 +155,7 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
 }
 
 __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back,
-                                                                                    int back_max_level, double fb_threshold) {
+                                                                                    int back_max_level, double fb_threshold, int tcache_flags) {
     __shared__ __align__(16) uint8_t s_win[LK_WARPS][LK_WIN_BYTES];
     const LkGroup& G = groups[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,29 +207,57 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 if (level == 0) st = 0;
                 continue;
             }
-            // ---- stage the 24x24 window of I around the patch (rows ipy-1.., columns ipx-1..) ----
-            __syncwarp();
-            for (int t = lane; t < 24 * 6; t += 32) {          // 24 rows x 6 words, rows are 4-byte aligned in smem
-                const int r = t / 6, c4 = (t - r * 6) * 4;
-                *reinterpret_cast<unsigned*>(win + r * 24 + c4) = load4(Ipx + (ipy - 1 + r) * L.pitch, ipx - 1 + c4);
-            }
-            __syncwarp();
-
-            float a = prevx - (float)ipx, b = prevy - (float)ipy;
-            int iw00, iw01, iw10, iw11;
-            lk_weights(a, b, iw00, iw01, iw10, iw11);
-            const bool interior = ipx >= 0 && ipy >= 0 && ipx + 22 <= L.w && ipy + 22 <= L.h;
-
             int Ix0[LK_RUN], Iy0[LK_RUN], Ix1[LK_RUN], Iy1[LK_RUN];
             int c1 = 0, c2 = 0;          // sum I*Ix, sum I*Iy over this lane's pixels (constant over the iterations)
-            int sA11 = 0, sA12 = 0, sA22 = 0;
-            lk_template_run(win, ry0, rx0, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
-                            sA11, sA12, sA22);
-            lk_template_run(win, ry1, rx1, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
-                            sA11, sA12, sA22);
-            const float A11 = __ll2float_rn(warp_sum_i64(sA11)) * FLT_SCALE;
-            const float A12 = __ll2float_rn(warp_sum_i64(sA12)) * FLT_SCALE;
-            const float A22 = __ll2float_rn(warp_sum_i64(sA22)) * FLT_SCALE;
+            float A11, A12, A22;
+            // The forward template of a stereo call (current left image at the current points) is bit for bit the
+            // forward template of the next temporal call (same image, now `prev`, same points): the stereo call
+            // stores it, the temporal call loads it instead of rebuilding it (4 of the 12 templates of a frame).
+            unsigned* __restrict__ tc = (pass == 0 && G.tcache != nullptr && level < DVFE_MAX_PYR_LEVELS)
+                                            ? G.tcache + ((size_t)i * DVFE_MAX_PYR_LEVELS + level) * LK_TCACHE_WORDS + lane : nullptr;
+            if (tc != nullptr && (tcache_flags & LK_TCACHE_READ)) {
+#pragma unroll
+                for (int j = 0; j < LK_RUN; j++) {
+                    const int w0 = (int)tc[j * 32], w1 = (int)tc[(LK_RUN + j) * 32];
+                    Ix0[j] = (w0 << 16) >> 16; Iy0[j] = w0 >> 16;
+                    Ix1[j] = (w1 << 16) >> 16; Iy1[j] = w1 >> 16;
+                }
+                c1 = (int)tc[14 * 32]; c2 = (int)tc[15 * 32];
+                const unsigned m = tc[16 * 32];
+                A11 = __uint_as_float(__shfl_sync(0xffffffffu, m, 0));
+                A12 = __uint_as_float(__shfl_sync(0xffffffffu, m, 1));
+                A22 = __uint_as_float(__shfl_sync(0xffffffffu, m, 2));
+            } else {
+                // ---- stage the 24x24 window of I around the patch (rows ipy-1.., columns ipx-1..) ----
+                __syncwarp();
+                for (int t = lane; t < 24 * 6; t += 32) {          // 24 rows x 6 words, rows are 4-byte aligned in smem
+                    const int r = t / 6, c4 = (t - r * 6) * 4;
+                    *reinterpret_cast<unsigned*>(win + r * 24 + c4) = load4(Ipx + (ipy - 1 + r) * L.pitch, ipx - 1 + c4);
+                }
+                __syncwarp();
+
+                const float a = prevx - (float)ipx, b = prevy - (float)ipy;
+                int iw00, iw01, iw10, iw11;
+                lk_weights(a, b, iw00, iw01, iw10, iw11);
+                const bool interior = ipx >= 0 && ipy >= 0 && ipx + 22 <= L.w && ipy + 22 <= L.h;
+                int sA11 = 0, sA12 = 0, sA22 = 0;
+                lk_template_run(win, ry0, rx0, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
+                                sA11, sA12, sA22);
+                lk_template_run(win, ry1, rx1, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
+                                sA11, sA12, sA22);
+                A11 = __ll2float_rn(warp_sum_i64(sA11)) * FLT_SCALE;
+                A12 = __ll2float_rn(warp_sum_i64(sA12)) * FLT_SCALE;
+                A22 = __ll2float_rn(warp_sum_i64(sA22)) * FLT_SCALE;
+                if (tc != nullptr && (tcache_flags & LK_TCACHE_WRITE)) {
+#pragma unroll
+                    for (int j = 0; j < LK_RUN; j++) {
+                        tc[j * 32] = __byte_perm((unsigned)Ix0[j], (unsigned)Iy0[j], 0x5410);
+                        tc[(LK_RUN + j) * 32] = __byte_perm((unsigned)Ix1[j], (unsigned)Iy1[j], 0x5410);
+                    }
+                    tc[14 * 32] = (unsigned)c1; tc[15 * 32] = (unsigned)c2;
+                    tc[16 * 32] = __float_as_uint(lane == 0 ? A11 : (lane == 1 ? A12 : A22));
+                }
+            }
             float D = A11 * A22 - A12 * A12;
             const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * DVFE_WIN * DVFE_WIN);
             if ((double)minEig < 1e-4 || D < 1.1920928955078125e-07f) {
@@ -247,7 +275,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                     if (level == 0) st = 0;
                     break;
                 }
-                a = nextx - (float)inx; b = nexty - (float)iny;
+                const float a = nextx - (float)inx, b = nexty - (float)iny;
+                int iw00, iw01, iw10, iw11;
                 lk_weights(a, b, iw00, iw01, iw10, iw11);
                 const int W01 = (iw00 & 0xffff) | (iw01 << 16);
                 const int W23 = (iw10 & 0xffff) | (iw11 << 16);
@@ -321,10 +350,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
 }
 
 int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
-              int back_max_level, double fb_threshold) {
+              int back_max_level, double fb_threshold, int tcache_flags) {
     if (n_groups <= 0 || max_pts <= 0) return DVFE_OK;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, n_groups);
-    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back, back_max_level, fb_threshold);
+    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back, back_max_level, fb_threshold, tcache_flags);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

@@ -206,6 +206,8 @@ int dvfe_tracker::init() {
     if (staged_upload)
         for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
+    if (cfg.stereo)
+        DVFE_CHECK(dmalloc(&d_tcache, (size_t)B * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS));
     // LK groups: [phase][temporal raw | temporal semantic | stereo]
     std::vector<LkGroup> g(B);
     for (int ph = 0; ph < 6; ph++) {
@@ -228,6 +230,7 @@ int dvfe_tracker::init() {
                     G.ptsA = bg.pts + o; G.ptsB = bg.rpts + o; G.status = bg.rstatus + o;
                 }
                 G.n = bg.n + s;
+                G.tcache = d_tcache ? d_tcache + (size_t)s * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS : nullptr;
             }
             DVFE_CHECK(dmalloc(&d_groups[ph][kind], (size_t)B));
             DVFE_CUDA(cudaMemcpy(d_groups[ph][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
@@ -275,7 +278,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
-    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFree(t->d_err);
+    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFree(t->d_err); cudaFree(t->d_tcache);
     for (int p = 0; p < 2; p++) {
         cudaFree(t->d_obs[p]); cudaFree(t->d_nobs[p]);
         if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
@@ -327,7 +330,8 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
-        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
+        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh,
+                             tcache_valid ? LK_TCACHE_READ : 0));
     mark(ST_LK_TEMPORAL + 1);
     if (k > 0)   // ReduceVector x4 + track_cnt++
         DVFE_CHECK(launch_compact(bg, B, cap, st));
@@ -350,7 +354,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     mark(ST_LEFT_POST + 1);
     if (stereo_now) DVFE_CUDA(cudaStreamWaitEvent(st, ev_rpyr[par], 0));
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
-        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh));
+        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh,
+                             LK_TCACHE_WRITE));
+    tcache_valid = stereo_now && d_tcache != nullptr;
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs[par], d_nobs[par], st));
     mark(ST_PACK + 1);
@@ -714,6 +720,7 @@ extern "C" int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* stt
     DVFE_CUDA(cudaMemcpy(t->bg.n + stream, &n, sizeof(int), cudaMemcpyHostToDevice));
     DVFE_CUDA(cudaMemcpy(t->d_next_id + stream, &stt->next_id, sizeof(uint32_t), cudaMemcpyHostToDevice));
     t->prev_time[stream] = stt->prev_time;
+    t->tcache_valid = false;                 // the cached templates belong to the points that were just replaced
     if (n > 0) {
         DVFE_CUDA(cudaMemcpy(t->bg.ids + o, stt->ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
         DVFE_CUDA(cudaMemcpy(t->bg.track_cnt + o, stt->track_cnt, n * sizeof(int32_t), cudaMemcpyHostToDevice));

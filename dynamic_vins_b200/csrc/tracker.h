@@ -63,6 +63,8 @@ struct dvfe_tracker {
     LkGroup* d_groups[6][3] = {};                    // [phase][temporal raw | temporal semantic | stereo]
     GfttJob* d_jobs[6][2] = {};                      // [phase][raw | semantic]
     InstanceState* inst = nullptr;
+    unsigned* d_tcache = nullptr;                    // LK template cache [B][cap][DVFE_MAX_PYR_LEVELS][LK_TCACHE_WORDS] (stereo only)
+    bool tcache_valid = false;                       // the last step ran the stereo LK on the points `bg` holds now
     int lk_back_level = 1;                           // backward LK maxLevel (feature_utils.cpp:51: 1; cv::cuda path: 3)
     double lk_fb_thresh = 0.5;                       // forward-backward threshold in px (:57: 0.5; cv::cuda path: 1.0)
 
