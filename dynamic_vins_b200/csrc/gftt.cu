@@ -111,117 +111,198 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 #endif
 #define RS_WARPS 8
 
+#ifndef RS_OPT_I2F
+#define RS_OPT_I2F 1
+#endif
+#ifndef RS_OPT_DSHFL
+#define RS_OPT_DSHFL 0
+#endif
+#ifndef RS_UNROLL
+#define RS_UNROLL 3
+#endif
+constexpr int kRsUnroll = RS_UNROLL;
+// u8 -> float without the XU-pipe I2F: 2^23 + v as bits, minus 2^23 (exact)
+__device__ __forceinline__ float u8_to_float(unsigned v) {
+#if RS_OPT_I2F
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+#else
+    return (float)v;
+#endif
+}
+
+struct RespCtx {                 // per-strip constants of the marching stencil
+    const uint8_t* __restrict__ img; int pitch, w, h, xb, y0, y1, lane, x;
+    const uint8_t* __restrict__ col;       // img + reflect101(x)
+    const uint8_t* __restrict__ col_edge;  // lanes 0 / 31: the column outside the 32-lane window
+    bool owned_col, cand_col, x_border;
+    float* __restrict__ eig; const uint8_t* __restrict__ mask; int mask_pitch;
+    int* __restrict__ counters; unsigned long long* __restrict__ cand; int cand_cap;
+};
+struct RespState {               // registers carried from row to row
+    float dxr0 = 0.f, dxr1 = 0.f, smr0 = 0.f, smr1 = 0.f;             // row-filter outputs of rows y-2, y-1
+    double h0x = 0.0, h0y = 0.0, h0z = 0.0, h1x = 0.0, h1y = 0.0, h1z = 0.0;   // H(y-3), H(y-2)
+    float lam1 = 0.f, lr1 = 0.f, hm1 = 0.f, hm0 = 0.f;                 // lambda row y-3 (lam, left/right max), hm of y-3, y-4
+    int best = INT_MIN;
+    uint8_t mk1 = 0;                                                   // mask of row y-3 at this column
+};
+
+// One step of the marching stencil: load image row y, finish the derivatives of row y-1, lambda of row y-2 and the
+// local-maximum test of row y-3.  FAST = the step is interior: rows y-3..y inside the image and the strip (no reflection,
+// no box-filter border rule, every row owned) and the warp's 32 columns inside the image; all the index tests fold away.
+// The arithmetic is the same expression by expression in both variants.
+template <bool WRITE_EIG, bool EMIT, bool FAST>
+__device__ __forceinline__ void resp_step(const RespCtx& C, RespState& S, int y, unsigned pre_c = 0, unsigned pre_edge = 0,
+                                          unsigned pre_mask = 0) {
+    const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
+    const float s2 = s * 2.0f;
+    const int lane = C.lane, x = C.x, w = C.w, h = C.h;
+    // ---- image row y (REFLECT_101; y is within 3 rows of the image), horizontal neighbours by shuffle ----
+    const int ry = FAST ? y : (y < 0 ? -y : (y >= h ? 2 * (h - 1) - y : y));
+    const int ro = ry * C.pitch;
+    // FAST steps get the bytes of this row from the caller, which loaded them one step ahead (the load latency
+    // would otherwise sit at the head of a fully dependent chain)
+    const float c = u8_to_float(FAST ? pre_c : __ldg(C.col + ro));
+    const int yl = y - 2;
+    // mask of row yl, needed for the masked maximum now and for the candidate test of the next step
+    uint8_t mk2 = 0;
+    if (FAST) mk2 = (uint8_t)pre_mask;
+    else if (EMIT && C.owned_col && yl >= C.y0 && yl < C.y1) mk2 = __ldg(C.mask + yl * C.mask_pitch + x);
+    float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+    if (FAST) {
+        const float e = u8_to_float(pre_edge);
+        if (lane == 0) l = e;
+        if (lane == 31) r = e;
+    } else {
+        if (lane == 0) l = u8_to_float(__ldg(C.col_edge + ro));
+        if (lane == 31) r = u8_to_float(__ldg(C.col_edge + ro));
+    }
+    // row filters: [-1 0 1] exact; [1 2 1]*scale as fma(s, r, fma(2s, c, s*l))
+    const float dxr2 = r - l;
+    const float smr2 = __fmaf_rn(s, r, __fmaf_rn(s2, c, __fmul_rn(s, l)));
+    // ---- derivatives of row y-1: column filters [1 2 1]*scale -> fma(s, d0 + d2, (2s)*d1) ; [-1 0 1] ----
+    const float dx = __fmaf_rn(s, __fadd_rn(S.dxr0, dxr2), __fmul_rn(s2, S.dxr1));
+    const float dy = __fsub_rn(smr2, S.smr0);
+    S.dxr0 = S.dxr1; S.dxr1 = dxr2; S.smr0 = S.smr1; S.smr1 = smr2;
+    float pxx = __fmul_rn(dx, dx), pxy = __fmul_rn(dx, dy), pyy = __fmul_rn(dy, dy);
+    // box-filter border rule (REFLECT_101 on the cov image): column -1 takes column 1, column w takes w-2
+    if (!FAST && C.x_border) {
+        const float axx = __shfl_down_sync(0xffffffffu, pxx, 2), axy = __shfl_down_sync(0xffffffffu, pxy, 2),
+                    ayy = __shfl_down_sync(0xffffffffu, pyy, 2);
+        const float bxx = __shfl_up_sync(0xffffffffu, pxx, 2), bxy = __shfl_up_sync(0xffffffffu, pxy, 2),
+                    byy = __shfl_up_sync(0xffffffffu, pyy, 2);
+        if (x == -1) { pxx = axx; pxy = axy; pyy = ayy; }
+        if (x == w) { pxx = bxx; pxy = bxy; pyy = byy; }
+    }
+    // ---- H(y-1): horizontal 3-sum in double, left to right ----
+#if RS_OPT_DSHFL
+    // widen once, move the doubles: 3 conversions + 12 shuffles instead of 9 conversions + 6 shuffles (the conversions
+    // run on the 16-lane XU pipe, which bounds this kernel together with the issue slots)
+    const double qxx = (double)pxx, qxy = (double)pxy, qyy = (double)pyy;
+    double h2x = (__shfl_up_sync(0xffffffffu, qxx, 1) + qxx) + __shfl_down_sync(0xffffffffu, qxx, 1);
+    double h2y = (__shfl_up_sync(0xffffffffu, qxy, 1) + qxy) + __shfl_down_sync(0xffffffffu, qxy, 1);
+    double h2z = (__shfl_up_sync(0xffffffffu, qyy, 1) + qyy) + __shfl_down_sync(0xffffffffu, qyy, 1);
+#else
+    const float lxx = __shfl_up_sync(0xffffffffu, pxx, 1), lxy = __shfl_up_sync(0xffffffffu, pxy, 1),
+                lyy = __shfl_up_sync(0xffffffffu, pyy, 1);
+    const float rxx = __shfl_down_sync(0xffffffffu, pxx, 1), rxy = __shfl_down_sync(0xffffffffu, pxy, 1),
+                ryy = __shfl_down_sync(0xffffffffu, pyy, 1);
+    double h2x = ((double)lxx + (double)pxx) + (double)rxx;
+    double h2y = ((double)lxy + (double)pxy) + (double)rxy;
+    double h2z = ((double)lyy + (double)pyy) + (double)ryy;
+#endif
+    // ---- lambda of row yl = y-2: vertical 3-sum top to bottom; rows -1 / h take rows 1 / h-2 ----
+    double ax = S.h0x, ay = S.h0y, az = S.h0z;
+    if (!FAST && (yl == 0 || yl == h - 1)) {
+        if (yl == 0) { ax = h2x; ay = h2y; az = h2z; }
+        if (yl == h - 1) { h2x = S.h0x; h2y = S.h0y; h2z = S.h0z; }
+    }
+    const float cxx = (float)((ax + S.h1x) + h2x);
+    const float cxy = (float)((ay + S.h1y) + h2y);
+    const float cyy = (float)((az + S.h1z) + h2z);
+    S.h0x = S.h1x; S.h0y = S.h1y; S.h0z = S.h1z; S.h1x = h2x; S.h1y = h2y; S.h1z = h2z;
+    float lam = 0.f;
+    if (FAST || (yl >= 0 && yl < h && x >= 0 && x < w)) {
+        const float a = __fmul_rn(cxx, 0.5f), b = cxy, cc = __fmul_rn(cyy, 0.5f);
+        const float amc = __fsub_rn(a, cc);
+        lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+        if (C.owned_col && (FAST || (yl >= C.y0 && yl < C.y1))) {
+            if (WRITE_EIG) C.eig[(size_t)yl * w + x] = lam;
+            if (EMIT && mk2 != 0) S.best = max(S.best, f2ord(lam));
+        }
+    }
+    if (!EMIT) return;
+    // ---- 3x3 local maximum of row yc = y-3 ----
+    const float ll = __shfl_up_sync(0xffffffffu, lam, 1), rl = __shfl_down_sync(0xffffffffu, lam, 1);
+    const float lr2 = fmaxf(ll, rl), hm2 = fmaxf(lr2, lam);
+    const int yc = y - 3;
+    bool is_cand = false;
+    if (C.cand_col && (FAST || (yc >= C.y0 && yc < C.y1 && yc >= 1 && yc < h - 1)) && S.lam1 != 0.f) {
+        const float m = fmaxf(fmaxf(S.hm0, hm2), S.lr1);
+        if (!(m > S.lam1)) is_cand = S.mk1 != 0;
+    }
+    const float v = S.lam1;
+    S.hm0 = S.hm1; S.hm1 = hm2; S.lam1 = lam; S.lr1 = lr2; S.mk1 = mk2;
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+    if (ballot) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&C.counters[0], __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_cand) {
+            const int pos = base + __popc(ballot & ((1u << lane) - 1));
+            if (pos < C.cand_cap)
+                C.cand[pos] = ((unsigned long long)((unsigned)f2ord(v) ^ 0x80000000u) << 32) | (unsigned)(yc * w + x);
+            else
+                C.counters[2] = 1;
+        }
+    }
+}
+
 template <bool WRITE_EIG, bool EMIT>
 __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int pitch, int w, int h, int xb, int y0,
                                            float* __restrict__ eig, const uint8_t* __restrict__ mask, int mask_pitch,
                                            int* __restrict__ counters, unsigned long long* __restrict__ cand, int cand_cap) {
-    const int lane = threadIdx.x & 31;
-    const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
-    const float s2 = s * 2.0f;
-    const int x = xb + lane - 2;
-    const int y1 = min(y0 + RS_ROWS, h);
-    const uint8_t* __restrict__ col = img + reflect101(x, w);
-    const uint8_t* __restrict__ col_edge = img + reflect101(lane == 0 ? x - 1 : x + 1, w);   // lanes 0 / 31 only
-    const bool owned_col = lane >= 2 && lane < 2 + RS_COLS && x < w;
-    const bool cand_col = owned_col && x >= 1 && x < w - 1;
-
-    float dxr0 = 0.f, dxr1 = 0.f, smr0 = 0.f, smr1 = 0.f;           // row-filter outputs of rows y-2, y-1
-    double h0x = 0.0, h0y = 0.0, h0z = 0.0, h1x = 0.0, h1y = 0.0, h1z = 0.0;   // H(y-3), H(y-2)
-    float lam1 = 0.f, lr1 = 0.f, hm1 = 0.f, hm0 = 0.f;               // lambda row y-3 (lam, left/right max), hm of y-3, y-4
-    int best = INT_MIN;
-
-    const int y_last = y1 + (EMIT ? 2 : 1);
-    uint8_t mk1 = 0;                                                 // mask of row y-3 at this column
-    for (int y = y0 - 3; y <= y_last; y++) {
-        // ---- image row y (REFLECT_101; y is within 3 rows of the image), horizontal neighbours by shuffle ----
-        const int ry = y < 0 ? -y : (y >= h ? 2 * (h - 1) - y : y);
-        const int ro = ry * pitch;
-        const float c = (float)__ldg(col + ro);
-        const int yl = y - 2;
-        // mask of row yl, needed for the masked maximum now and for the candidate test of the next step
-        uint8_t mk2 = 0;
-        if (EMIT && owned_col && yl >= y0 && yl < y1) mk2 = __ldg(mask + yl * mask_pitch + x);
-        float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
-        if (lane == 0) l = (float)__ldg(col_edge + ro);
-        if (lane == 31) r = (float)__ldg(col_edge + ro);
-        // row filters: [-1 0 1] exact; [1 2 1]*scale as fma(s, r, fma(2s, c, s*l))
-        const float dxr2 = r - l;
-        const float smr2 = __fmaf_rn(s, r, __fmaf_rn(s2, c, __fmul_rn(s, l)));
-        // ---- derivatives of row y-1: column filters [1 2 1]*scale -> fma(s, d0 + d2, (2s)*d1) ; [-1 0 1] ----
-        const float dx = __fmaf_rn(s, __fadd_rn(dxr0, dxr2), __fmul_rn(s2, dxr1));
-        const float dy = __fsub_rn(smr2, smr0);
-        dxr0 = dxr1; dxr1 = dxr2; smr0 = smr1; smr1 = smr2;
-        float pxx = __fmul_rn(dx, dx), pxy = __fmul_rn(dx, dy), pyy = __fmul_rn(dy, dy);
-        // box-filter border rule (REFLECT_101 on the cov image): column -1 takes column 1, column w takes w-2
-        if (xb < 2 || xb + 30 > w) {
-            const float axx = __shfl_down_sync(0xffffffffu, pxx, 2), axy = __shfl_down_sync(0xffffffffu, pxy, 2),
-                        ayy = __shfl_down_sync(0xffffffffu, pyy, 2);
-            const float bxx = __shfl_up_sync(0xffffffffu, pxx, 2), bxy = __shfl_up_sync(0xffffffffu, pxy, 2),
-                        byy = __shfl_up_sync(0xffffffffu, pyy, 2);
-            if (x == -1) { pxx = axx; pxy = axy; pyy = ayy; }
-            if (x == w) { pxx = bxx; pxy = bxy; pyy = byy; }
-        }
-        // ---- H(y-1): horizontal 3-sum in double, left to right ----
-        const float lxx = __shfl_up_sync(0xffffffffu, pxx, 1), lxy = __shfl_up_sync(0xffffffffu, pxy, 1),
-                    lyy = __shfl_up_sync(0xffffffffu, pyy, 1);
-        const float rxx = __shfl_down_sync(0xffffffffu, pxx, 1), rxy = __shfl_down_sync(0xffffffffu, pxy, 1),
-                    ryy = __shfl_down_sync(0xffffffffu, pyy, 1);
-        double h2x = ((double)lxx + (double)pxx) + (double)rxx;
-        double h2y = ((double)lxy + (double)pxy) + (double)rxy;
-        double h2z = ((double)lyy + (double)pyy) + (double)ryy;
-        // ---- lambda of row yl = y-2: vertical 3-sum top to bottom; rows -1 / h take rows 1 / h-2 ----
-        double ax = h0x, ay = h0y, az = h0z;
-        if (yl == 0 || yl == h - 1) {
-            if (yl == 0) { ax = h2x; ay = h2y; az = h2z; }
-            if (yl == h - 1) { h2x = h0x; h2y = h0y; h2z = h0z; }
-        }
-        const float cxx = (float)((ax + h1x) + h2x);
-        const float cxy = (float)((ay + h1y) + h2y);
-        const float cyy = (float)((az + h1z) + h2z);
-        h0x = h1x; h0y = h1y; h0z = h1z; h1x = h2x; h1y = h2y; h1z = h2z;
-        float lam = 0.f;
-        if (yl >= 0 && yl < h && x >= 0 && x < w) {
-            const float a = __fmul_rn(cxx, 0.5f), b = cxy, cc = __fmul_rn(cyy, 0.5f);
-            const float amc = __fsub_rn(a, cc);
-            lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
-            if (owned_col && yl >= y0 && yl < y1) {
-                if (WRITE_EIG) eig[(size_t)yl * w + x] = lam;
-                if (EMIT && mk2 != 0) best = max(best, f2ord(lam));
+    RespCtx C;
+    C.img = img; C.pitch = pitch; C.w = w; C.h = h; C.xb = xb; C.y0 = y0; C.y1 = min(y0 + RS_ROWS, h);
+    C.lane = threadIdx.x & 31;
+    C.x = xb + C.lane - 2;
+    C.col = img + reflect101(C.x, w);
+    C.col_edge = img + reflect101(C.lane == 0 ? C.x - 1 : C.x + 1, w);   // lanes 0 / 31 only
+    C.owned_col = C.lane >= 2 && C.lane < 2 + RS_COLS && C.x < w;
+    C.cand_col = C.owned_col && C.x >= 1 && C.x < w - 1;
+    C.x_border = xb < 2 || xb + 30 > w;
+    C.eig = eig; C.mask = mask; C.mask_pitch = mask_pitch; C.counters = counters; C.cand = cand; C.cand_cap = cand_cap;
+    RespState S;
+    const int y_first = y0 - 3, y_last = C.y1 + (EMIT ? 2 : 1);
+    // interior steps: rows y-3..y inside the image and owned by the strip, all 32 columns (plus the edge columns) inside
+    const int f0 = max(y0 + 3, 4), f1 = C.x_border ? f0 - 1 : min(C.y1 + 1, h - 1);      // [f0, f1]
+    int y = y_first;
+    for (; y <= y_last && y < f0; y++) resp_step<WRITE_EIG, EMIT, false>(C, S, y);
+    if (y <= f1) {
+        const bool edge_lane = C.lane == 0 || C.lane == 31;
+        const uint8_t* __restrict__ pc = C.col + (size_t)y * pitch;
+        const uint8_t* __restrict__ pe = C.col_edge + (size_t)y * pitch;
+        const uint8_t* __restrict__ pm = (EMIT && C.owned_col) ? mask + (size_t)(y - 2) * mask_pitch + C.x : nullptr;
+        unsigned nc = __ldg(pc), ne = edge_lane ? __ldg(pe) : 0u, nm = pm ? __ldg(pm) : 0u;
+#pragma unroll kRsUnroll
+        for (; y <= f1; y++) {
+            const unsigned cc = nc, ce = ne, cm = nm;
+            if (y < f1) {                      // rows y+1 <= f1 <= h-1 and y-1 < y1: in bounds
+                pc += pitch; pe += pitch;
+                nc = __ldg(pc);
+                if (edge_lane) ne = __ldg(pe);
+                if (pm) { pm += mask_pitch; nm = __ldg(pm); }
             }
-        }
-        if (!EMIT) continue;
-        // ---- 3x3 local maximum of row yc = y-3 ----
-        const float ll = __shfl_up_sync(0xffffffffu, lam, 1), rl = __shfl_down_sync(0xffffffffu, lam, 1);
-        const float lr2 = fmaxf(ll, rl), hm2 = fmaxf(lr2, lam);
-        const int yc = y - 3;
-        bool is_cand = false;
-        if (cand_col && yc >= y0 && yc < y1 && yc >= 1 && yc < h - 1 && lam1 != 0.f) {
-            const float m = fmaxf(fmaxf(hm0, hm2), lr1);
-            if (!(m > lam1)) is_cand = mk1 != 0;
-        }
-        const float v = lam1;
-        hm0 = hm1; hm1 = hm2; lam1 = lam; lr1 = lr2; mk1 = mk2;
-        const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
-        if (ballot) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&counters[0], __popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (is_cand) {
-                const int pos = base + __popc(ballot & ((1u << lane) - 1));
-                if (pos < cand_cap)
-                    cand[pos] = ((unsigned long long)((unsigned)f2ord(v) ^ 0x80000000u) << 32) | (unsigned)(yc * w + x);
-                else
-                    counters[2] = 1;
-            }
+            resp_step<WRITE_EIG, EMIT, true>(C, S, y, cc, ce, cm);
         }
     }
+    for (; y <= y_last; y++) resp_step<WRITE_EIG, EMIT, false>(C, S, y);
     if (EMIT) {
-        best = __reduce_max_sync(0xffffffffu, best);
-        if (lane == 0 && best != INT_MIN) atomicMax(&counters[1], best);
+        S.best = __reduce_max_sync(0xffffffffu, S.best);
+        if (C.lane == 0 && S.best != INT_MIN) atomicMax(&counters[1], S.best);
     }
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32) k_gftt_response(const GfttJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(RS_WARPS * 32, 4) k_gftt_response(const GfttJob* __restrict__ jobs) {
     const GfttJob& J = jobs[blockIdx.z];
     if (!gftt_job_active(J) || J.eig_in != nullptr) return;
     const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
@@ -230,7 +311,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_gftt_response(const GfttJob* 
                             J.cand_cap);
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
+__global__ void __launch_bounds__(RS_WARPS * 32, 4) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
     const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
     if (xb >= w || y0 >= h) return;
     resp_strip<true, false>(img, pitch, w, h, xb, y0, eig, nullptr, 0, nullptr, nullptr, 0);
