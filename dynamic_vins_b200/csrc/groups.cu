@@ -96,6 +96,20 @@ int grp_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int*
     return DVFE_OK;
 }
 
+int grp_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv, size_t stride,
+                            int pitch, const int* exist, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0) {
+    size_t boff = 0;
+    for (size_t g = 0; g < t->groups.size(); g++) {
+        const int f = t->group_first[g];
+        const size_t off = (size_t)f * stride;
+        const size_t moff = off / (size_t)(t->groups[g]->prep_active() ? t->groups[g]->in_ch : 1);
+        DVFE_CHECK(dvfe_track_dynamic_async(t->groups[g], left + off, right ? right + off : nullptr, inv ? inv + moff : nullptr,
+                                            stride, pitch, exist + f, boxes ? boxes + boff : nullptr, n_boxes + f, time0 + f));
+        for (int s = f; s < t->group_first[g + 1]; s++) boff += (size_t)n_boxes[s];
+    }
+    return DVFE_OK;
+}
+
 int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local) {
     const int g = t ? grp_of(t, stream, local) : -1;
     if (g < 0) { dvfe_set_error("bad stream index %d", stream); return DVFE_ERR_INVALID; }

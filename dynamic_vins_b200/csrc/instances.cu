@@ -91,6 +91,32 @@ struct Arena {
 };
 }  // namespace
 
+// Everything one InstsTrack call hands to the device and gets back: descriptor arena, packed ROI masks, output records.
+// Two of them, indexed by the parity of the frame step the call belongs to, so that a deferred call
+// (dvfe_track_dynamic_async) can be prepared while the previous step is still running.
+struct InstCall {
+    Arena arena;                         // per-call descriptors (NS entries each), one pinned blob + one device blob
+    uint8_t *h_mask_stage = nullptr, *d_mask_stage = nullptr;    // packed ROI masks of one call (pinned / device)
+    Staged<CropJob> crop;
+    Staged<PyrJob> pyr;                  // 2*NS
+    Staged<LkGroup> lk_t, lk_s;
+    Staged<ErodeJob> erode;
+    Staged<GfttJob> gftt;
+    Staged<uint8_t> act_track, act_vis, clear_flags;    // indexed by set
+    Staged<double> dt;
+    Staged<float2> offs;
+    Staged<uint32_t> inst_id;
+    dvfe_inst_obs* d_out = nullptr;      // [NS*cap]
+    dvfe_inst_obs* h_out = nullptr;      // pinned
+    int* h_n = nullptr;                  // pinned [NS]
+    cudaEvent_t ev_packed = nullptr;     // instance kernels of the call are done (compute stream)
+    cudaEvent_t ev_up = nullptr;         // masks + descriptors of the call are on the device (upload stream)
+    // host side of Output(), fixed when the call is enqueued
+    int s0 = 0, s1 = 0;                  // streams whose Output() this call replaces
+    std::vector<std::pair<int, int>> plan;   // (stream, set) of the visible instances in output order
+    bool has_records = false;            // the call launched kernels (h_n / h_out are meaningful)
+};
+
 struct InstanceState {
     int MI = 0, cap = 0;                 // slots per stream, points per slot (max_dynamic_cnt)
     size_t P = 0;                        // W*H: capacity of one ROI buffer
@@ -101,22 +127,8 @@ struct InstanceState {
     uint8_t *roi_mask = nullptr, *roi_mask_tmp = nullptr, *roi_mask_er = nullptr;   // [B*MI][P]
     uint8_t *pyr_prev = nullptr, *pyr_cur = nullptr;                                 // [B*MI][full.bytes]
     GfttScratch gsc{};                   // B*MI jobs at full image size
-    dvfe_inst_obs* d_out = nullptr;      // [B*MI*cap]
-    dvfe_inst_obs* h_out = nullptr;      // pinned
-    int* h_n = nullptr;                  // pinned [B*MI]
-    // per-call descriptors (MI entries; one stream per call), all inside `arena`
-    Arena arena;
-    uint8_t *h_mask_stage = nullptr, *d_mask_stage = nullptr;    // packed ROI masks of one call (pinned / device)
     size_t mask_stage_cap = 0;
-    Staged<CropJob> crop;
-    Staged<PyrJob> pyr;                  // 2*MI
-    Staged<LkGroup> lk_t, lk_s;
-    Staged<ErodeJob> erode;
-    Staged<GfttJob> gftt;
-    Staged<uint8_t> act_track, act_vis, clear_flags;    // indexed by slot within the stream
-    Staged<double> dt;
-    Staged<float2> offs;
-    Staged<uint32_t> inst_id;
+    InstCall call[2];
 };
 
 int dvfe_tracker::init_instances() {
@@ -142,26 +154,31 @@ int dvfe_tracker::init_instances() {
     DVFE_CHECK(dmalloc(&I.pyr_prev, NS * I.full.bytes));
     DVFE_CHECK(dmalloc(&I.pyr_cur, NS * I.full.bytes));
     DVFE_CHECK(alloc_gftt_scratch(&I.gsc, (int)NS, W, H, (float)cfg.min_dynamic_dist));
-    DVFE_CHECK(dmalloc(&I.d_out, NS * I.cap));
-    DVFE_CUDA(cudaMallocHost((void**)&I.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
-    DVFE_CUDA(cudaMallocHost((void**)&I.h_n, NS * sizeof(int)));
-    DVFE_CHECK(I.arena.alloc(NS * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
-                                             sizeof(GfttJob) + 3 + sizeof(double) + sizeof(float2) + sizeof(uint32_t)) + 4096));
-    I.arena.take(I.crop, (int)NS);
-    I.arena.take(I.pyr, 2 * (int)NS);
-    I.arena.take(I.lk_t, (int)NS);
-    I.arena.take(I.lk_s, (int)NS);
-    I.arena.take(I.erode, (int)NS);
-    I.arena.take(I.gftt, (int)NS);
-    I.arena.take(I.act_track, (int)NS);
-    I.arena.take(I.act_vis, (int)NS);
-    I.arena.take(I.clear_flags, (int)NS);
-    I.arena.take(I.dt, (int)NS);
-    I.arena.take(I.offs, (int)NS);
-    I.arena.take(I.inst_id, (int)NS);
     I.mask_stage_cap = (size_t)(B < 4 ? 4 : B) * I.P;      // ROI masks of one call, packed
-    DVFE_CUDA(cudaMallocHost((void**)&I.h_mask_stage, I.mask_stage_cap));
-    DVFE_CHECK(dmalloc(&I.d_mask_stage, I.mask_stage_cap));
+    for (int p = 0; p < 2; p++) {
+        InstCall& C = I.call[p];
+        DVFE_CHECK(dmalloc(&C.d_out, NS * I.cap));
+        DVFE_CUDA(cudaMallocHost((void**)&C.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
+        DVFE_CUDA(cudaMallocHost((void**)&C.h_n, NS * sizeof(int)));
+        DVFE_CHECK(C.arena.alloc(NS * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
+                                       sizeof(GfttJob) + 3 + sizeof(double) + sizeof(float2) + sizeof(uint32_t)) + 4096));
+        C.arena.take(C.crop, (int)NS);
+        C.arena.take(C.pyr, 2 * (int)NS);
+        C.arena.take(C.lk_t, (int)NS);
+        C.arena.take(C.lk_s, (int)NS);
+        C.arena.take(C.erode, (int)NS);
+        C.arena.take(C.gftt, (int)NS);
+        C.arena.take(C.act_track, (int)NS);
+        C.arena.take(C.act_vis, (int)NS);
+        C.arena.take(C.clear_flags, (int)NS);
+        C.arena.take(C.dt, (int)NS);
+        C.arena.take(C.offs, (int)NS);
+        C.arena.take(C.inst_id, (int)NS);
+        DVFE_CUDA(cudaMallocHost((void**)&C.h_mask_stage, I.mask_stage_cap));
+        DVFE_CHECK(dmalloc(&C.d_mask_stage, I.mask_stage_cap));
+        DVFE_CUDA(cudaEventCreateWithFlags(&C.ev_packed, cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&C.ev_up, cudaEventDisableTiming));
+    }
     return DVFE_OK;
 }
 
@@ -172,10 +189,15 @@ void dvfe_tracker::free_instances() {
     cudaFree(I.roi_gray); cudaFree(I.roi_mask); cudaFree(I.roi_mask_tmp); cudaFree(I.roi_mask_er);
     cudaFree(I.pyr_prev); cudaFree(I.pyr_cur);
     free_gftt_scratch(&I.gsc);
-    cudaFree(I.d_out); cudaFreeHost(I.h_out); cudaFreeHost(I.h_n);
-    I.arena.release();
-    if (I.h_mask_stage) cudaFreeHost(I.h_mask_stage);
-    cudaFree(I.d_mask_stage);
+    for (int p = 0; p < 2; p++) {
+        InstCall& C = I.call[p];
+        cudaFree(C.d_out); cudaFreeHost(C.h_out); cudaFreeHost(C.h_n);
+        C.arena.release();
+        if (C.h_mask_stage) cudaFreeHost(C.h_mask_stage);
+        cudaFree(C.d_mask_stage);
+        if (C.ev_packed) cudaEventDestroy(C.ev_packed);
+        if (C.ev_up) cudaEventDestroy(C.ev_up);
+    }
     delete inst;
     inst = nullptr;
 }
@@ -199,11 +221,16 @@ static void manage_instances(InstStream& S) {
 
 // InstsTrack for the streams [s0, s1): boxes_of[s - s0] / n_of[s - s0] / time_of[s - s0].  Every visible instance of
 // every stream is one job of each batched launch; one descriptor upload, one mask upload, one synchronisation.
+// defer = false: synchronous (the background step has been waited for; ends with a synchronisation and Output() ready).
+// defer = true: enqueue only, behind the background step just submitted; the records come home on the download stream and
+// dvfe_tracker::wait_one() finishes the call (finish_instances).  Nothing on the host side depends on device results.
 static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of,
-                               const double* time_of) {
+                               const double* time_of, bool defer) {
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
-    DVFE_CHECK(t->wait_all());
+    if (!defer) DVFE_CHECK(t->wait_all());
     InstanceState& I = *t->inst;
+    const int par = (int)((t->frames - 1) % 2);          // the step these instances belong to
+    InstCall& C = I.call[par];
     cudaStream_t st = t->st;
     const int W = t->W, H = t->H, MI = I.MI, cap = I.cap, B = t->B;
     const size_t P = I.P;
@@ -212,11 +239,12 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
     const PyrLevel& L0 = t->desc.lv[0];
     const bool stereo_now = t->cfg.stereo && t->last_has_right;
 
-    memset(I.act_track.h, 0, NS); memset(I.act_vis.h, 0, NS); memset(I.clear_flags.h, 0, NS);
+    memset(C.act_track.h, 0, NS); memset(C.act_vis.h, 0, NS); memset(C.clear_flags.h, 0, NS);
     size_t mask_used = 0;
     int nv = 0, n_track = 0, max_rw = 1, max_rh = 1, max_pw = 1, max_ph = 1, max_lv = 1;
     bool any_clear = false;
     std::vector<char> exist(s1 - s0, 0);
+    C.s0 = s0; C.s1 = s1; C.plan.clear(); C.has_records = false;
 
     for (int stream = s0; stream < s1; stream++) {
         InstStream& S = I.streams[stream];
@@ -248,8 +276,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
                 in.track_id = bx.track_id;
                 in.slot = S.free_slots.back();
                 S.free_slots.pop_back();
-                const int zero = 0;
-                DVFE_CUDA(cudaMemcpyAsync(I.pts.n + base_set + in.slot, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+                DVFE_CUDA(cudaMemsetAsync(I.pts.n + base_set + in.slot, 0, sizeof(int), st));
                 it = S.insts.emplace(bx.track_id, in).first;
             }
             InstHost& in = it->second;
@@ -259,7 +286,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             const size_t bytes = (size_t)bx.w * bx.h;
             if (mask_used + bytes <= I.mask_stage_cap) {
                 for (int r = 0; r < bx.h; r++)
-                    memcpy(I.h_mask_stage + mask_used + (size_t)r * bx.w, bx.mask + (size_t)r * bx.mask_pitch, bx.w);
+                    memcpy(C.h_mask_stage + mask_used + (size_t)r * bx.w, bx.mask + (size_t)r * bx.mask_pitch, bx.w);
                 in.mask_off = (long long)mask_used;
                 mask_used += (bytes + 15) & ~(size_t)15;
             } else {
@@ -273,13 +300,12 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             if (!kv.second.visible) kv.second.lost_num++;
             else kv.second.lost_num = 0;
         }
-        S.out.clear();
         exist[stream - s0] = n_boxes > 0;
         if (!exist[stream - s0]) {
             manage_instances(S);
             // ClearState (:41-58) for the instances ExecInst still visits (lost_num == 0)
             for (auto& kv : S.insts)
-                if (kv.second.lost_num == 0) { I.clear_flags.h[base_set + kv.second.slot] = 1; any_clear = true; }
+                if (kv.second.lost_num == 0) { C.clear_flags.h[base_set + kv.second.slot] = 1; any_clear = true; }
             S.last_time = time0;
             continue;
         }
@@ -292,39 +318,39 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             // roi_gray = gray0(rect): crop into the buffer that does not hold prev_roi_gray
             in.cur_buf = in.prev_w > 0 ? 1 - in.cur_buf : in.cur_buf;
             in.roi_w = in.w; in.roi_h = in.h;
-            CropJob& c = I.crop.h[j];
+            CropJob& c = C.crop.h[j];
             c.src = left_px; c.spitch = L0.pitch; c.x = in.x; c.y = in.y; c.w = in.w; c.h = in.h;
             c.dst = I.roi_gray + (set * 2 + in.cur_buf) * P;
             max_rw = std::max(max_rw, in.w); max_rh = std::max(max_rh, in.h);
-            I.act_vis.h[set] = 1;
-            I.dt.h[set] = time0 - S.last_time;                         // curr_time - last_time
-            I.offs.h[set] = make_float2((float)in.x, (float)in.y);       // box2d->rect.tl()
-            I.inst_id.h[set] = in.track_id;
+            C.act_vis.h[set] = 1;
+            C.dt.h[set] = time0 - S.last_time;                         // curr_time - last_time
+            C.offs.h[set] = make_float2((float)in.x, (float)in.y);       // box2d->rect.tl()
+            C.inst_id.h[set] = in.track_id;
             if (in.prev_w > 0) {
                 // InstanceImagePadding: both crops zero-padded to (max rows, max cols)
                 const int pw = std::max(in.prev_w, in.w), ph = std::max(in.prev_h, in.h);
                 const PyrDesc d = make_pyr_desc(pw, ph, t->cfg.lk_max_level > 1 ? t->cfg.lk_max_level : 1);
-                PyrJob& a = I.pyr.h[2 * n_track];
-                PyrJob& b = I.pyr.h[2 * n_track + 1];
+                PyrJob& a = C.pyr.h[2 * n_track];
+                PyrJob& b = C.pyr.h[2 * n_track + 1];
                 a.src = I.roi_gray + (set * 2 + (1 - in.cur_buf)) * P; a.sw = in.prev_w; a.sh = in.prev_h; a.spitch = in.prev_w;
                 a.dst = I.pyr_prev + set * I.full.bytes; a.desc = d;
                 b.src = c.dst; b.sw = in.w; b.sh = in.h; b.spitch = in.w;
                 b.dst = I.pyr_cur + set * I.full.bytes; b.desc = d;
-                LkGroup& G = I.lk_t.h[n_track];
+                LkGroup& G = C.lk_t.h[n_track];
                 memset(&G, 0, sizeof(G));
                 G.pyrA = a.dst; G.pyrB = b.dst; G.desc = d;
                 G.ptsA = I.pts.pts + set * cap; G.ptsB = I.pts.lk_out + set * cap; G.status = I.pts.status + set * cap;
                 G.n = I.pts.n + set;
-                I.act_track.h[set] = 1;
+                C.act_track.h[set] = 1;
                 max_pw = std::max(max_pw, pw); max_ph = std::max(max_ph, ph); max_lv = std::max(max_lv, d.n_levels);
                 n_track++;
             }
             // detection job (:418-446)
-            ErodeJob& e = I.erode.h[j];
-            e.src = in.mask_off >= 0 ? I.d_mask_stage + in.mask_off : I.roi_mask + set * P;
+            ErodeJob& e = C.erode.h[j];
+            e.src = in.mask_off >= 0 ? C.d_mask_stage + in.mask_off : I.roi_mask + set * P;
             e.tmp = I.roi_mask_tmp + set * P; e.dst = I.roi_mask_er + set * P;
             e.w = in.w; e.h = in.h; e.k = 5;
-            GfttJob& J = I.gftt.h[j];
+            GfttJob& J = C.gftt.h[j];
             memset(&J, 0, sizeof(J));
             J.img = c.dst; J.img_pitch = in.w; J.w = in.w; J.h = in.h;
             J.region_mask = e.dst; J.region_pitch = in.w;
@@ -335,7 +361,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             J.disc_radius = t->cfg.min_dynamic_dist; J.min_dist = (float)t->cfg.min_dynamic_dist; J.quality = 0.01;
             J.err = t->d_err;
             // stereo job: TrackRightByPad — full images, points offset by rect.tl()
-            LkGroup& R = I.lk_s.h[j];
+            LkGroup& R = C.lk_s.h[j];
             memset(&R, 0, sizeof(R));
             R.pyrA = left_pyr; R.pyrB = right_pyr; R.desc = t->desc;
             R.ptsA = I.pts.pts + set * cap; R.ptsB = I.pts.rpts + set * cap; R.status = I.pts.rstatus + set * cap;
@@ -343,8 +369,14 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
         }
     }
 
-    if (mask_used > 0) DVFE_CUDA(cudaMemcpyAsync(I.d_mask_stage, I.h_mask_stage, mask_used, cudaMemcpyHostToDevice, st));
-    if (nv > 0 || any_clear) DVFE_CHECK(I.arena.push(st));          // every descriptor array of this call in one copy
+    // host -> device on the upload stream (all H2D traffic stays in one FIFO; the compute stream never queues a copy
+    // behind the next frame's images): the packed masks and every descriptor array of this call in one copy each
+    if (mask_used > 0) DVFE_CUDA(cudaMemcpyAsync(C.d_mask_stage, C.h_mask_stage, mask_used, cudaMemcpyHostToDevice, t->cs));
+    if (nv > 0 || any_clear) DVFE_CHECK(C.arena.push(t->cs));
+    if (mask_used > 0 || nv > 0 || any_clear) {
+        DVFE_CUDA(cudaEventRecord(C.ev_up, t->cs));
+        DVFE_CUDA(cudaStreamWaitEvent(st, C.ev_up, 0));
+    }
     const size_t set0 = (size_t)s0 * MI;
     const int n_sets = (s1 - s0) * MI;
     if (nv > 0) {
@@ -354,51 +386,80 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
         V.pts += o; V.lk_out += o; V.un += o; V.vel += o; V.ids += o; V.track_cnt += o; V.status += o; V.rpts += o;
         V.rstatus += o; V.rprev_un += o; V.rprev_valid += o; V.n += set0;
 
-        DVFE_CHECK(launch_crop_jobs(I.crop.d, nv, max_rw, max_rh, st));
+        DVFE_CHECK(launch_crop_jobs(C.crop.d, nv, max_rw, max_rh, st));
         // inst.TrackLeft(roi_gray_padded, prev_roi_gray_padded): previous-box crop -> current-box crop (:381-413)
-        DVFE_CHECK(launch_build_pyramids_jobs(I.pyr.d, 2 * n_track, max_pw, max_ph, max_lv, st));
-        DVFE_CHECK(launch_lk(I.lk_t.d, n_track, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
-        DVFE_CHECK(launch_compact(V, n_sets, cap, st, I.act_track.d + set0));
+        DVFE_CHECK(launch_build_pyramids_jobs(C.pyr.d, 2 * n_track, max_pw, max_ph, max_lv, st));
+        DVFE_CHECK(launch_lk(C.lk_t.d, n_track, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
+        DVFE_CHECK(launch_compact(V, n_sets, cap, st, C.act_track.d + set0));
         // ErodeMask(roi mask, 5) + discs(min_dynamic_dist) + goodFeaturesToTrack on the ROI + ids (:418-446)
-        DVFE_CHECK(launch_erode_jobs(I.erode.d, nv, max_rw, max_rh, st));
-        DVFE_CHECK(launch_gftt(I.gftt.d, nullptr, nv, max_rw, max_rh, cap, st));
+        DVFE_CHECK(launch_erode_jobs(C.erode.d, nv, max_rw, max_rh, st));
+        DVFE_CHECK(launch_gftt(C.gftt.d, nullptr, nv, max_rw, max_rh, cap, st));
         // UndistortedPointsWithAddOffset(cam0) + PtsVelocity(curr_time - last_time) (:448-457)
-        DVFE_CHECK(launch_left_post(V, n_sets, cap, t->cam0, I.dt.d + set0, I.offs.d + set0, st, I.act_vis.d + set0));
+        DVFE_CHECK(launch_left_post(V, n_sets, cap, t->cam0, C.dt.d + set0, C.offs.d + set0, st, C.act_vis.d + set0));
         // TrackRightByPad + RightUndistortedPts + RightPtsVelocity (:462-471), then the Output() records
-        if (stereo_now) DVFE_CHECK(launch_lk(I.lk_s.d, nv, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
-        DVFE_CHECK(launch_inst_post_pack(V, n_sets, cap, t->cam1, I.dt.d + set0, I.act_vis.d + set0, stereo_now ? 1 : 0,
-                                         I.inst_id.d + set0, I.d_out + o, st));
-        DVFE_CUDA(cudaMemcpyAsync(I.h_n + set0, I.pts.n + set0, n_sets * sizeof(int), cudaMemcpyDeviceToHost, st));
-        DVFE_CUDA(cudaMemcpyAsync(I.h_out + o, I.d_out + o, (size_t)n_sets * cap * sizeof(dvfe_inst_obs),
-                                  cudaMemcpyDeviceToHost, st));
+        if (stereo_now) DVFE_CHECK(launch_lk(C.lk_s.d, nv, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
+        DVFE_CHECK(launch_inst_post_pack(V, n_sets, cap, t->cam1, C.dt.d + set0, C.act_vis.d + set0, stereo_now ? 1 : 0,
+                                         C.inst_id.d + set0, C.d_out + o, st));
+        C.has_records = true;
     }
-    if (any_clear) DVFE_CHECK(launch_clear_sets(I.pts.n + set0, I.clear_flags.d + set0, n_sets, st));
-    if (nv > 0 || any_clear || mask_used > 0) DVFE_CUDA(cudaStreamSynchronize(st));
+    if (any_clear) DVFE_CHECK(launch_clear_sets(I.pts.n + set0, C.clear_flags.d + set0, n_sets, st));
+    if (nv > 0) {
+        // records home: on the download stream when deferred (the next step's kernels do not queue behind the copy)
+        cudaStream_t os = defer ? t->ds : st;
+        if (defer) {
+            DVFE_CUDA(cudaEventRecord(C.ev_packed, st));
+            DVFE_CUDA(cudaStreamWaitEvent(os, C.ev_packed, 0));
+        }
+        const size_t o = set0 * cap;
+        DVFE_CUDA(cudaMemcpyAsync(C.h_n + set0, I.pts.n + set0, n_sets * sizeof(int), cudaMemcpyDeviceToHost, os));
+        DVFE_CUDA(cudaMemcpyAsync(C.h_out + o, C.d_out + o, (size_t)n_sets * cap * sizeof(dvfe_inst_obs),
+                                  cudaMemcpyDeviceToHost, os));
+    }
 
+    // host bookkeeping after the frame: ManageInstances (:474), PostProcess (:479-481), the Output() plan (:521-577)
     for (int stream = s0; stream < s1; stream++) {
         if (!exist[stream - s0]) continue;
         InstStream& S = I.streams[stream];
         const size_t base_set = (size_t)stream * MI;
-        manage_instances(S);                                                      // :474
-        // PostProcess for every instance that is still live and not lost (:479-481): prev_roi_gray = roi_gray
+        manage_instances(S);
         for (auto& kv : S.insts) {
             InstHost& in = kv.second;
             if (in.lost_num > 0) continue;
-            in.prev_w = in.roi_w; in.prev_h = in.roi_h;
+            in.prev_w = in.roi_w; in.prev_h = in.roi_h;          // prev_roi_gray = roi_gray
         }
-        // Output() (:521-577): lost_num == 0 && is_curr_visible, ascending instance id, ascending feature id
+        // Output(): lost_num == 0 && is_curr_visible, ascending instance id, ascending feature id
         for (auto& kv : S.insts) {
             const InstHost& in = kv.second;
             if (in.lost_num > 0 || !in.visible) continue;
-            const size_t set = base_set + in.slot;
-            const int n = I.h_n[set];
-            S.out.insert(S.out.end(), I.h_out + set * cap, I.h_out + set * cap + n);
+            C.plan.emplace_back(stream, (int)(base_set + in.slot));
         }
         S.last_time = time_of[stream - s0];
+    }
+    if (defer) {
+        DVFE_CUDA(cudaEventRecord(t->ev_inst[par], nv > 0 ? t->ds : st));
+        t->inst_pending[par] = true;
+        return DVFE_OK;
+    }
+    if (nv > 0 || any_clear || mask_used > 0) DVFE_CUDA(cudaStreamSynchronize(st));
+    return t->finish_instances(par);
+}
+
+// Output() of a finished call: copy the records of the planned instances out of the pinned buffer
+int dvfe_tracker::finish_instances(int par) {
+    InstanceState& I = *inst;
+    InstCall& C = I.call[par];
+    for (int s = C.s0; s < C.s1; s++) I.streams[s].out.clear();
+    for (const auto& e : C.plan) {
+        std::vector<dvfe_inst_obs>& out = I.streams[e.first].out;
+        const size_t set = (size_t)e.second;
+        const int n = C.has_records ? C.h_n[set] : 0;
+        out.insert(out.end(), C.h_out + set * I.cap, C.h_out + set * I.cap + n);
     }
     return DVFE_OK;
 }
 
+int grp_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv, size_t stride,
+                            int pitch, const int* exist, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0);
 int grp_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n, double time0);
 int grp_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0);
 int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
@@ -422,7 +483,7 @@ extern "C" int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in*
         dvfe_set_error("insts_track: bad argument");
         return DVFE_ERR_INVALID;
     }
-    return insts_track_streams(t, stream, stream + 1, &boxes, &n_boxes, &time0);
+    return insts_track_streams(t, stream, stream + 1, &boxes, &n_boxes, &time0, false);
 }
 
 extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0) {
@@ -439,7 +500,30 @@ extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes
         of[s] = boxes + off;
         off += (size_t)n_boxes[s];
     }
-    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0);
+    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0, false);
+}
+
+// One frame of dynamic mode for all streams, pipelined: TrackSemanticImage + InstsTrack are enqueued behind the previous
+// step (two steps in flight); dvfe_wait() completes the oldest one, after which dvfe_get_features / dvfe_insts_output
+// return its results.
+extern "C" int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,
+                                        size_t stream_stride, int pitch, const int* exist_inst, const dvfe_inst_in* boxes,
+                                        const int* n_boxes, const double* time0) {
+    if (!t || !left || !time0 || !exist_inst || !n_boxes) { dvfe_set_error("track_dynamic_async: null argument"); return DVFE_ERR_INVALID; }
+    if (!t->groups.empty())
+        return grp_track_dynamic_async(t, left, right, inv_merge_mask, stream_stride, pitch, exist_inst, boxes, n_boxes, time0);
+    if (!t->inst) { dvfe_set_error("track_dynamic_async: max_instances must be > 0 at create"); return DVFE_ERR_INVALID; }
+    if (pitch < t->W * t->in_ch) { dvfe_set_error("track_dynamic_async: bad pitch"); return DVFE_ERR_INVALID; }
+    std::vector<const dvfe_inst_in*> of(t->B);
+    size_t off = 0;
+    for (int s = 0; s < t->B; s++) {
+        if (n_boxes[s] < 0 || (n_boxes[s] > 0 && !boxes)) { dvfe_set_error("track_dynamic_async: bad box count"); return DVFE_ERR_INVALID; }
+        of[s] = boxes + off;
+        off += (size_t)n_boxes[s];
+    }
+    DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(t->semantic_submit(left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0));
+    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0, true);
 }
 
 extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out) {

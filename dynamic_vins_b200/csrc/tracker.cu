@@ -196,9 +196,12 @@ int dvfe_tracker::init() {
     }
     DVFE_CHECK(dmalloc(&d_region, (size_t)B * P));
     DVFE_CHECK(dmalloc(&d_region_tmp, (size_t)B * P));
-    DVFE_CHECK(dmalloc(&d_inv_in, (size_t)B * P));
     DVFE_CHECK(dmalloc(&d_exist, (size_t)B));
-    DVFE_CUDA(cudaMallocHost((void**)&h_exist, B * sizeof(int)));
+    for (int p = 0; p < 2; p++) {
+        DVFE_CHECK(dmalloc(&d_inv_in[p], (size_t)B * P));
+        DVFE_CUDA(cudaMallocHost((void**)&h_exist[p], B * sizeof(int)));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_inst[p], cudaEventDisableTiming));
+    }
     DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
     // pitched host->device DMA straight into the padded level 0 runs at full PCIe rate only for rows that are a
     // multiple of 64 bytes; other widths go through a dense staging buffer (one linear copy) and the copy kernel
@@ -291,8 +294,11 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     }
     cudaFree(t->d_stage[0]); cudaFree(t->d_stage[1]);
     for (int i = 0; i < 2; i++) { cudaFree(t->d_raw[i]); cudaFree(t->d_map1[i]); cudaFree(t->d_map2[i]); }
-    cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_inv_in); cudaFree(t->d_exist);
-    cudaFreeHost(t->h_exist);
+    cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_exist);
+    for (int p = 0; p < 2; p++) {
+        cudaFree(t->d_inv_in[p]); cudaFreeHost(t->h_exist[p]);
+        if (t->ev_inst[p]) cudaEventDestroy(t->ev_inst[p]);
+    }
     free_gftt_scratch(&t->gsc);
     for (int p = 0; p < 6; p++) {
         for (int k = 0; k < 3; k++) cudaFree(t->d_groups[p][k]);
@@ -387,6 +393,11 @@ int dvfe_tracker::wait_one() {
     }
     out_slot = par;
     completed++;
+    if (inst_pending[par]) {
+        inst_pending[par] = false;
+        DVFE_CUDA(cudaEventSynchronize(ev_inst[par]));
+        DVFE_CHECK(finish_instances(par));
+    }
     if (h_nobs[par][B] != 0) {
         dvfe_set_error("corner detection: more local maxima than the candidate buffer holds (W*H/4 + 4096); "
                        "the selection of some frame was truncated");
@@ -621,6 +632,42 @@ extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_t
     return DVFE_OK;
 }
 
+int dvfe_tracker::semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,
+                                  size_t stream_stride, int pitch, const int* exist_inst, const double* time0) {
+    while (frames - completed >= 2) DVFE_CHECK(wait_one());      // buffers of step k-2 are free again
+    const size_t P = (size_t)W * H;
+    const int par = (int)(frames % 2);
+    const bool prep = prep_active();
+    // the region mask is one byte per pixel whatever the image format
+    const size_t mask_stride = prep ? stream_stride / (size_t)in_ch : stream_stride;
+    const int mask_pitch = prep ? pitch / in_ch : pitch;
+    // inv_merge_mask -> device on the upload stream, ahead of the images (one copy when every stream has one)
+    bool all = true;
+    for (int s = 0; s < B; s++) {
+        h_exist[par][s] = exist_inst[s] ? 1 : 0;
+        all = all && exist_inst[s];
+        if (exist_inst[s] && !inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
+    }
+    if (all && mask_pitch == W && mask_stride == P) {
+        DVFE_CUDA(cudaMemcpyAsync(d_inv_in[par], inv_merge_mask, (size_t)B * P, cudaMemcpyHostToDevice, cs));
+    } else {
+        for (int s = 0; s < B; s++)
+            if (exist_inst[s])
+                DVFE_CUDA(cudaMemcpy2DAsync(d_inv_in[par] + s * P, W, inv_merge_mask + s * mask_stride, mask_pitch, W, (size_t)H,
+                                            cudaMemcpyHostToDevice, cs));
+    }
+    if (prep) DVFE_CHECK(upload_prepared(left, right, stream_stride, pitch));
+    else if (staged_upload) DVFE_CHECK(upload_staged(left, right, stream_stride, pitch));
+    else DVFE_CHECK(upload_in_place(left, right, stream_stride, pitch));          // records ev_up; st waits for it
+    DVFE_CUDA(cudaMemcpyAsync(d_exist, h_exist[par], B * sizeof(int), cudaMemcpyHostToDevice, st));
+    // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772)
+    const int k = cfg.use_mask_morphology ? cfg.mask_morphology_size : 1;
+    DVFE_CHECK(launch_erode_rect(d_inv_in[par], W, d_region, W, d_region_tmp, W, H, k < 1 ? 1 : k, B, P, d_exist, st));
+    if (!prep && staged_upload)
+        return submit(d_stage[par], right ? d_stage[par] + B * P : nullptr, P, W, time0, true, false, right != nullptr);
+    return submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr);
+}
+
 extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, const uint8_t* right,
                                          const uint8_t* inv_merge_mask, size_t stream_stride, int pitch,
                                          const int* exist_inst, const double* time0) {
@@ -629,33 +676,7 @@ extern "C" int dvfe_track_semantic_image(dvfe_tracker* t, const uint8_t* left, c
     if (IS_GROUP(t)) return grp_track_semantic(t, left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0);
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
-    const size_t P = (size_t)t->W * t->H;
-    const int par = (int)(t->frames % 2);
-    const bool prep = t->prep_active();
-    if (prep) DVFE_CHECK(t->upload_prepared(left, right, stream_stride, pitch));
-    else if (t->staged_upload) DVFE_CHECK(t->upload_staged(left, right, stream_stride, pitch));
-    else DVFE_CHECK(t->upload_in_place(left, right, stream_stride, pitch));
-    // the region mask is one byte per pixel whatever the image format
-    const size_t mask_stride = prep ? stream_stride / (size_t)t->in_ch : stream_stride;
-    const int mask_pitch = prep ? pitch / t->in_ch : pitch;
-    for (int s = 0; s < t->B; s++) {
-        t->h_exist[s] = exist_inst[s] ? 1 : 0;
-        if (exist_inst[s]) {
-            if (!inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
-            DVFE_CUDA(cudaMemcpy2DAsync(t->d_inv_in + s * P, t->W, inv_merge_mask + s * mask_stride, mask_pitch, t->W,
-                                        (size_t)t->H, cudaMemcpyHostToDevice, t->st));
-        }
-    }
-    DVFE_CUDA(cudaMemcpyAsync(t->d_exist, t->h_exist, t->B * sizeof(int), cudaMemcpyHostToDevice, t->st));
-    // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772)
-    const int k = t->cfg.use_mask_morphology ? t->cfg.mask_morphology_size : 1;
-    DVFE_CHECK(launch_erode_rect(t->d_inv_in, t->W, t->d_region, t->W, t->d_region_tmp, t->W, t->H, k < 1 ? 1 : k, t->B, P,
-                                 t->d_exist, t->st));
-    if (!prep && t->staged_upload)
-        DVFE_CHECK(t->submit(t->d_stage[par], right ? t->d_stage[par] + t->B * P : nullptr, P, t->W, time0, true, false,
-                             right != nullptr));
-    else
-        DVFE_CHECK(t->submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr));
+    DVFE_CHECK(t->semantic_submit(left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0));
     return t->wait_all();
 }
 

@@ -56,9 +56,12 @@ struct dvfe_tracker {
     int* d_err = nullptr;
     int out_slot = 0;                                // which h_obs holds the newest completed step
     cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {}, ev_resp[2] = {}, ev_rpyr[2] = {};
-    uint8_t *d_region = nullptr, *d_region_tmp = nullptr, *d_inv_in = nullptr;
+    uint8_t *d_region = nullptr, *d_region_tmp = nullptr;
+    uint8_t* d_inv_in[2] = {nullptr, nullptr};       // uploaded inv_merge_mask, one per in-flight step
     int* d_exist = nullptr;
-    int* h_exist = nullptr;
+    int* h_exist[2] = {nullptr, nullptr};            // pinned, one per in-flight step
+    cudaEvent_t ev_inst[2] = {};                     // instance records of the step are on the host
+    bool inst_pending[2] = {false, false};           // the step carried a deferred InstsTrack (dvfe_track_dynamic_async)
     GfttScratch gsc{};
     LkGroup* d_groups[6][3] = {};                    // [phase][temporal raw | temporal semantic | stereo]
     GfttJob* d_jobs[6][2] = {};                      // [phase][raw | semantic]
@@ -100,6 +103,10 @@ struct dvfe_tracker {
     // enqueue one frame step (no host synchronisation); at most two steps are in flight
     int submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
                bool semantic, bool level0_in_place, bool has_right);
+    // TrackSemanticImage of one frame, enqueued only (uploads on the copy stream, mask erosion + the frame step)
+    int semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask, size_t stream_stride,
+                        int pitch, const int* exist_inst, const double* time0);
+    int finish_instances(int par);                   // instances.cu: host side of a deferred InstsTrack
     int wait_one();                                  // oldest in-flight step -> outputs readable
     int wait_all();
 };

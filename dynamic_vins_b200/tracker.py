@@ -176,8 +176,9 @@ class BatchTracker:
             arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
         L.check(L.lib().dvfe_insts_track(self._h, stream, arr, len(boxes), float(time0)))
 
-    def insts_track_batch(self, boxes_per_stream: Sequence[Sequence[dict]], time0) -> None:
-        """InstsTrack for all B streams in one set of launches"""
+    @staticmethod
+    def marshal_boxes(boxes_per_stream: Sequence[Sequence[dict]]):
+        """the dvfe_inst_in array + per-stream counts of a frame's box lists (a C++ caller holds these natively)"""
         flat = [b for bs in boxes_per_stream for b in bs]
         arr = (L.InstIn * max(1, len(flat)))()
         keep = []
@@ -188,9 +189,27 @@ class BatchTracker:
             arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
             arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
         counts = np.asarray([len(bs) for bs in boxes_per_stream], np.int32)
+        return arr, counts, keep
+
+    def insts_track_batch(self, boxes_per_stream, time0) -> None:
+        """InstsTrack for all B streams in one set of launches; boxes_per_stream: per-stream box lists or marshal_boxes()'s result"""
+        arr, counts, _keep = boxes_per_stream if isinstance(boxes_per_stream, tuple) else self.marshal_boxes(boxes_per_stream)
         assert len(counts) == self.B
         t = self._times(time0)
         L.check(L.lib().dvfe_insts_track_batch(self._h, arr, L.ptr(counts), L.ptr(t)))
+
+    def track_dynamic_async(self, left, right, inv_merge_mask, exist_inst, boxes_per_stream, time0) -> None:
+        """TrackSemanticImage + InstsTrack of one frame for all streams, pipelined; results after the matching wait()"""
+        l = self._batch(left, self.B, self.H, self.W, self.ch)
+        r = self._batch(right, self.B, self.H, self.W, self.ch)
+        m = self._batch(inv_merge_mask, self.B, self.H, self.W)
+        e = np.ascontiguousarray(np.broadcast_to(np.asarray(exist_inst, np.int32), (self.B,)))
+        arr, counts, keep = boxes_per_stream if isinstance(boxes_per_stream, tuple) else self.marshal_boxes(boxes_per_stream)
+        assert len(counts) == self.B
+        t = self._times(time0)
+        self._keep = (l, r, m, e, arr, counts, keep, t, getattr(self, "_keep", None) and self._keep[:8])
+        L.check(L.lib().dvfe_track_dynamic_async(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W * self.ch,
+                                                 self.W * self.ch, L.ptr(e), arr, L.ptr(counts), L.ptr(t)))
 
     # ---- outputs -------------------------------------------------------------------------------
     def features(self, stream: int = 0) -> np.ndarray:

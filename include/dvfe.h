@@ -251,6 +251,16 @@ int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int h, uint8_t
 int dvfe_op_remap(const uint8_t* src, int w, int h, int channels, int pitch, const int16_t* map1, const uint16_t* map2,
                   int to_gray, uint8_t* dst);
 
+/* One frame of dynamic mode for ALL streams, pipelined (the asynchronous form of FeatureTrack()'s dynamic branch,
+ * system/main.cpp:247-254: TrackSemanticImage + InstsTrack of the same frame): both are enqueued behind the previous
+ * step (two steps in flight; the uploads of frame k+1 overlap the kernels of frame k) and the call returns.
+ * dvfe_wait() completes the oldest step; dvfe_get_features / dvfe_insts_output then return ITS results.
+ * Arguments as dvfe_track_semantic_image + dvfe_insts_track_batch; the images, masks and ROI masks must stay valid until
+ * the matching dvfe_wait() (ROI masks are copied to a staging buffer during the call when they fit it). */
+int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,
+                             size_t stream_stride, int pitch, const int* exist_inst, const dvfe_inst_in* boxes,
+                             const int* n_boxes, const double* time0);
+
 /* ---- frame ingest inside the tracker (SURVEY.md §8f N1 + N2) ---------------------------------------------
  * dvfe_set_input: the images handed to dvfe_track_image[_async|_device*] / dvfe_track_semantic_image are `channels`
  * interleaved bytes per pixel: 1 = gray (default), 3 = BGR as in SemanticImage::color0/color1; pitch >= channels * width.

@@ -609,3 +609,50 @@ def test_color_ingest_semantic_path():
         assert trk.features(0).tobytes() == ref.features(0).tobytes()
         assert trk.insts_output(0).tobytes() == ref.insts_output(0).tobytes()
     ref.close(); trk.close()
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_dynamic_pipelined_equals_synchronous(groups):
+    """dvfe_track_dynamic_async + dvfe_wait (two frames in flight) == dvfe_track_semantic_image + dvfe_insts_track_batch,
+    record for record, including a stream that loses its detections for one frame and a frame without any"""
+    name, B, T = "c3_zed_dynamic", 3, 7
+    streams = [synth.make_stream(name, s) for s in range(B)]
+    sync = BatchTracker(cfg_of(name, n_streams=B, max_instances=8))
+    pipe = BatchTracker(cfg_of(name, n_streams=B, max_instances=8, n_groups=groups))
+    want, got = [], []
+    for k in range(T):
+        frs = [s.frame(k) for s in streams]
+        if k == 2:
+            frs[1].boxes, frs[1].exist_inst = [], False
+            frs[1].inv_merge_mask = np.full_like(frs[1].inv_merge_mask, 255)
+        if k == 4:
+            for f in frs:
+                f.boxes, f.exist_inst = [], False
+                f.inv_merge_mask = np.full_like(f.inv_merge_mask, 255)
+        L = np.stack([f.gray0 for f in frs]); R = np.stack([f.gray1 for f in frs]); M = np.stack([f.inv_merge_mask for f in frs])
+        ex = [int(f.exist_inst) for f in frs]; tm = [f.time0 for f in frs]
+        sync.track_semantic_image(L, R, M, ex, tm)
+        sync.insts_track_batch([f.boxes for f in frs], tm)
+        want.append([(sync.features(s).tobytes(), sync.insts_output(s).tobytes()) for s in range(B)])
+        pipe.track_dynamic_async(L, R, M, ex, [f.boxes for f in frs], tm)
+        if k > 0:
+            pipe.wait()
+            got.append([(pipe.features(s).tobytes(), pipe.insts_output(s).tobytes()) for s in range(B)])
+    pipe.wait()
+    got.append([(pipe.features(s).tobytes(), pipe.insts_output(s).tobytes()) for s in range(B)])
+    assert len(got) == T
+    for k in range(T):
+        for s in range(B):
+            assert got[k][s][0] == want[k][s][0], ("features", k, s)
+            assert got[k][s][1] == want[k][s][1], ("instances", k, s)
+    assert len(want[3][0][1]) > 0 and len(want[4][0][1]) == 0
+    # a synchronous call after pipelined ones continues the same state
+    frs = [s.frame(T) for s in streams]
+    L = np.stack([f.gray0 for f in frs]); R = np.stack([f.gray1 for f in frs]); M = np.stack([f.inv_merge_mask for f in frs])
+    for t in (sync, pipe):
+        t.track_semantic_image(L, R, M, [int(f.exist_inst) for f in frs], [f.time0 for f in frs])
+        t.insts_track_batch([f.boxes for f in frs], [f.time0 for f in frs])
+    for s in range(B):
+        assert sync.features(s).tobytes() == pipe.features(s).tobytes()
+        assert sync.insts_output(s).tobytes() == pipe.insts_output(s).tobytes()
+    sync.close(); pipe.close()
