@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU")
     ap.add_argument("--workload", default=WORKLOAD, choices=["c1_euroc_mono", "c2_kitti_stereo", "c3_zed_dynamic", "c4_hd_stereo", "c5_zed_streams"],
                     help="BASELINE.json config shape of every stream (default: configs[4], the metric's configuration)")
+    ap.add_argument("--max-cnt", type=int, default=0, help="override the workload's max_cnt (points per frame)")
+    ap.add_argument("--min-dist", type=int, default=0, help="override the workload's min_dist")
     ap.add_argument("--groups", type=int, default=4, help="stream groups per tracker (dvfe_config::n_groups)")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -319,6 +321,11 @@ def run_dvfe(args):
         except Exception:
             pass
         achieved = ab / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        sm_l1 = {}
+        try:      # sm__throughput / l1tex__throughput % of peak of the same kernel, from the committed ncu --set full capture
+            sm_l1 = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("_sm_l1", {}).get(dom, {})
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -336,7 +343,10 @@ def run_dvfe(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom],
-                         "measured_on": "same steps, one stream group (launch = all streams), kernels serialised"},
+                         "measured_on": "same steps, one stream group (launch = all streams), kernels serialised",
+                         "ncu_sm_throughput_pct": sm_l1.get("sm_pct"), "ncu_l1tex_throughput_pct": sm_l1.get("l1tex_pct"),
+                         "note": "issue/latency-bound integer kernel (see profiles/ncu_r1_v6_summary.md); traffic above the "
+                                 "algorithmic bytes is the forward-template cache the stereo call writes for the next temporal call"},
         }
         out["config"]["host_placement"] = numa_note
         if world == 1 and not args.no_cpu_baseline:
@@ -500,6 +510,7 @@ def single_stream_latency(device: int, n_frames: int = 40) -> dict:
 def _ref_worker(wid: int, T: int, conn, workload: str):
     import cv2
     cv2.setNumThreads(1)
+    apply_overrides()
     st, fe = _oracle_frontend(wid, workload)
     frames = [st.frame(k) for k in range(T)]
     from dynamic_vins_b200.synth import pingpong_positions
@@ -571,9 +582,29 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def apply_overrides():
+    """--max-cnt / --min-dist travel to spawned reference workers through the environment"""
+    from dynamic_vins_b200 import synth
+    wl = os.environ.get("DVFE_BENCH_WORKLOAD")
+    mc, md = int(os.environ.get("DVFE_BENCH_MAX_CNT", "0")), int(os.environ.get("DVFE_BENCH_MIN_DIST", "0"))
+    if wl and (mc or md):
+        c = dict(synth.CONFIGS[wl])
+        if mc:
+            c["max_cnt"] = mc
+        if md:
+            c["min_dist"] = md
+        synth.CONFIGS[wl] = c
+
+
 if __name__ == "__main__":
     a = parse_args()
     WORKLOAD = a.workload
+    os.environ["DVFE_BENCH_WORKLOAD"] = WORKLOAD
+    if a.max_cnt:
+        os.environ["DVFE_BENCH_MAX_CNT"] = str(a.max_cnt)
+    if a.min_dist:
+        os.environ["DVFE_BENCH_MIN_DIST"] = str(a.min_dist)
+    apply_overrides()
     if a.impl == "reference":
         run_reference(a)
     elif WORKLOAD == "c3_zed_dynamic":
