@@ -58,15 +58,44 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  In-process NVML polling
+    every 5 ms (an `nvidia-smi -lms` child needs > 100 ms to start on an 8-GPU box and misses short timed regions);
+    falls back to the nvidia-smi child when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nv, self.h, self.stop_flag, self.sm, self.mx, self.bits = None, None, False, [], None, 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -81,6 +110,12 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self) -> dict:
+        if self.nv is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -102,7 +137,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def bind_to_gpu_cpus(gpu_index: int) -> str:
