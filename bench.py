@@ -506,19 +506,22 @@ def parity_sample(device: int, n_frames: int = 6) -> dict:
     trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"],
                                    stereo=c["stereo"], device=device))
     worst, ids_equal, n_obs = 0.0, True, 0
+    n_want, n_common = 0, 0
     for k in range(n_frames):
         fr = st.frame(k)
         want = fe.step(fr)["features"]
         trk.track_image(fr.gray0, fr.gray1, fr.time0)
         got = obs_to_map(trk.features(0))
         ids_equal &= sorted(got) == sorted(want) and all([c0 for c0, _ in got[i]] == [c0 for c0, _ in want[i]] for i in want)
+        n_want += len(want); n_common += len(set(got) & set(want))
         for i in set(got) & set(want):
             for (_, a), (_, b) in zip(got[i], want[i]):
                 worst = max(worst, float(np.abs(a[3:5] - b[3:5]).max()))
                 n_obs += 1
     trk.close()
     return {"max_px_err_vs_ref_cpu": worst, "ids_and_stereo_bits_equal": bool(ids_equal), "frames": n_frames,
-            "observations": n_obs, "tolerance_px": 0.02}
+            "observations": n_obs, "tolerance_px": 0.02,
+            "corner_set_agreement": (n_common / n_want) if n_want else None, "corner_set_bar": 0.99}
 
 
 def single_stream_latency(device: int, n_frames: int = 40) -> dict:

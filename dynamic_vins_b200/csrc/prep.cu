@@ -227,20 +227,37 @@ extern "C" int dvfe_op_remap(const uint8_t* src, int w, int h, int channels, int
     return DVFE_OK;
 }
 
+namespace {
+struct PrepBuf {                 // device buffer freed on every exit path
+    void* p = nullptr;
+    ~PrepBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        DVFE_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        return DVFE_OK;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+int prep_device() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        dvfe_set_error("no CUDA device available: libdvfe has no CPU fallback");
+        return DVFE_ERR_NO_DEVICE;
+    }
+    return DVFE_OK;
+}
+}  // namespace
+
 extern "C" int dvfe_op_bgr_to_gray(const uint8_t* bgr, int w, int h, int pitch, uint8_t* gray_out) {
     if (!bgr || !gray_out || w < 1 || h < 1 || pitch < 3 * w) { dvfe_set_error("op_bgr_to_gray: bad argument"); return DVFE_ERR_INVALID; }
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { dvfe_set_error("no CUDA device available: libdvfe has no CPU fallback"); return DVFE_ERR_NO_DEVICE; }
-    uint8_t *d_bgr = nullptr, *d_gray = nullptr;
-    DVFE_CUDA(cudaMalloc((void**)&d_bgr, (size_t)3 * w * h));
-    DVFE_CUDA(cudaMalloc((void**)&d_gray, (size_t)w * h));
-    DVFE_CUDA(cudaMemcpy2D(d_bgr, (size_t)3 * w, bgr, pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice));
+    if (int rc = prep_device()) return rc;
+    PrepBuf d_bgr, d_gray;
+    if (int rc = d_bgr.alloc((size_t)3 * w * h)) return rc;
+    if (int rc = d_gray.alloc((size_t)w * h)) return rc;
+    DVFE_CUDA(cudaMemcpy2D(d_bgr.p, (size_t)3 * w, bgr, pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice));
     dim3 blk(32, 8), grid(((w + 3) / 4 + 31) / 32, (h + 7) / 8);
-    DVFE_LAUNCH(k_bgr_to_gray, grid, blk, 0, 0, d_bgr, 3 * w, d_gray, w, w, h);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(gray_out, d_gray, (size_t)w * h, cudaMemcpyDeviceToHost);
-    cudaFree(d_bgr); cudaFree(d_gray);
-    if (e != cudaSuccess) { dvfe_set_error("op_bgr_to_gray: %s", cudaGetErrorString(e)); return DVFE_ERR_CUDA; }
+    DVFE_LAUNCH(k_bgr_to_gray, grid, blk, 0, 0, d_bgr.as<uint8_t>(), 3 * w, d_gray.as<uint8_t>(), w, w, h);
+    DVFE_CUDA(cudaDeviceSynchronize());
+    DVFE_CUDA(cudaMemcpy(gray_out, d_gray.p, (size_t)w * h, cudaMemcpyDeviceToHost));
     return DVFE_OK;
 }
 
@@ -249,20 +266,17 @@ extern "C" int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int
         dvfe_set_error("op_merge_masks: bad argument");
         return DVFE_ERR_INVALID;
     }
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { dvfe_set_error("no CUDA device available: libdvfe has no CPU fallback"); return DVFE_ERR_NO_DEVICE; }
+    if (int rc = prep_device()) return rc;
     const size_t P = (size_t)w * h;
-    uint8_t *d_m = nullptr, *d_merge = nullptr, *d_inv = nullptr;
-    DVFE_CUDA(cudaMalloc((void**)&d_m, P * (n_masks > 0 ? n_masks : 1)));
-    DVFE_CUDA(cudaMalloc((void**)&d_merge, P));
-    DVFE_CUDA(cudaMalloc((void**)&d_inv, P));
-    if (n_masks > 0) DVFE_CUDA(cudaMemcpy(d_m, masks, P * n_masks, cudaMemcpyHostToDevice));
+    PrepBuf d_m, d_merge, d_inv;
+    if (int rc = d_m.alloc(P * (n_masks > 0 ? n_masks : 1))) return rc;
+    if (int rc = d_merge.alloc(P)) return rc;
+    if (int rc = d_inv.alloc(P)) return rc;
+    if (n_masks > 0) DVFE_CUDA(cudaMemcpy(d_m.p, masks, P * n_masks, cudaMemcpyHostToDevice));
     dim3 blk(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    DVFE_LAUNCH(k_merge_masks, grid, blk, 0, 0, d_m, n_masks, P, w, d_merge, d_inv, w, w, h);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(merge_out, d_merge, P, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(inv_out, d_inv, P, cudaMemcpyDeviceToHost);
-    cudaFree(d_m); cudaFree(d_merge); cudaFree(d_inv);
-    if (e != cudaSuccess) { dvfe_set_error("op_merge_masks: %s", cudaGetErrorString(e)); return DVFE_ERR_CUDA; }
+    DVFE_LAUNCH(k_merge_masks, grid, blk, 0, 0, d_m.as<uint8_t>(), n_masks, P, w, d_merge.as<uint8_t>(), d_inv.as<uint8_t>(), w, w, h);
+    DVFE_CUDA(cudaDeviceSynchronize());
+    DVFE_CUDA(cudaMemcpy(merge_out, d_merge.p, P, cudaMemcpyDeviceToHost));
+    DVFE_CUDA(cudaMemcpy(inv_out, d_inv.p, P, cudaMemcpyDeviceToHost));
     return DVFE_OK;
 }

@@ -13,7 +13,7 @@
 #include "tracker.h"
 
 unsigned long long g_dvfe_launches = 0;
-static char g_err[512] = "";
+static thread_local char g_err[512] = "";       // per calling thread: trackers on different host threads do not clobber each other
 
 void dvfe_set_error(const char* fmt, ...) {
     va_list ap;
