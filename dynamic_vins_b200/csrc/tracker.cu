@@ -3,6 +3,7 @@
 // 757-837) and the seam-level operators.  Host code only orchestrates launches; no pixel or point
 // arithmetic happens on the CPU and there is no fallback when no CUDA device is present.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -206,6 +207,7 @@ int dvfe_tracker::init() {
     // pitched host->device DMA straight into the padded level 0 runs at full PCIe rate only for rows that are a
     // multiple of 64 bytes; other widths go through a dense staging buffer (one linear copy) and the copy kernel
     staged_upload = (W % 64) != 0;
+    if (const char* e = getenv("DVFE_STAGED_UPLOAD")) staged_upload = atoi(e) != 0;      // experiment / override
     if (staged_upload)
         for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
