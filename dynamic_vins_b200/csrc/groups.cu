@@ -26,7 +26,11 @@ int grp_create(const dvfe_config* cfg, dvfe_tracker** out) {
         c.n_streams = cfg->n_streams / G + (g < cfg->n_streams % G ? 1 : 0);
         dvfe_tracker* leaf = nullptr;
         const int rc = dvfe_create(&c, &leaf);
-        if (rc != DVFE_OK) { dvfe_destroy(t); return rc; }
+        if (rc != DVFE_OK) {                       // keep the leaf's error message; release what was built
+            for (dvfe_tracker* l : t->groups) dvfe_destroy(l);
+            delete t;
+            return rc;
+        }
         t->groups.push_back(leaf);
         t->group_first.push_back(t->group_first.back() + c.n_streams);
     }

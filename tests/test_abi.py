@@ -100,3 +100,30 @@ def test_no_cpu_fallback():
     with pytest.raises(dv.DvfeError) as e:
         dv.BatchTracker(dv.make_config(640, 480, 100, 30, dv.synth.KITTI_CAM))
     assert e.value.code == -5
+
+
+def test_new_entry_points_reject_bad_arguments_and_have_no_fallback():
+    """frame-ingest / remap / pipelined-dynamic entry points: argument errors are reported before any device work, a valid
+    call without a device fails with DVFE_ERR_NO_DEVICE (no CPU path), a grouped tracker cannot be created either"""
+    import ctypes as C
+    L = dv._lib.lib()
+    assert L.dvfe_set_input(None, 3) == -1
+    assert L.dvfe_set_undistort_maps(None, 0, None, None) == -1
+    assert L.dvfe_track_dynamic_async(None, None, None, None, 0, 0, None, None, None, None) == -1
+    src = np.zeros((8, 8, 3), np.uint8); dst = np.zeros((8, 8), np.uint8)
+    assert L.dvfe_op_remap(src.ctypes.data, 8, 8, 2, 24, None, None, 1, dst.ctypes.data) == -1        # 2 channels
+    assert L.dvfe_op_remap(src.ctypes.data, 8, 8, 3, 8, None, None, 1, dst.ctypes.data) == -1         # pitch < 3 * w
+    m1 = np.zeros((8, 8, 2), np.int16)
+    assert L.dvfe_op_remap(src.ctypes.data, 8, 8, 3, 24, m1.ctypes.data, None, 1, dst.ctypes.data) == -1   # map2 missing
+    if not conftest_has_gpu():
+        with pytest.raises(dv.DvfeError) as e:
+            dv.ops.remap(src, None, None, to_gray=True)
+        assert e.value.code == -5
+        with pytest.raises(dv.DvfeError) as e:
+            dv.BatchTracker(dv.make_config(640, 480, 100, 30, dv.synth.KITTI_CAM, n_streams=4, n_groups=2))
+        assert e.value.code == -5
+
+
+def conftest_has_gpu():
+    import conftest
+    return conftest._has_gpu()
