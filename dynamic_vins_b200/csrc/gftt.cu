@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 #ifndef RS_ROWS
 #define RS_ROWS 48
 #endif
+#define RS_ROWS_SMALL 16
 #define RS_WARPS 8
 
 #ifndef RS_OPT_I2F
@@ -258,11 +259,11 @@ __device__ __forceinline__ void resp_step(const RespCtx& C, RespState& S, int y,
 }
 
 template <bool WRITE_EIG, bool EMIT>
-__device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int pitch, int w, int h, int xb, int y0,
+__device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int pitch, int w, int h, int xb, int y0, int rows,
                                            float* __restrict__ eig, const uint8_t* __restrict__ mask, int mask_pitch,
                                            int* __restrict__ counters, unsigned long long* __restrict__ cand, int cand_cap) {
     RespCtx C;
-    C.img = img; C.pitch = pitch; C.w = w; C.h = h; C.xb = xb; C.y0 = y0; C.y1 = min(y0 + RS_ROWS, h);
+    C.img = img; C.pitch = pitch; C.w = w; C.h = h; C.xb = xb; C.y0 = y0; C.y1 = min(y0 + rows, h);
     C.lane = threadIdx.x & 31;
     C.x = xb + C.lane - 2;
     C.col = img + reflect101(C.x, w);
@@ -302,19 +303,21 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
     }
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32, 4) k_gftt_response(const GfttJob* __restrict__ jobs) {
+// rows = strip height: RS_ROWS when the launch has enough warps to fill the GPU, RS_ROWS_SMALL for small batches (a single
+// camera), where three times as many, shorter strips cut the latency of the serial march
+__global__ void __launch_bounds__(RS_WARPS * 32, 4) k_gftt_response(const GfttJob* __restrict__ jobs, int rows) {
     const GfttJob& J = jobs[blockIdx.z];
     if (!gftt_job_active(J) || J.eig_in != nullptr) return;
-    const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
+    const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * rows;
     if (xb >= J.w || y0 >= J.h) return;
-    resp_strip<false, true>(J.img, J.img_pitch, J.w, J.h, xb, y0, nullptr, J.mask, J.mask_pitch, J.counters, J.cand,
+    resp_strip<false, true>(J.img, J.img_pitch, J.w, J.h, xb, y0, rows, nullptr, J.mask, J.mask_pitch, J.counters, J.cand,
                             J.cand_cap);
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32, 4) k_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig) {
     const int xb = (blockIdx.x * RS_WARPS + (threadIdx.x >> 5)) * RS_COLS, y0 = blockIdx.y * RS_ROWS;
     if (xb >= w || y0 >= h) return;
-    resp_strip<true, false>(img, pitch, w, h, xb, y0, eig, nullptr, 0, nullptr, nullptr, 0);
+    resp_strip<true, false>(img, pitch, w, h, xb, y0, RS_ROWS, eig, nullptr, 0, nullptr, nullptr, 0);
 }
 
 // ---- externally supplied response map (seam op): masked max, then the same pre-candidates ---------------
@@ -727,9 +730,11 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
         DVFE_LAUNCH(k_gftt_max_ext, grid, blk, 0, st, d_jobs);
         DVFE_LAUNCH(k_gftt_candidates_ext, grid, blk, 0, st, d_jobs);
     } else {
-        dim3 blk(RS_WARPS * 32),
-            grid((max_w + RS_COLS * RS_WARPS - 1) / (RS_COLS * RS_WARPS), (max_h + RS_ROWS - 1) / RS_ROWS, n_jobs);
-        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs);
+        const int gx = (max_w + RS_COLS * RS_WARPS - 1) / (RS_COLS * RS_WARPS);
+        const long warps = (long)gx * RS_WARPS * ((max_h + RS_ROWS - 1) / RS_ROWS) * n_jobs;
+        const int rows = warps >= 148L * 16 ? RS_ROWS : RS_ROWS_SMALL;       // fewer than 16 warps per SM: shorter strips
+        dim3 blk(RS_WARPS * 32), grid(gx, (max_h + rows - 1) / rows, n_jobs);
+        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs, rows);
     }
     GFTT_MARK();
     if (after_response) cudaEventRecord(after_response, st);

@@ -22,7 +22,9 @@
 //   * the 2x2 sums are reduced exactly with redux.sync on 16-bit halves.
 #include "kernels.cuh"
 
+#ifndef LK_WARPS
 #define LK_WARPS 4
+#endif
 #ifndef LK_MIN_BLOCKS
 #define LK_MIN_BLOCKS 6          // resident blocks per SM the register allocation targets
 #endif
