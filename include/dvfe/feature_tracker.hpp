@@ -177,4 +177,92 @@ private:
     FeatureTracker& t_;
 };
 
+// Many cameras on one GPU: B independent FeatureTracker states advanced together, pipelined.  Not in the reference (one
+// tracker configuration per process there); this is the host-side shape of the B200 deployment: one object per
+// GPU, `TrackImageAsync(frame k+1)` then `Wait()` -> results of frame k, so uploads overlap the kernels.  The images of
+// stream s start at `base + s * stream_stride`.
+class BatchFeatureTracker {
+public:
+    BatchFeatureTracker(const std::string& config_path, int n_streams, int n_groups = 4, int max_instances = 0) {
+        if (dvfe_config_from_yaml(config_path.c_str(), &cfg_) != DVFE_OK) throw std::runtime_error(dvfe_last_error(nullptr));
+        cfg_.n_streams = n_streams; cfg_.n_groups = n_groups; cfg_.max_instances = max_instances;
+        if (dvfe_create(&cfg_, &h_) != DVFE_OK) throw std::runtime_error(dvfe_last_error(nullptr));
+    }
+    explicit BatchFeatureTracker(const dvfe_config& cfg) : cfg_(cfg) {
+        if (dvfe_create(&cfg_, &h_) != DVFE_OK) throw std::runtime_error(dvfe_last_error(nullptr));
+    }
+    ~BatchFeatureTracker() { dvfe_destroy(h_); }
+    BatchFeatureTracker(const BatchFeatureTracker&) = delete;
+    BatchFeatureTracker& operator=(const BatchFeatureTracker&) = delete;
+
+    int streams() const { return cfg_.n_streams; }
+    const dvfe_config& config() const { return cfg_; }
+    dvfe_tracker* handle() { return h_; }
+
+    // TrackImage of all cameras, enqueued; `time0` has one entry per stream; the images stay valid until the matching Wait()
+    void TrackImageAsync(const uint8_t* left, const uint8_t* right, size_t stream_stride, int step, const std::vector<double>& time0) {
+        check(time0);
+        if (dvfe_track_image_async(h_, left, right, stream_stride, step, time0.data()) != DVFE_OK)
+            throw std::runtime_error(dvfe_last_error(h_));
+    }
+    // TrackSemanticImage + InstsTrack of all cameras, enqueued (dynamic mode; FeatureTrack() in system/main.cpp:247-254)
+    void TrackDynamicAsync(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask, size_t stream_stride, int step,
+                           const std::vector<int>& exist_inst, const std::vector<std::vector<Box2D>>& boxes2d,
+                           const std::vector<double>& time0) {
+        check(time0);
+        if ((int)exist_inst.size() != cfg_.n_streams || (int)boxes2d.size() != cfg_.n_streams)
+            throw std::runtime_error("BatchFeatureTracker: one exist_inst / box list per stream expected");
+        std::vector<dvfe_inst_in> in;
+        std::vector<int> n(boxes2d.size());
+        for (size_t s = 0; s < boxes2d.size(); s++) {
+            n[s] = (int)boxes2d[s].size();
+            for (const Box2D& b : boxes2d[s]) in.push_back({b.track_id, b.x, b.y, b.w, b.h, b.mask, b.mask_step});
+        }
+        if (dvfe_track_dynamic_async(h_, left, right, inv_merge_mask, stream_stride, step, exist_inst.data(),
+                                     in.empty() ? nullptr : in.data(), n.data(), time0.data()) != DVFE_OK)
+            throw std::runtime_error(dvfe_last_error(h_));
+    }
+    // the oldest enqueued frame is finished: Features() / InstsOutput() return its results
+    void Wait() {
+        if (dvfe_wait(h_) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
+    }
+    // SetOutputFeats() of one camera (front_end/background_tracker.cpp:340-392)
+    FeatureBackground Features(int stream) {
+        std::vector<dvfe_obs> rec(2 * (size_t)cfg_.max_cnt);
+        int n = 0;
+        if (dvfe_get_features(h_, stream, rec.data(), (int)rec.size(), &n) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
+        FeatureBackground fb;
+        for (int i = 0; i < n; i++) {
+            Vec7d v;
+            for (int k = 0; k < 7; k++) v[k] = rec[i].v[k];
+            fb.points[rec[i].id].emplace_back(rec[i].cam, v);
+        }
+        return fb;
+    }
+    // InstsFeatManager::Output() of one camera (front_end/dynamic_tracker.cpp:521-577)
+    std::map<unsigned int, FeatureInstance> InstsOutput(int stream) {
+        std::vector<dvfe_inst_obs> rec((size_t)(cfg_.max_instances > 0 ? cfg_.max_instances : 1) *
+                                       (size_t)(cfg_.max_dynamic_cnt > 0 ? cfg_.max_dynamic_cnt : 1));
+        int n = 0;
+        if (dvfe_insts_output(h_, stream, rec.data(), (int)rec.size(), &n) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
+        std::map<unsigned int, FeatureInstance> out;
+        for (int i = 0; i < n; i++) {
+            FeaturePoint f;
+            for (int k = 0; k < 3; k++) { f.point[k] = rec[i].point[k]; f.point_right[k] = rec[i].point_right[k]; }
+            for (int k = 0; k < 2; k++) { f.vel[k] = rec[i].vel[k]; f.vel_right[k] = rec[i].vel_right[k]; }
+            f.is_stereo = rec[i].is_stereo != 0;
+            f.disp = rec[i].disp;
+            out[rec[i].inst_id].features[rec[i].id] = f;
+        }
+        return out;
+    }
+
+private:
+    void check(const std::vector<double>& time0) const {
+        if ((int)time0.size() != cfg_.n_streams) throw std::runtime_error("BatchFeatureTracker: one time0 per stream expected");
+    }
+    dvfe_config cfg_{};
+    dvfe_tracker* h_ = nullptr;
+};
+
 }  // namespace dynamic_vins

@@ -342,6 +342,54 @@ def test_cpp_reference_shaped_api(tmp_path):
             assert len(vals) == len(ref) and np.abs(vals[3:5] - ref[3:5]).max() <= POS_TOL
 
 
+def test_cpp_batch_tracker_pipelined(tmp_path):
+    """dynamic_vins::BatchFeatureTracker (C++ host side for many cameras: TrackImageAsync / Wait / Features, 2 stream groups)
+    gives, value for value, the records of the python-driven tracker on the same frames"""
+    import subprocess
+    from conftest import ROOT
+    name, B, T = "c2_kitti_stereo", 3, 5
+    c = synth.CONFIGS[name]
+    for i, cam in enumerate((c["cam0"], c["cam1"])):
+        (tmp_path / f"cam{i}.yaml").write_text(
+            "%YAML:1.0\n---\nmodel_type: PINHOLE\ncamera_name: camera\n"
+            f"image_width: {c['width']}\nimage_height: {c['height']}\ndistortion_parameters:\n"
+            f"   k1: {cam['k1']!r}\n   k2: {cam['k2']!r}\n   p1: {cam['p1']!r}\n   p2: {cam['p2']!r}\n"
+            f"projection_parameters:\n   fx: {cam['fx']!r}\n   fy: {cam['fy']!r}\n   cx: {cam['cx']!r}\n   cy: {cam['cy']!r}\n")
+    (tmp_path / "cfg.yaml").write_text(
+        "%YAML:1.0\n\nnum_of_cam: 2\nslam_type: \"raw\"\n"
+        f"image_width: {c['width']}\nimage_height: {c['height']}\ncam0_calib: \"cam0.yaml\"\ncam1_calib: \"cam1.yaml\"\n"
+        f"max_cnt: {c['max_cnt']}\nmin_dist: {c['min_dist']}\nF_threshold: 1.0\nshow_track: 0\nflow_back: 1\n"
+        "min_dynamic_dist: 5\nmax_dynamic_cnt: 50\nuse_mask_morphology: 0\nmask_morphology_size: 5\n")
+    exe = str(tmp_path / "test_feature_tracker")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_feature_tracker.cpp"),
+                           "-L" + os.path.join(ROOT, "dynamic_vins_b200"), "-ldvfe",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe])
+    streams = [synth.make_stream(name, 20 + s) for s in range(B)]
+    ref = BatchTracker(cfg_of(name, n_streams=B))
+    want = []
+    with open(tmp_path / "frames.bin", "wb") as f:
+        for k in range(T):
+            frs = [s.frame(k) for s in streams]
+            tm = np.array([fr.time0 + 0.002 * i for i, fr in enumerate(frs)], np.float64)
+            L = np.stack([fr.gray0 for fr in frs]); R = np.stack([fr.gray1 for fr in frs])
+            f.write(tm.tobytes()); f.write(L.tobytes()); f.write(R.tobytes())
+            ref.track_image(L, R, tm)
+            want.append([obs_to_map(ref.features(s)) for s in range(B)])
+    ref.close()
+    subprocess.check_call([exe, "batch", str(tmp_path / "cfg.yaml"), str(tmp_path / "frames.bin"), str(T), str(B),
+                           str(tmp_path / "out"), "2"])
+    for k in range(T):
+        for s in range(B):
+            lines = open(tmp_path / f"out_s{s}_{k}_point.txt").read().strip().split("\n")
+            assert len(lines) == len(want[k][s]) > 50
+            for ln, (fid, obs) in zip(lines, want[k][s].items()):
+                tok = ln.split()
+                assert int(tok[1]) == fid and int(tok[0]) == (1 if len(obs) == 2 else 0)
+                vals = np.array([float(x) for x in tok[2:]])
+                assert np.array_equal(vals, np.concatenate([o[1] for o in obs]))
+
+
 def test_pipelined_async_equals_sync():
     """dvfe_track_image_async / dvfe_wait (two steps in flight, upload overlapping compute) gives the same records
     as the synchronous call, step by step"""
