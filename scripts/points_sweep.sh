@@ -3,7 +3,7 @@
 # reference arm (all host cores), 64 streams
 for cfg in "150 30" "400 25" "1000 10"; do
   set -- $cfg
-  python bench.py --max-cnt $1 --min-dist $2 --steps 100 --no-cpu-baseline > /tmp/a.json 2>/dev/null
+  python bench.py --max-cnt $1 --min-dist $2 --steps 100 --no-cpu-baseline --e2e-groups $([ $1 -ge 1000 ] && echo 4 || echo 1) > /tmp/a.json 2>/dev/null
   python bench.py --impl reference --max-cnt $1 --min-dist $2 --steps 8 --warmup 3 > /tmp/r.json 2>/dev/null
   python - $1 $2 <<PY
 import json, sys
