@@ -383,6 +383,9 @@ def run_dvfe(args):
                          "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom],
                          "measured_on": "same steps, one stream group (launch = all streams), kernels serialised",
                          "ncu_sm_throughput_pct": sm_l1.get("sm_pct"), "ncu_l1tex_throughput_pct": sm_l1.get("l1tex_pct"),
+                         # warp instructions per launch (ncu, static) / live launch time, against 4 issue slots x 148 SMs x SM clock
+                         "issue_slot_frac": (sm_l1["warp_inst"] / (stage_ms[dom] * 1e-3) / (4 * 148 * (clock_info.get("sm_mhz") or 1965.0) * 1e6)
+                                             if sm_l1.get("warp_inst") and stage_ms[dom] > 0 else None),
                          "note": "issue/latency-bound integer kernel (see profiles/ncu_r1_v6_summary.md); traffic above the "
                                  "algorithmic bytes is the forward-template cache the stereo call writes for the next temporal call"},
         }
