@@ -59,6 +59,23 @@ def parse_args():
     return ap.parse_args()
 
 
+def nvml_handle(cuda_index: int):
+    """NVML handle of the CUDA device `cuda_index` of this process: by UUID / PCI bus id, because NVML enumerates the physical
+    GPUs while CUDA_VISIBLE_DEVICES may renumber (or hide) them; plain index as the last resort"""
+    import pynvml
+    pynvml.nvmlInit()
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(cuda_index)
+        try:
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(pr.uuid)).encode())
+        except Exception:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+    except Exception:
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  In-process NVML polling
     every 5 ms (an `nvidia-smi -lms` child needs > 100 ms to start on an 8-GPU box and misses short timed regions);
@@ -73,10 +90,8 @@ class ClockSampler:
         self.idx, self.proc, self.lines = gpu_index, None, []
         self.nv, self.h, self.stop_flag, self.sm, self.mx, self.bits = None, None, False, [], None, 0
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv, self.h = nvml_handle(gpu_index)
+            self.mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
         except Exception:
             self.nv = None
 
@@ -146,9 +161,7 @@ def bind_to_gpu_cpus(gpu_index: int) -> str:
     """Best effort: run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers the
     e2e leg uploads from live on that GPU's NUMA node (matters when 8 ranks upload at once)."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml, h = nvml_handle(gpu_index)
         n_cpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
         cpus = {64 * i + b for i, wv in enumerate(words) for b in range(64) if (int(wv) >> b) & 1}
