@@ -72,7 +72,7 @@ SYMBOLS = [
     "dvfe_insts_track", "dvfe_insts_track_batch", "dvfe_get_features", "dvfe_insts_output", "dvfe_get_state", "dvfe_set_state",
     "dvfe_op_build_pyramid", "dvfe_op_lk", "dvfe_op_min_eigen_val", "dvfe_op_good_features",
     "dvfe_op_disc_mask", "dvfe_op_erode_rect", "dvfe_op_lift_projective", "dvfe_op_bgr_to_gray", "dvfe_op_merge_masks",
-    "dvfe_op_remap", "dvfe_set_input", "dvfe_set_undistort_maps", "dvfe_track_dynamic_async",
+    "dvfe_op_remap", "dvfe_set_input", "dvfe_set_undistort_maps", "dvfe_track_dynamic_async", "dvfe_op_punch_out",
 ]
 
 _lib = None
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
         L.dvfe_op_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.dvfe_track_dynamic_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dvfe_op_punch_out.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.dvfe_set_input.argtypes = [C.c_void_p, C.c_int]
         L.dvfe_set_undistort_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.dvfe_op_merge_masks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

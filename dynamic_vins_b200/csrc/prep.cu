@@ -280,3 +280,42 @@ extern "C" int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int
     DVFE_CUDA(cudaMemcpy(inv_out, d_inv.p, P, cudaMemcpyDeviceToHost));
     return DVFE_OK;
 }
+
+// FeatureTrack(): "remove the masks of static objects" (system/main.cpp:219-242): for every pixel of a static instance's
+// ROI mask that is set, merge_mask = 0; afterwards inv_merge_mask = bitwise_not(merge_mask) (:238-240).
+__global__ void __launch_bounds__(256) k_punch_out(uint8_t* __restrict__ merge, uint8_t* __restrict__ inv, int pitch, int w, int h,
+                                                   const uint8_t* __restrict__ roi, int roi_pitch, int rx, int ry, int rw, int rh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= rw || y >= rh) return;
+    const int gx = rx + x, gy = ry + y;
+    if (gx < 0 || gx >= w || gy < 0 || gy >= h) return;
+    if (roi[(size_t)y * roi_pitch + x] != 0) {           // mask_cv.at<uchar>(row, col) >= 0.5
+        merge[(size_t)gy * pitch + gx] = 0;
+        inv[(size_t)gy * pitch + gx] = 255;
+    }
+}
+
+extern "C" int dvfe_op_punch_out(uint8_t* merge_mask, uint8_t* inv_merge_mask, int w, int h, const uint8_t* roi_mask,
+                                 int roi_pitch, int x, int y, int roi_w, int roi_h) {
+    if (!merge_mask || !inv_merge_mask || !roi_mask || w < 1 || h < 1 || roi_w < 1 || roi_h < 1 || roi_pitch < roi_w) {
+        dvfe_set_error("op_punch_out: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    if (int rc = prep_device()) return rc;
+    const size_t P = (size_t)w * h;
+    PrepBuf d_merge, d_inv, d_roi;
+    if (int rc = d_merge.alloc(P)) return rc;
+    if (int rc = d_inv.alloc(P)) return rc;
+    if (int rc = d_roi.alloc((size_t)roi_w * roi_h)) return rc;
+    DVFE_CUDA(cudaMemcpy(d_merge.p, merge_mask, P, cudaMemcpyHostToDevice));
+    DVFE_CUDA(cudaMemcpy(d_inv.p, inv_merge_mask, P, cudaMemcpyHostToDevice));
+    DVFE_CUDA(cudaMemcpy2D(d_roi.p, roi_w, roi_mask, roi_pitch, roi_w, roi_h, cudaMemcpyHostToDevice));
+    dim3 blk(32, 8), grid((roi_w + 31) / 32, (roi_h + 7) / 8);
+    DVFE_LAUNCH(k_punch_out, grid, blk, 0, 0, d_merge.as<uint8_t>(), d_inv.as<uint8_t>(), w, w, h, d_roi.as<uint8_t>(), roi_w, x, y,
+                roi_w, roi_h);
+    DVFE_CUDA(cudaDeviceSynchronize());
+    DVFE_CUDA(cudaMemcpy(merge_mask, d_merge.p, P, cudaMemcpyDeviceToHost));
+    DVFE_CUDA(cudaMemcpy(inv_merge_mask, d_inv.p, P, cudaMemcpyDeviceToHost));
+    return DVFE_OK;
+}

@@ -124,3 +124,15 @@ def merge_masks(masks):
     merge, inv = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
     L.check(L.lib().dvfe_op_merge_masks(L.ptr(m) if n else None, n, w, h, L.ptr(merge), L.ptr(inv)))
     return merge, inv
+
+
+def punch_out(merge_mask, inv_merge_mask, roi_mask, rect):
+    """remove a static instance from the merged masks (system/main.cpp:219-242); returns new (merge_mask, inv_merge_mask)"""
+    m = np.ascontiguousarray(merge_mask, np.uint8).copy()
+    iv = np.ascontiguousarray(inv_merge_mask, np.uint8).copy()
+    r = np.ascontiguousarray(roi_mask, np.uint8)
+    h, w = m.shape
+    x, y, rw, rh = rect
+    assert r.shape == (rh, rw)
+    L.check(L.lib().dvfe_op_punch_out(L.ptr(m), L.ptr(iv), w, h, L.ptr(r), r.strides[0], int(x), int(y), int(rw), int(rh)))
+    return m, iv

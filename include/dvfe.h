@@ -243,6 +243,11 @@ int dvfe_op_bgr_to_gray(const uint8_t* bgr, int w, int h, int pitch, uint8_t* gr
  * instance masks (non-zero = object) -> merge_mask (255 = object) and inv_merge_mask (bitwise_not). */
 int dvfe_op_merge_masks(const uint8_t* masks, int n_masks, int w, int h, uint8_t* merge_out, uint8_t* inv_out);
 
+/* FeatureTrack() static-instance punch-out (system/main.cpp:219-242): merge_mask = 0 (and inv_merge_mask = 255) wherever the
+ * ROI mask (roi_h x roi_w at rect.tl() = (x, y)) of a static instance is set.  Both full masks are dense w x h, in place. */
+int dvfe_op_punch_out(uint8_t* merge_mask, uint8_t* inv_merge_mask, int w, int h, const uint8_t* roi_mask, int roi_pitch,
+                      int x, int y, int roi_w, int roi_h);
+
 /* ImageProcessor::Run undistortion (image_process/image_process.cpp:109-122): cv::remap(src, dst, map1, map2, INTER_LINEAR)
  * with the fixed-point maps of cv::initUndistortRectifyMap(..., CV_16SC2, map1, map2) (utils/camera_model.cpp:483-497):
  * map1 = w*h (x, y) int16 pairs, map2 = w*h uint16 table indices; BORDER_CONSTANT 0; dst has the size of src.

@@ -47,3 +47,14 @@ def background_mask(merge_mask: np.ndarray, maps0=None) -> np.ndarray:
     if maps0 is not None:
         merge_mask = cv2.remap(merge_mask, maps0[0], maps0[1], cv2.INTER_LINEAR)
     return cv2.bitwise_not(merge_mask)
+
+
+def punch_out_static(merge_mask: np.ndarray, roi_mask: np.ndarray, rect) -> Tuple[np.ndarray, np.ndarray]:
+    """FeatureTrack(): remove the mask of a static instance (system/main.cpp:219-242), then inv = bitwise_not(merge) (:238-240)"""
+    m = merge_mask.copy()
+    x, y, w, h = rect
+    for row in range(roi_mask.shape[0]):
+        for col in range(roi_mask.shape[1]):
+            if roi_mask[row, col] >= 0.5:
+                m[row + y, col + x] = 0
+    return m, cv2.bitwise_not(m)

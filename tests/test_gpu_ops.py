@@ -261,3 +261,15 @@ def test_remap_golden_and_euroc_undistortion():
     m1, m2, _ = ip.undistort_maps(c["cam0"], c["width"], c["height"])
     gray = synth.make_stream("c1_euroc_mono", 0).frame(0).gray0
     assert crc(ops.remap(synth.colorize(gray), m1, m2, to_gray=True)) == int(g["euroc_undist_gray_crc"])
+
+
+def test_static_instance_punch_out():
+    """system/main.cpp:219-242: the ROI mask of a static instance is removed from merge_mask, inv_merge_mask follows"""
+    from oracle import image_process as ip
+    fr = synth.make_stream("c3_zed_dynamic", 1).frame(3)
+    merge, inv = fr.merge_mask.copy(), fr.inv_merge_mask.copy()
+    for b in fr.boxes[:3]:
+        want_m, want_i = ip.punch_out_static(merge, b["mask"], b["rect"])
+        merge, inv = ops.punch_out(merge, inv, b["mask"], b["rect"])
+        assert np.array_equal(merge, want_m) and np.array_equal(inv, want_i)
+    assert merge.sum() < fr.merge_mask.sum()
