@@ -3,12 +3,15 @@ import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 from dynamic_vins_b200 import BatchTracker, make_config, synth
-from oracle import image_process as ip
+import cv2
 
 c = synth.CONFIGS["c5_zed_streams"]
 W, H, S = c["width"], c["height"], int(sys.argv[1]) if len(sys.argv) > 1 else 64
 cam = dict(synth.EUROC_CAM0, cx=W / 2, cy=H / 2, fx=700.0, fy=700.0)
-m1, m2, _ = ip.undistort_maps(cam, W, H)
+K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], np.float64)
+D = np.array([cam["k1"], cam["k2"], cam["p1"], cam["p2"]], np.float64)
+newK, _ = cv2.getOptimalNewCameraMatrix(K, D, (W, H), 0, (W, H))          # utils/camera_model.cpp:479-501
+m1, m2 = cv2.initUndistortRectifyMap(K, D, None, newK, (W, H), cv2.CV_16SC2)
 st = synth.SynthStream(W, H, seed=5000, stereo=True)
 fr = [st.frame(k) for k in range(3)]
 col = [(torch.from_numpy(synth.colorize(f.gray0)).cuda(), torch.from_numpy(synth.colorize(f.gray1)).cuda()) for f in fr]

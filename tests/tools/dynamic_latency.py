@@ -1,7 +1,7 @@
 """Development aid: per-frame latency of the dynamic mode (TrackSemanticImage + InstsTrack + Output), B = 1,
 BASELINE.json config 3 (1280x720 stereo, 8 instances), against the cv2 oracle on the same frames."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from dynamic_vins_b200 import BatchTracker, make_config, synth
 from oracle import cv_front_end as cvfe

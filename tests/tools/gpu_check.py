@@ -1,6 +1,6 @@
 """Ad-hoc GPU diagnostics (development aid, not part of the test suite)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import cv2
 from dynamic_vins_b200 import ops, synth, make_config, BatchTracker, obs_to_map
