@@ -15,8 +15,8 @@
 //   * the 21x21 window is cut into 63 horizontal runs of 7 pixels; a lane owns runs `lane` and `lane+32`
 //     (14 pixels), whose template values (I, Ix, Iy) stay in registers for all iterations of a level;
 //   * per iteration a run needs 2 rows x 8 bytes of J: three aligned 32-bit loads per row, funnel-shifted to
-//     the window origin, instead of 4 byte loads per pixel; the four bilinear taps of a pixel are gathered
-//     with one PRMT and reduced with two dp2a (16-bit weights x 8-bit pixels);
+//     the window origin, instead of 4 byte loads per pixel; the bilinear sample of a pixel is two dp2a (16-bit
+//     weights x 8-bit pixels) on the row registers and their 1-byte-shifted copies (dp2a.lo / .hi select the byte pair);
 //   * the Scharr derivatives are computed on the fly from a 24x24 u8 window staged in shared memory (the
 //     reference materialises a 4 B/px derivative image per level and per call);
 //   * the 2x2 sums are reduced exactly with redux.sync on 16-bit halves.
@@ -86,6 +86,24 @@ __device__ __forceinline__ unsigned load4(const uint8_t* __restrict__ row, int x
         T[4] = __byte_perm(A_hi, B_hi, 0x5410);                              \
         T[5] = __byte_perm(A_hi, B_hi, 0x6521);                              \
         T[6] = __byte_perm(A_hi, B_hi, 0x7632);                              \
+    }
+
+// bilinear samples of the 7 pixels of a run from its two rows of 8 bytes (A: upper, B: lower) and MAC with the template:
+// pixel j needs the byte pairs (A[j], A[j+1]) and (B[j], B[j+1]); dp2a.lo / dp2a.hi pick the pair at bytes 0-1 / 2-3 of a
+// register, so the rows and their 1-byte-shifted copies serve all 7 pixels without assembling a tap word per pixel
+#define LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, IX, IY)                                                         \
+    {                                                                                                      \
+        const unsigned A_m1 = __funnelshift_r(A_lo, A_hi, 8), B_m1 = __funnelshift_r(B_lo, B_hi, 8);       \
+        const unsigned A_m2 = A_hi >> 8, B_m2 = B_hi >> 8;                                                 \
+        const int rnd = 1 << (W_BITS - 5 - 1);                                                             \
+        int v;                                                                                             \
+        v = dp2a_lo_su(W23, B_lo, dp2a_lo_su(W01, A_lo, rnd)) >> (W_BITS - 5); sb1 += v * IX[0]; sb2 += v * IY[0]; \
+        v = dp2a_lo_su(W23, B_m1, dp2a_lo_su(W01, A_m1, rnd)) >> (W_BITS - 5); sb1 += v * IX[1]; sb2 += v * IY[1]; \
+        v = dp2a_hi_su(W23, B_lo, dp2a_hi_su(W01, A_lo, rnd)) >> (W_BITS - 5); sb1 += v * IX[2]; sb2 += v * IY[2]; \
+        v = dp2a_hi_su(W23, B_m1, dp2a_hi_su(W01, A_m1, rnd)) >> (W_BITS - 5); sb1 += v * IX[3]; sb2 += v * IY[3]; \
+        v = dp2a_lo_su(W23, B_hi, dp2a_lo_su(W01, A_hi, rnd)) >> (W_BITS - 5); sb1 += v * IX[4]; sb2 += v * IY[4]; \
+        v = dp2a_lo_su(W23, B_m2, dp2a_lo_su(W01, A_m2, rnd)) >> (W_BITS - 5); sb1 += v * IX[5]; sb2 += v * IY[5]; \
+        v = dp2a_hi_su(W23, B_hi, dp2a_hi_su(W01, A_hi, rnd)) >> (W_BITS - 5); sb1 += v * IX[6]; sb2 += v * IY[6]; \
     }
 
 // d = sum_i a.u8[i] * b.s8[i] + c
@@ -286,28 +304,16 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 // sum (J - I) * Ix = sum J * Ix - sum I * Ix
                 int sb1 = -c1, sb2 = -c2;
                 {
-                    unsigned A_lo, A_hi, B_lo, B_hi, T[LK_RUN];
+                    unsigned A_lo, A_hi, B_lo, B_hi;
                     load8(Jw + roff0, inx + rx0, A_lo, A_hi);
                     load8(Jw + roff0 + L.pitch, inx + rx0, B_lo, B_hi);
-                    LK_TAPS(A_lo, A_hi, B_lo, B_hi, T);
-#pragma unroll
-                    for (int j = 0; j < LK_RUN; j++) {
-                        const int v = dp2a_hi_su(W23, T[j], dp2a_lo_su(W01, T[j], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        sb1 += v * Ix0[j];
-                        sb2 += v * Iy0[j];
-                    }
+                    LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, Ix0, Iy0);
                 }
                 {
-                    unsigned A_lo, A_hi, B_lo, B_hi, T[LK_RUN];
+                    unsigned A_lo, A_hi, B_lo, B_hi;
                     load8(Jw + roff1, inx + rx1, A_lo, A_hi);
                     load8(Jw + roff1 + L.pitch, inx + rx1, B_lo, B_hi);
-                    LK_TAPS(A_lo, A_hi, B_lo, B_hi, T);
-#pragma unroll
-                    for (int j = 0; j < LK_RUN; j++) {
-                        const int v = dp2a_hi_su(W23, T[j], dp2a_lo_su(W01, T[j], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        sb1 += v * Ix1[j];
-                        sb2 += v * Iy1[j];
-                    }
+                    LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, Ix1, Iy1);
                 }
                 const float b1 = __ll2float_rn(warp_sum_i64(sb1)) * FLT_SCALE;
                 const float b2 = __ll2float_rn(warp_sum_i64(sb2)) * FLT_SCALE;
