@@ -74,20 +74,6 @@ __device__ __forceinline__ unsigned load4(const uint8_t* __restrict__ row, int x
     return __funnelshift_r(__ldg(wp), __ldg(wp + 1), (x & 3) * 8);
 }
 
-// the 7 tap words (t00, t01, t10, t11) of a run from its two rows of 8 bytes
-#define LK_TAPS(A_lo, A_hi, B_lo, B_hi, T)                                   \
-    {                                                                        \
-        const unsigned A_mid = __funnelshift_r(A_lo, A_hi, 16);              \
-        const unsigned B_mid = __funnelshift_r(B_lo, B_hi, 16);              \
-        T[0] = __byte_perm(A_lo, B_lo, 0x5410);                              \
-        T[1] = __byte_perm(A_lo, B_lo, 0x6521);                              \
-        T[2] = __byte_perm(A_lo, B_lo, 0x7632);                              \
-        T[3] = __byte_perm(A_mid, B_mid, 0x6521);                            \
-        T[4] = __byte_perm(A_hi, B_hi, 0x5410);                              \
-        T[5] = __byte_perm(A_hi, B_hi, 0x6521);                              \
-        T[6] = __byte_perm(A_hi, B_hi, 0x7632);                              \
-    }
-
 // bilinear samples of the 7 pixels of a run from its two rows of 8 bytes (A: upper, B: lower) and MAC with the template:
 // pixel j needs the byte pairs (A[j], A[j+1]) and (B[j], B[j+1]); dp2a.lo / dp2a.hi pick the pair at bytes 0-1 / 2-3 of a
 // register, so the rows and their 1-byte-shifted copies serve all 7 pixels without assembling a tap word per pixel
