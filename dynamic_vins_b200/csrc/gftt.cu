@@ -279,20 +279,20 @@ __device__ __forceinline__ void resp_strip(const uint8_t* __restrict__ img, int 
     int y = y_first;
     for (; y <= y_last && y < f0; y++) resp_step<WRITE_EIG, EMIT, false>(C, S, y);
     if (y <= f1) {
+        // every lane prefetches its column, an edge column (its own column again unless it is lane 0 / 31) and a mask byte
+        // (column clamped into the image for lanes that own none): no divergent branches in the loop body
         const bool edge_lane = C.lane == 0 || C.lane == 31;
         const uint8_t* __restrict__ pc = C.col + (size_t)y * pitch;
-        const uint8_t* __restrict__ pe = C.col_edge + (size_t)y * pitch;
-        const uint8_t* __restrict__ pm = (EMIT && C.owned_col) ? mask + (size_t)(y - 2) * mask_pitch + C.x : nullptr;
-        unsigned nc = __ldg(pc), ne = edge_lane ? __ldg(pe) : 0u, nm = pm ? __ldg(pm) : 0u;
+        const uint8_t* __restrict__ pe = (edge_lane ? C.col_edge : C.col) + (size_t)y * pitch;
+        const uint8_t* __restrict__ pm = EMIT ? mask + (size_t)(y - 2) * mask_pitch + min(max(C.x, 0), w - 1) : C.col;
+        const int mstep = EMIT ? mask_pitch : 0;
+        unsigned nc = __ldg(pc), ne = __ldg(pe), nm = __ldg(pm);
 #pragma unroll kRsUnroll
         for (; y <= f1; y++) {
-            const unsigned cc = nc, ce = ne, cm = nm;
-            if (y < f1) {                      // rows y+1 <= f1 <= h-1 and y-1 < y1: in bounds
-                pc += pitch; pe += pitch;
-                nc = __ldg(pc);
-                if (edge_lane) ne = __ldg(pe);
-                if (pm) { pm += mask_pitch; nm = __ldg(pm); }
-            }
+            const unsigned cc = nc, ce = ne, cm = C.owned_col ? nm : 0u;
+            const bool more = y < f1;              // rows y+1 <= f1 <= h-1 and y-1 < y1: in bounds
+            pc += more ? pitch : 0; pe += more ? pitch : 0; pm += more ? mstep : 0;
+            nc = __ldg(pc); ne = __ldg(pe); nm = __ldg(pm);
             resp_step<WRITE_EIG, EMIT, true>(C, S, y, cc, ce, cm);
         }
     }
