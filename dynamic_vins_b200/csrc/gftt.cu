@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 #define RS_OPT_DSHFL 0
 #endif
 #ifndef RS_UNROLL
-#define RS_UNROLL 3
+#define RS_UNROLL 6
 #endif
 constexpr int kRsUnroll = RS_UNROLL;
 // u8 -> float without the XU-pipe I2F: 2^23 + v as bits, minus 2^23 (exact)
