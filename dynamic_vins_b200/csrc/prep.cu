@@ -72,6 +72,45 @@ __device__ __noinline__ void remap_taps_border(const uint8_t* __restrict__ img, 
     }
 }
 
+// d = a.s16[0] * b.u8[2h] + a.s16[1] * b.u8[2h+1] + c     (h = 0: lo, 1: hi)
+__device__ __forceinline__ int prep_dp2a_lo(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int prep_dp2a_hi(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// 6 consecutive bytes at p (any alignment) as two registers: lo = bytes 0..3, hi = bytes 4..7 (reads the 12 aligned bytes
+// around them: the caller guarantees p + 12 stays inside the image)
+__device__ __forceinline__ void prep_load6(const uint8_t* __restrict__ p, unsigned& lo, unsigned& hi) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned* wp = reinterpret_cast<const unsigned*>(a & ~(uintptr_t)3);
+    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+    const int sh = (int)(a & 3) * 8;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+// bilinear BGR sample from the two 6-byte rows (B G R B G R) of the 2 x 2 footprint: per channel the taps (top c, top 3+c,
+// bottom c, bottom 3+c) are gathered into one register with PRMT and reduced with two dp2a against the packed weights
+__device__ __forceinline__ void remap_bgr_words(const uint8_t* __restrict__ p, int pitch, int wa, int wb, unsigned out[3]) {
+    unsigned tl, th, bl, bh;
+    prep_load6(p, tl, th);
+    prep_load6(p + pitch, bl, bh);
+    const unsigned X0 = __byte_perm(tl, bl, 0x7430);        // t0 t3 b0 b3
+    const unsigned H = __byte_perm(th, bh, 0x5410);         // t4 t5 b4 b5
+    const unsigned U = __byte_perm(tl, bl, 0x6521);         // t1 t2 b1 b2
+    const unsigned X1 = __byte_perm(U, H, 0x6240);          // t1 t4 b1 b4
+    const unsigned X2 = __byte_perm(U, H, 0x7351);          // t2 t5 b2 b5
+    out[0] = (unsigned)prep_dp2a_hi(wb, X0, prep_dp2a_lo(wa, X0, 512)) >> 10;
+    out[1] = (unsigned)prep_dp2a_hi(wb, X1, prep_dp2a_lo(wa, X1, 512)) >> 10;
+    out[2] = (unsigned)prep_dp2a_hi(wb, X2, prep_dp2a_lo(wa, X2, 512)) >> 10;
+}
+
 __device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r) {
     return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
 }
@@ -139,7 +178,10 @@ __global__ void __launch_bounds__(256) k_ingest_remap(IngestArgs a) {
             sxs[i] = (short)sx; sys[i] = (short)sy;
             wa[i] = ((32 - fx) * (32 - fy)) | (fx * (32 - fy)) << 16;
             wb[i] = ((32 - fx) * fy) | (fx * fy) << 16;
-            if ((unsigned)sx < (unsigned)(a.w - 1) && (unsigned)sy < (unsigned)(a.h - 1)) {
+            // inside = the 2 x 2 footprint is in the image AND (3 channels) the 12 aligned bytes the word path reads around
+            // each 6-byte row stay inside the image buffer; everything else takes the bounds-checked path
+            if ((unsigned)sx < (unsigned)(a.w - 1) && (unsigned)sy < (unsigned)(a.h - 1) &&
+                (CH != 3 || (sy + 1) * a.src_pitch + sx * CH + 12 <= a.h * a.src_pitch)) {
                 inside |= 1u << i;
                 off[i] = sy * a.src_pitch + sx * CH;
             }
@@ -156,10 +198,14 @@ __global__ void __launch_bounds__(256) k_ingest_remap(IngestArgs a) {
             const int w00 = wa[i] & 0xffff, w01 = wa[i] >> 16, w10 = wb[i] & 0xffff, w11 = wb[i] >> 16;
             if (inside >> i & 1) {
                 const uint8_t* p = img + off[i];
+                if (CH == 3) {
+                    remap_bgr_words(p, a.src_pitch, wa[i], wb[i], res[i]);
+                } else {
 #pragma unroll
-                for (int c = 0; c < CH; c++)
-                    res[i][c] = (unsigned)(w00 * __ldg(p + c) + w01 * __ldg(p + CH + c) + w10 * __ldg(p + a.src_pitch + c) +
-                                           w11 * __ldg(p + a.src_pitch + CH + c) + 512) >> 10;
+                    for (int c = 0; c < CH; c++)
+                        res[i][c] = (unsigned)(w00 * __ldg(p + c) + w01 * __ldg(p + CH + c) + w10 * __ldg(p + a.src_pitch + c) +
+                                               w11 * __ldg(p + a.src_pitch + CH + c) + 512) >> 10;
+                }
             } else {
                 remap_taps_border<CH>(img, a.src_pitch, a.w, a.h, sxs[i], sys[i], w00, w01, w10, w11, res[i]);
             }
