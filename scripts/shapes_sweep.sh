@@ -1,7 +1,7 @@
 #!/bin/bash
 # the other BASELINE.json config shapes (C1, C2, C4): our arm and the reference arm on the same box, 64 streams
 for wl in c1_euroc_mono c2_kitti_stereo c4_hd_stereo; do
-  g=1; [ $wl = c4_hd_stereo ] && g=4
+  g=1; [ $wl = c4_hd_stereo ] && g=4; [ $wl = c1_euroc_mono ] && g=2   # e2e groups: 1 when PCIe-bound, more when upload ~ compute
   python bench.py --workload $wl --steps 100 --e2e-groups $g > /tmp/a.json 2>/dev/null
   python bench.py --impl reference --workload $wl --steps 6 --warmup 2 > /tmp/r.json 2>/dev/null
   python - $wl <<PY
