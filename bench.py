@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=4, help="stream groups per tracker (dvfe_config::n_groups), device-resident leg")
     ap.add_argument("--e2e-groups", type=int, default=1,
                     help="stream groups of the end-to-end leg (PCIe-bound: one group = fewer, larger uploads, +1.6 %%)")
+    ap.add_argument("--dyn-groups", type=int, default=2, help="stream groups of the dynamic-mode workload (c3): PCIe-bound, 2 is best")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -438,7 +439,7 @@ def run_dvfe_dynamic(args):
     cfg = make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S,
                       max_dynamic_cnt=c["max_dynamic_cnt"], min_dynamic_dist=c["min_dynamic_dist"],
                       use_mask_morphology=c["use_mask_morphology"], mask_morphology_size=c["mask_morphology_size"],
-                      max_instances=8, device=local, n_groups=max(1, min(args.groups, S)))
+                      max_instances=8, device=local, n_groups=max(1, min(args.dyn_groups, S)))
     trk = BatchTracker(cfg)
     order = synth.pingpong_positions(T, args.warmup + args.steps)
     ones = [1] * S
