@@ -131,8 +131,8 @@ int grp_set_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* 
     return DVFE_OK;
 }
 
-int grp_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb) {
-    for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_set_lk_mode(g, back_max_level, fb));
+int grp_set_lk_mode(dvfe_tracker* t, int site, int back_max_level, double fb) {
+    for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_set_lk_mode_site(g, site, back_max_level, fb));
     return DVFE_OK;
 }
 

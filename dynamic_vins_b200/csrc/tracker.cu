@@ -39,7 +39,7 @@ int grp_wait_all(dvfe_tracker* t);
 int grp_track_semantic(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv, size_t stride, int pitch,
                        const int* exist, const double* time0);
 int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
-int grp_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb);
+int grp_set_lk_mode(dvfe_tracker* t, int site, int back_max_level, double fb);
 int grp_profile(dvfe_tracker* t, int enable);
 int grp_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps);
 #define IS_GROUP(t) ((t) != nullptr && !(t)->groups.empty())
@@ -338,7 +338,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
-        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh,
+        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st,
+                             lk_back_level[semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL],
+                             lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL],
                              tcache_valid ? LK_TCACHE_READ : 0));
     mark(ST_LK_TEMPORAL + 1);
     if (k > 0)   // ReduceVector x4 + track_cnt++
@@ -362,8 +364,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     mark(ST_LEFT_POST + 1);
     if (stereo_now) DVFE_CUDA(cudaStreamWaitEvent(st, ev_rpyr[par], 0));
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
-        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level, lk_fb_thresh,
-                             LK_TCACHE_WRITE));
+        DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st,
+                             lk_back_level[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO],
+                             lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO], LK_TCACHE_WRITE));
     tcache_valid = stereo_now && d_tcache != nullptr;
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs[par], d_nobs[par], st));
@@ -623,15 +626,20 @@ extern "C" int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_l
     return t->submit(d_left, d_right, stream_stride, pitch, time0, false, false, d_right != nullptr);
 }
 
-extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold) {
-    if (!t || back_max_level < 0 || back_max_level >= DVFE_MAX_PYR_LEVELS || !(fb_threshold > 0.0)) {
+extern "C" int dvfe_set_lk_mode_site(dvfe_tracker* t, int site, int back_max_level, double fb_threshold) {
+    if (!t || site < -1 || site > DVFE_LK_SEMANTIC_STEREO || back_max_level < 0 || back_max_level >= DVFE_MAX_PYR_LEVELS ||
+        !(fb_threshold > 0.0)) {
         dvfe_set_error("set_lk_mode: bad argument");
         return DVFE_ERR_INVALID;
     }
-    if (IS_GROUP(t)) return grp_set_lk_mode(t, back_max_level, fb_threshold);
-    t->lk_back_level = back_max_level;
-    t->lk_fb_thresh = fb_threshold;
+    if (IS_GROUP(t)) return grp_set_lk_mode(t, site, back_max_level, fb_threshold);
+    for (int i = 0; i < 4; i++)
+        if (site < 0 || site == i) { t->lk_back_level[i] = back_max_level; t->lk_fb_thresh[i] = fb_threshold; }
     return DVFE_OK;
+}
+
+extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold) {
+    return dvfe_set_lk_mode_site(t, -1, back_max_level, fb_threshold);
 }
 
 int dvfe_tracker::semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,

@@ -68,8 +68,11 @@ struct dvfe_tracker {
     InstanceState* inst = nullptr;
     unsigned* d_tcache = nullptr;                    // LK template cache [B][cap][DVFE_MAX_PYR_LEVELS][LK_TCACHE_WORDS] (stereo only)
     bool tcache_valid = false;                       // the last step ran the stereo LK on the points `bg` holds now
-    int lk_back_level = 1;                           // backward LK maxLevel (feature_utils.cpp:51: 1; cv::cuda path: 3)
-    double lk_fb_thresh = 0.5;                       // forward-backward threshold in px (:57: 0.5; cv::cuda path: 1.0)
+    // backward LK maxLevel / forward-backward threshold per call site [DVFE_LK_*]: the CPU FeatureTrackByLK pair
+    // (feature_utils.cpp:51,57: 1, 0.5) everywhere except TrackSemanticImage's right image, which the reference tracks with
+    // the cv::cuda call pattern (TrackRightGPU, background_tracker.cpp:801: 3 levels, 1.0 px)
+    int lk_back_level[4] = {1, 1, 1, 3};
+    double lk_fb_thresh[4] = {0.5, 0.5, 0.5, 1.0};
 
     // per-stage device timers (one event set per in-flight step)
     enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT_MASK, ST_GFTT_DISCS, ST_GFTT_RESPONSE, ST_GFTT_SELECT, ST_LEFT_POST,

@@ -151,9 +151,12 @@ class BatchTracker:
         L.check(L.lib().dvfe_track_image_device_async(self._h, C.c_void_p(d_left), C.c_void_p(d_right) if d_right else None,
                                                       stream_stride, pitch, L.ptr(t)))
 
-    def set_lk_mode(self, back_max_level: int = 1, fb_threshold: float = 0.5) -> None:
-        """cv::cuda call pattern of FeatureTrackByLKGpu: back_max_level=3, fb_threshold=1.0"""
-        L.check(L.lib().dvfe_set_lk_mode(self._h, int(back_max_level), float(fb_threshold)))
+    LK_RAW_TEMPORAL, LK_RAW_STEREO, LK_SEMANTIC_TEMPORAL, LK_SEMANTIC_STEREO = 0, 1, 2, 3
+
+    def set_lk_mode(self, back_max_level: int = 1, fb_threshold: float = 0.5, site: int = -1) -> None:
+        """Backward-pass depth / round-trip threshold of the LK at one call site (LK_*) or, site = -1, at all four.
+        CPU FeatureTrackByLK: (1, 0.5); cv::cuda call pattern of FeatureTrackByLKGpu: (3, 1.0)."""
+        L.check(L.lib().dvfe_set_lk_mode_site(self._h, int(site), int(back_max_level), float(fb_threshold)))
 
     def track_semantic_image(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
         l = self._batch(left, self.B, self.H, self.W, self.ch)

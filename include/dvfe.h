@@ -154,12 +154,22 @@ int dvfe_track_image_device(dvfe_tracker* t, const uint8_t* d_left, const uint8_
 int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride,
                                   int pitch, const double* time0);
 
-/* FeatureTracker::TrackImageNaive-style variant of the step (front_end/background_tracker.cpp:400-516): the
- * cv::cuda LK call pattern of FeatureTrackByLKGpu (front_end/feature_utils.cpp:83-163) — backward pass over all
- * `back_max_level`+1 levels (3) and a forward-backward threshold of `fb_threshold` px (1.0) — evaluated with this
- * library's fixed-point LK arithmetic (cv::cuda's fp32 texture interpolation is not reproduced).  Applies to all later
- * steps of the tracker; the defaults (1, 0.5) are the CPU FeatureTrackByLK. */
+/* Backward-pass depth and forward-backward threshold of the LK at each of the reference's four call sites.  The
+ * reference uses two pairs: the CPU FeatureTrackByLK (front_end/feature_utils.cpp:35-69: backward maxLevel 1, round
+ * trip <= 0.5 px) and the cv::cuda call pattern of FeatureTrackByLKGpu (:83-163 with the objects created at
+ * front_end/background_tracker.cpp:36-38: backward over all 3 levels, <= 1.0 px).  Defaults follow the reference:
+ *   DVFE_LK_RAW_TEMPORAL, DVFE_LK_RAW_STEREO        TrackImage (:61-63, :117-118)                 CPU pair (1, 0.5)
+ *   DVFE_LK_SEMANTIC_TEMPORAL                       TrackSemanticImage -> bg.TrackLeft (:783)      CPU pair (1, 0.5)
+ *   DVFE_LK_SEMANTIC_STEREO                         TrackSemanticImage -> bg.TrackRightGPU (:801)  GPU pair (3, 1.0)
+ * Both pairs are evaluated with this library's fixed-point LK arithmetic (cv::cuda's fp32 texture interpolation is not
+ * reproduced).  dvfe_set_lk_mode_site sets one site; dvfe_set_lk_mode sets all four (e.g. (3, 1.0) for the
+ * TrackImageNaive flow, front_end/background_tracker.cpp:400-516).  Applies to all later steps of the tracker. */
+#define DVFE_LK_RAW_TEMPORAL 0
+#define DVFE_LK_RAW_STEREO 1
+#define DVFE_LK_SEMANTIC_TEMPORAL 2
+#define DVFE_LK_SEMANTIC_STEREO 3
 int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold);
+int dvfe_set_lk_mode_site(dvfe_tracker* t, int site, int back_max_level, double fb_threshold);
 
 /* FeatureTracker::TrackSemanticImage(SemanticImage&) (front_end/background_tracker.cpp:757-837).
  * inv_merge_mask: HOST, same layout as left (0 = object, 255 = background), may be NULL when no stream has

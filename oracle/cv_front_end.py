@@ -6,20 +6,15 @@ CPU restatement of the reference's point-feature front-end, line by line, over
 legs of `bench.py` may import this module.  The product path
 (`dynamic_vins_b200/`) never does.
 
-PARITY UNPINNED against the reference binary: the reference ships no tests, golden vectors or fixtures for this
-path and cannot be built or run here, so nothing produced by the reference itself anchors this oracle.  What IS
-pinned: the OpenCV stages are executed by the third-party library itself (cv2) at the reference's call sites, and
-the plain-C arithmetic spec (oracle/spec.c) is checked against that library.
-
-Pinning details: the reference C++ cannot be built here (ROS, OpenCV-C++ 3.4.16+CUDA, Eigen,
-libtorch, TensorRT, PCL, Ceres are absent) and it ships no tests or golden vectors
-for this path.  The arithmetic lives in a third-party
-dependency, OpenCV (pinned 3.4.16, dynamic_vins/CMakeLists.txt:36; un-vendored).
-This oracle executes that dependency itself (python `cv2` 4.13.0 — version skew
-3.4.16 -> 4.13.0 is stated, it cannot be checked here) at the reference's own call
-sites, so the OpenCV stages are "the reference run here"; the glue around them is
-restated from the files cited per function.  Golden fixtures under
-`tests/golden/` are produced by `tests/golden/make_golden.py` from this module.
+PARITY PINNED against reference-compiled code: the reference ships no tests, golden vectors or fixtures for this
+path, and the whole ROS binary cannot be built here, but its front-end translation units can:
+oracle/ref/Makefile compiles camera_models/src/camera_models/{PinholeCamera,Camera}.cc and
+dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp UNMODIFIED (stand-in
+third-party headers in oracle/shim/, OpenCV image algorithms served by cv2 through hooks) into oracle/_ref/libdvref.so.
+tests/test_ref_compiled.py asserts that every function of this module and whole-frame `FrontEnd.step` sequences (raw,
+semantic, dynamic) equal that library bit for bit.  What remains unpinned is only the OpenCV version: cv2 4.13.0 runs where
+the reference pins OpenCV 3.4.16 (dynamic_vins/CMakeLists.txt:36; un-vendored, skew cannot be checked offline).
+Golden fixtures under `tests/golden/` are produced by `tests/golden/make_golden.py` from this module.
 
 All paths below are under /root/reference/dynamic_vins/src/ unless absolute.
 
@@ -28,12 +23,14 @@ Deliberate, documented choices where the reference is nondeterministic or UB:
     `InstsTrack` thread (front_end/instance_feature.h:137, system/main.cpp:247-250).
     Oracle and product use: background first, then instances in ascending
     instance id (the reference iterates an `unordered_map`).
-  * `TrackSemanticImage` calls the cv::cuda LK for the right image
-    (front_end/background_tracker.cpp:801); the parity target is the CPU tracker
-    (north_star), so the right image uses the CPU `FeatureTrackByLK` (FB 0.5 px),
-    i.e. `InstFeat::TrackRight` without the VIODE-only segmentation test.
-  * `Output()` reads `prev_img.disp` with ROI-local coordinates
-    (front_end/dynamic_tracker.cpp:547); no disparity map is supplied -> disp = 0.
+  * `TrackSemanticImage` calls the cv::cuda LK for the right image (`TrackRightGPU`,
+    front_end/background_tracker.cpp:801 -> `FeatureTrackByLKGpu`, front_end/feature_utils.cpp:83-163): backward pass
+    over all 3 levels with the forward result as initial flow, round-trip test <= 1.0 px.  That CALL PATTERN is
+    reproduced (`gpu_lk_back_max_level`, `gpu_fb_threshold`); cv::cuda's fp32 texture arithmetic is not: the
+    CPU `calcOpticalFlowPyrLK` arithmetic runs in its place (the parity target is the CPU tracker, north_star).
+    The VIODE-only segmentation test of `TrackRightGPU` does not apply (dataset != VIODE).
+  * `Output()` reads `prev_img.disp` with ROI-local coordinates (front_end/dynamic_tracker.cpp:547); reproduced as
+    written when a disparity map is supplied, 0 otherwise (the reference would read an empty Mat).
   * If the left point set is empty, the right-image lists are cleared (the reference
     leaves stale vectors in `TrackSemanticImage`; `TrackImage` clears them).
 """
@@ -64,6 +61,10 @@ class FrontEndParams:
     lk_max_level: int = 3         # cv::calcOpticalFlowPyrLK(..., Size(21,21), 3)
     lk_back_max_level: int = 1    # backward call: maxLevel 1 (feature_utils.cpp:51); FeatureTrackByLKGpu: 3
     fb_threshold: float = 0.5     # forward-backward distance (feature_utils.cpp:57); FeatureTrackByLKGpu: 1.0 (:117)
+    # FeatureTrackByLKGpu call pattern (feature_utils.cpp:83-163; lk_optical_flow_back = create(21x21, 3, 30, true),
+    # background_tracker.cpp:36-38), used by TrackSemanticImage for the right image (TrackRightGPU)
+    gpu_lk_back_max_level: int = 3
+    gpu_fb_threshold: float = 1.0
 
 
 class IdCounter:
@@ -298,7 +299,7 @@ class InstFeat:
         self.track_cnt = [c + 1 for c in _reduce(self.track_cnt, status)]
 
     # front_end/instance_feature.cpp:229-247 (TrackRight) / :251-275 (TrackRightByPad), non-VIODE branch
-    def track_right(self, gray0, gray1, P: FrontEndParams, offset=(0.0, 0.0)):
+    def track_right(self, gray0, gray1, P: FrontEndParams, offset=(0.0, 0.0), gpu_pattern: bool = False):
         if len(self.curr_points) == 0:
             # the reference returns with stale right_* vectors; they can only refer to ids that no
             # longer exist (unobservable through Output()), so they are cleared here
@@ -307,8 +308,10 @@ class InstFeat:
         pts = self.curr_points
         if offset != (0.0, 0.0):
             pts = np.stack([pts[:, 0] + f32(offset[0]), pts[:, 1] + f32(offset[1])], axis=1).astype(f32)
-        rp, status = feature_track_by_lk(gray0, gray1, pts, bool(P.flow_back), P.lk_max_level, P.lk_back_max_level,
-                                         P.fb_threshold)
+        # gpu_pattern: InstFeat::TrackRightGPU (:278-312) -> FeatureTrackByLKGpu's backward level / threshold
+        rp, status = feature_track_by_lk(gray0, gray1, pts, bool(P.flow_back), P.lk_max_level,
+                                         P.gpu_lk_back_max_level if gpu_pattern else P.lk_back_max_level,
+                                         P.gpu_fb_threshold if gpu_pattern else P.fb_threshold)
         self.right_points = _reduce(rp, status)
         self.right_ids = _reduce(list(self.ids), status)
 
@@ -377,13 +380,13 @@ class FeatureTracker:
                 points.setdefault(fid, []).append((1, v))
         return dict(sorted(points.items()))
 
-    def _right(self, gray0, gray1, dt):
+    def _right(self, gray0, gray1, dt, gpu_pattern: bool = False):
         bg = self.bg
         bg.right_ids, bg.right_points = [], np.zeros((0, 2), f32)
         bg.right_un_points, bg.right_pts_velocity = np.zeros((0, 2), f32), np.zeros((0, 2), f32)
         bg.right_curr_id_pts = {}
         if len(bg.curr_points) > 0:
-            bg.track_right(gray0, gray1, self.P)
+            bg.track_right(gray0, gray1, self.P, gpu_pattern=gpu_pattern)
             bg.right_un_points = self.cam1.undistort_points(bg.right_points)
             bg.right_pts_velocity_(dt)
         bg.right_prev_id_pts = dict(bg.right_curr_id_pts)
@@ -442,8 +445,8 @@ class FeatureTracker:
         dt = self.cur_time - self.prev_time
         bg.pts_velocity_(dt)
         stereo_now = bool(P.is_stereo and gray1 is not None)
-        if stereo_now:                                                              # :797-803 (CPU LK, see header)
-            self._right(gray0, gray1, dt)
+        if stereo_now:                                                              # :797-803 TrackRightGPU call pattern
+            self._right(gray0, gray1, dt, gpu_pattern=True)
         self.prev_gray0 = gray0
         self.prev_time = self.cur_time
         bg.post_process()
@@ -555,7 +558,10 @@ class InstsFeatManager:
         self.last_time = self.curr_time
 
     # front_end/dynamic_tracker.cpp:521-577
-    def output(self):
+    def output(self, disp: Optional[np.ndarray] = None):
+        """`disp`: SemanticImage::disp of the frame (CV_32F, full image size) or None = all zeros.  The reference reads it at
+        inst.curr_points, i.e. with ROI-LOCAL coordinates (:547, quirk Q8: `Mat::at<float>(Point2f)` rounds to the nearest
+        pixel, ties to even); that lookup is reproduced as written."""
         result = {}
         for key, inst in self._exec():
             if inst.lost_num > 0 or not inst.is_curr_visible:
@@ -565,7 +571,8 @@ class InstsFeatManager:
                 feats[inst.ids[i]] = dict(
                     point=np.array([inst.curr_un_points[i, 0], inst.curr_un_points[i, 1], 1.0]),
                     vel=np.array([inst.pts_velocity[i, 0], inst.pts_velocity[i, 1]], dtype=np.float64),
-                    point_right=np.zeros(3), vel_right=np.zeros(2), is_stereo=False, disp=0.0,
+                    point_right=np.zeros(3), vel_right=np.zeros(2), is_stereo=False,
+                    disp=0.0 if disp is None else float(disp[cv_round(inst.curr_points[i, 1]), cv_round(inst.curr_points[i, 0])]),
                     uv=np.array([inst.curr_points[i, 0], inst.curr_points[i, 1]], dtype=np.float64))
             if self.P.is_stereo:
                 for i in range(len(inst.right_un_points)):
@@ -595,8 +602,8 @@ class FrontEnd:
         self.tracker = FeatureTracker(params, c0, c1, self.idc)
         self.insts = InstsFeatManager(params, c0, c1, self.idc) if mode == "dynamic" else None
 
-    def step(self, frame) -> dict:
-        """frame: dynamic_vins_b200.synth.SynthFrame-shaped object."""
+    def step(self, frame, disp: Optional[np.ndarray] = None) -> dict:
+        """frame: dynamic_vins_b200.synth.SynthFrame-shaped object; disp: optional SemanticImage::disp (dynamic mode)."""
         if self.mode == "raw":
             return {"features": self.tracker.track_image(frame.gray0, frame.gray1, frame.time0), "instances": {}}
         self.insts.begin_frame()
@@ -605,7 +612,7 @@ class FrontEnd:
         feats = self.tracker.track_semantic_image(frame.gray0, frame.gray1, frame.time0,
                                                   frame.inv_merge_mask, frame.exist_inst)
         self.insts.insts_track(frame.gray0, frame.gray1, frame.time0, frame.boxes)
-        return {"features": feats, "instances": self.insts.output()}
+        return {"features": feats, "instances": self.insts.output(disp)}
 
 
 def serialize_point_features(points: Dict[int, List[Tuple[int, np.ndarray]]]) -> str:

@@ -1,0 +1,368 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY — never linked into, loaded by or shipped with the product.
+//
+// C entry points over the REFERENCE's own front-end code, compiled unmodified from /root/reference by oracle/ref/Makefile
+// into oracle/_ref/libdvref.so:
+//     camera_models/src/camera_models/{PinholeCamera,Camera}.cc
+//     dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp
+// against the stand-in third-party headers in oracle/shim/ (Eigen / OpenCV containers; OpenCV image algorithms are forwarded
+// through hooks to cv2 by the Python harness, oracle/ref_lib.py).  This file only (a) defines the few out-of-scope symbols
+// those translation units reference (line detector, yaml parameter loading, camera globals), (b) converts flat C arrays to
+// the reference's types and back.  It contains no front-end arithmetic of its own.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "front_end/background_tracker.h"
+#include "front_end/dynamic_tracker.h"
+#include "front_end/feature_utils.h"
+#include "front_end/front_end_parameters.h"
+#include "camodocal/camera_models/PinholeCamera.h"
+
+// ---- shim state ----------------------------------------------------------------------------------------------------
+namespace dvshim {
+Hooks& hooks() { static Hooks h; return h; }
+}
+
+// ---- out-of-scope symbols the reference translation units reference -------------------------------------------------
+namespace dynamic_vins {
+
+CameraInfo cam_s, cam_t, cam_v;                                   // utils/camera_model.cpp:21-23 (set by dvref_configure)
+std::vector<Eigen::Matrix3d> R_IC;
+std::vector<Eigen::Vector3d> T_IC;
+
+// front_end/front_end_parameters.cpp reads a yaml file through cv::FileStorage; the harness sets the statics directly
+void FrontendParemater::SetParameters(const std::string&) {}
+
+// line features are off on the parity path (cfg::use_line = false); the constructor runs, nothing else may
+LineDetector::LineDetector(const std::string&) {}
+FrameLines::Ptr LineDetector::Detect(cv::Mat&, const cv::Mat&) { dvshim_unreachable("LineDetector::Detect"); }
+void LineDetector::TrackLeftLine(const FrameLines::Ptr&, const FrameLines::Ptr&) { dvshim_unreachable("LineDetector"); }
+void LineDetector::TrackRightLine(const FrameLines::Ptr&, const FrameLines::Ptr&) { dvshim_unreachable("LineDetector"); }
+void LineDetector::VisualizeLine(cv::Mat&, const FrameLines::Ptr&) { dvshim_unreachable("LineDetector"); }
+void LineDetector::VisualizeRightLine(cv::Mat&, const FrameLines::Ptr&, bool) { dvshim_unreachable("LineDetector"); }
+void FrameLines::SetLines() { dvshim_unreachable("FrameLines"); }
+void FrameLines::UndistortedLineEndPoints(camodocal::CameraPtr&) { dvshim_unreachable("FrameLines"); }
+float Box2D::IoU(const cv::Rect2f&, const cv::Rect2f&) { dvshim_unreachable("Box2D::IoU"); }
+void Box3D::VisCorners2d(cv::Mat&, const cv::Scalar&, camodocal::CameraPtr&) { dvshim_unreachable("Box3D::VisCorners2d"); }
+
+}  // namespace dynamic_vins
+
+using namespace dynamic_vins;
+
+static thread_local char g_err[512] = "";
+static int fail(const std::exception& e) {
+    std::snprintf(g_err, sizeof(g_err), "%s", e.what());
+    return -1;
+}
+
+extern "C" {
+
+const char* dvref_last_error(void) { return g_err; }
+const char* dvref_sources(void) {
+    return "camera_models/src/camera_models/PinholeCamera.cc camera_models/src/camera_models/Camera.cc "
+           "dynamic_vins/src/front_end/feature_utils.cpp dynamic_vins/src/front_end/instance_feature.cpp "
+           "dynamic_vins/src/front_end/background_tracker.cpp dynamic_vins/src/front_end/dynamic_tracker.cpp";
+}
+
+void dvref_set_hooks(void* lk, void* gftt, void* erode, void* circle, void* bgr2gray) {
+    auto& h = dvshim::hooks();
+    h.calc_optical_flow_pyr_lk = reinterpret_cast<decltype(h.calc_optical_flow_pyr_lk)>(lk);
+    h.good_features_to_track = reinterpret_cast<decltype(h.good_features_to_track)>(gftt);
+    h.erode_rect = reinterpret_cast<decltype(h.erode_rect)>(erode);
+    h.circle_filled = reinterpret_cast<decltype(h.circle_filled)>(circle);
+    h.bgr2gray = reinterpret_cast<decltype(h.bgr2gray)>(bgr2gray);
+}
+
+// ---- camodocal::PinholeCamera ------------------------------------------------------------------------------------
+// cam = {k1, k2, p1, p2, fx, fy, cx, cy}
+void* dvref_camera_new(int w, int h, const double* cam) {
+    auto* p = new camodocal::CameraPtr(new camodocal::PinholeCamera("cam", w, h, cam[0], cam[1], cam[2], cam[3], cam[4], cam[5],
+                                                                    cam[6], cam[7]));
+    return p;
+}
+void dvref_camera_free(void* c) { delete static_cast<camodocal::CameraPtr*>(c); }
+
+// PinholeCamera::liftProjective: uv [n][2] -> P [n][3]
+void dvref_lift_projective(void* c, const double* uv, int n, double* P) {
+    camodocal::CameraPtr& cam = *static_cast<camodocal::CameraPtr*>(c);
+    for (int i = 0; i < n; i++) {
+        Eigen::Vector3d b;
+        cam->liftProjective(Eigen::Vector2d(uv[2 * i], uv[2 * i + 1]), b);
+        P[3 * i] = b.x(); P[3 * i + 1] = b.y(); P[3 * i + 2] = b.z();
+    }
+}
+// PinholeCamera::distortion: p_u [n][2] -> d_u [n][2]
+void dvref_distortion(void* c, const double* pu, int n, double* du) {
+    auto* cam = static_cast<camodocal::PinholeCamera*>(static_cast<camodocal::CameraPtr*>(c)->get());
+    for (int i = 0; i < n; i++) {
+        Eigen::Vector2d d;
+        cam->distortion(Eigen::Vector2d(pu[2 * i], pu[2 * i + 1]), d);
+        du[2 * i] = d(0); du[2 * i + 1] = d(1);
+    }
+}
+// PinholeCamera::spaceToPlane: P [n][3] -> p [n][2]
+void dvref_space_to_plane(void* c, const double* P, int n, double* p) {
+    camodocal::CameraPtr& cam = *static_cast<camodocal::CameraPtr*>(c);
+    for (int i = 0; i < n; i++) {
+        Eigen::Vector2d q;
+        cam->spaceToPlane(Eigen::Vector3d(P[3 * i], P[3 * i + 1], P[3 * i + 2]), q);
+        p[2 * i] = q(0); p[2 * i + 1] = q(1);
+    }
+}
+// UndistortedPts (front_end/feature_utils.cpp:193-203): pts [n][2] float -> un [n][2] float
+void dvref_undistorted_pts(void* c, const float* pts, int n, float* un) {
+    camodocal::CameraPtr& cam = *static_cast<camodocal::CameraPtr*>(c);
+    std::vector<cv::Point2f> v(n);
+    for (int i = 0; i < n; i++) v[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]);
+    std::vector<cv::Point2f> out = UndistortedPts(v, cam);
+    for (int i = 0; i < n; i++) { un[2 * i] = out[i].x; un[2 * i + 1] = out[i].y; }
+}
+
+// ---- front_end/feature_utils.h inline helpers ----------------------------------------------------------------------
+int dvref_in_border(float x, float y, int row, int col) { return InBorder(cv::Point2f(x, y), row, col) ? 1 : 0; }
+float dvref_point_distance(float x1, float y1, float x2, float y2) { return PointDistance(cv::Point2f(x1, y1), cv::Point2f(x2, y2)); }
+int dvref_cv_round_f(float v) { return cvRound(v); }
+// ReduceVector<cv::Point2f> / <int> / <unsigned>: compacts in place, returns the new size
+int dvref_reduce_points(float* pts, const unsigned char* status, int n) {
+    std::vector<cv::Point2f> v(n);
+    for (int i = 0; i < n; i++) v[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]);
+    ReduceVector(v, std::vector<uchar>(status, status + n));
+    for (size_t i = 0; i < v.size(); i++) { pts[2 * i] = v[i].x; pts[2 * i + 1] = v[i].y; }
+    return (int)v.size();
+}
+int dvref_reduce_ints(int* a, const unsigned char* status, int n) {
+    std::vector<int> v(a, a + n);
+    ReduceVector(v, std::vector<uchar>(status, status + n));
+    std::copy(v.begin(), v.end(), a);
+    return (int)v.size();
+}
+// SetStatusByMask (feature_utils.h:149-151)
+void dvref_set_status_by_mask(unsigned char* status, const float* pts, int n, const unsigned char* mask, int rows, int cols) {
+    std::vector<uchar> st(status, status + n);
+    std::vector<cv::Point2f> v(n);
+    for (int i = 0; i < n; i++) v[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]);
+    cv::Mat m(rows, cols, CV_8UC1, (void*)mask);
+    SetStatusByMask(st, v, m);
+    std::copy(st.begin(), st.end(), status);
+}
+// PtsVelocity (feature_utils.cpp:274-296)
+void dvref_pts_velocity(double dt, const unsigned* ids, const float* cur_un, int n, const unsigned* prev_ids, const float* prev_un,
+                        int m, float* vel) {
+    std::vector<unsigned> idv(ids, ids + n);
+    std::vector<cv::Point2f> cur(n), out;
+    for (int i = 0; i < n; i++) cur[i] = cv::Point2f(cur_un[2 * i], cur_un[2 * i + 1]);
+    std::map<unsigned, cv::Point2f> prev;
+    for (int i = 0; i < m; i++) prev[prev_ids[i]] = cv::Point2f(prev_un[2 * i], prev_un[2 * i + 1]);
+    PtsVelocity(dt, idv, cur, prev, out);
+    for (int i = 0; i < n; i++) { vel[2 * i] = out[i].x; vel[2 * i + 1] = out[i].y; }
+}
+// FeatureTrackByLK (feature_utils.cpp:35-69); fe_para::is_flow_back is read, not the argument (reference quirk Q1)
+int dvref_feature_track_by_lk(const unsigned char* img1, const unsigned char* img2, int rows, int cols, const float* pts1, int n,
+                              float* pts2, unsigned char* status, int flow_back) {
+    try {
+        cv::Mat a(rows, cols, CV_8UC1, (void*)img1), b(rows, cols, CV_8UC1, (void*)img2);
+        std::vector<cv::Point2f> p1(n), p2;
+        for (int i = 0; i < n; i++) p1[i] = cv::Point2f(pts1[2 * i], pts1[2 * i + 1]);
+        fe_para::is_flow_back = flow_back;
+        std::vector<uchar> st = FeatureTrackByLK(a, b, p1, p2, flow_back != 0);
+        for (int i = 0; i < n; i++) { pts2[2 * i] = p2[i].x; pts2[2 * i + 1] = p2[i].y; status[i] = st[i]; }
+        return n;
+    } catch (const std::exception& e) { return fail(e); }
+}
+// InstanceImagePadding (feature_utils.cpp:406-413): both outputs are max(rows) x max(cols)
+void dvref_instance_image_padding(const unsigned char* img1, int r1, int c1, const unsigned char* img2, int r2, int c2,
+                                  unsigned char* out1, unsigned char* out2) {
+    cv::Mat a(r1, c1, CV_8UC1, (void*)img1), b(r2, c2, CV_8UC1, (void*)img2);
+    auto [pa, pb] = InstanceImagePadding(a, b);
+    for (int r = 0; r < pa.rows; r++) {
+        std::memcpy(out1 + (size_t)r * pa.cols, pa.ptr(r), pa.cols);
+        std::memcpy(out2 + (size_t)r * pb.cols, pb.ptr(r), pb.cols);
+    }
+}
+// ErodeMask (feature_utils.h:141-146)
+void dvref_erode_mask(const unsigned char* in, int rows, int cols, int k, unsigned char* out) {
+    cv::Mat a = cv::Mat(rows, cols, CV_8UC1, (void*)in).clone(), b;
+    ErodeMask(a, b, k);
+    for (int r = 0; r < rows; r++) std::memcpy(out + (size_t)r * cols, b.ptr(r), cols);
+}
+
+// ---- the trackers ---------------------------------------------------------------------------------------------------
+typedef struct dvref_config {
+    int max_cnt, max_dynamic_cnt, min_dist, min_dynamic_dist, flow_back, use_mask_morphology, mask_morphology_size;
+    int width, height, stereo, dynamic;
+    double cam0[8], cam1[8];          // k1 k2 p1 p2 fx fy cx cy
+} dvref_config;
+
+typedef struct dvref_obs {            // one (feature id, camera) record of FeatureBackground::points
+    unsigned id;
+    int cam;
+    double v[7];                      // x y z u v vx vy
+} dvref_obs;
+
+typedef struct dvref_inst_obs {       // one feature of FeatureInstance::features
+    unsigned inst_id, id;
+    int is_stereo, reserved;
+    double point[3], vel[2], point_right[3], vel_right[2];
+    double disp;
+} dvref_inst_obs;
+
+typedef struct dvref_box {            // Box2D + InstRoi as SemanticImage::SetMaskAndRoi leaves them
+    unsigned track_id;
+    int x, y, w, h;
+    const unsigned char* mask;        // h x w, 255 = object
+    int mask_pitch;
+} dvref_box;
+
+struct RefFrontEnd {
+    std::unique_ptr<FeatureTracker> tracker;
+    std::unique_ptr<InstsFeatManager> insts;
+    int rows = 0, cols = 0;
+};
+
+void* dvref_front_end_new(const dvref_config* c) {
+    fe_para::kMaxCnt = c->max_cnt;
+    fe_para::kMaxDynamicCnt = c->max_dynamic_cnt;
+    fe_para::kMinDist = c->min_dist;
+    fe_para::kMinDynamicDist = c->min_dynamic_dist;
+    fe_para::kFThreshold = 1.0;
+    fe_para::is_show_track = 0;
+    fe_para::is_flow_back = c->flow_back;
+    fe_para::use_mask_morphology = c->use_mask_morphology != 0;
+    fe_para::kMaskMorphologySize = c->mask_morphology_size;
+    fe_para::kInputHeight = c->height;
+    fe_para::kInputWidth = c->width;
+    cfg::is_stereo = c->stereo != 0;
+    cfg::slam = c->dynamic ? SLAM::kDynamic : SLAM::kRaw;
+    cfg::dataset = DatasetType::kCustom;
+    cfg::dataset_name = "custom";
+    cfg::use_line = false;
+    cfg::use_det3d = false;
+    cfg::kInputHeight = c->height;
+    cfg::kInputWidth = c->width;
+    cam_t.cam0 = camodocal::CameraPtr(new camodocal::PinholeCamera("cam0", c->width, c->height, c->cam0[0], c->cam0[1], c->cam0[2],
+                                                                   c->cam0[3], c->cam0[4], c->cam0[5], c->cam0[6], c->cam0[7]));
+    cam_t.cam1 = camodocal::CameraPtr(new camodocal::PinholeCamera("cam1", c->width, c->height, c->cam1[0], c->cam1[1], c->cam1[2],
+                                                                   c->cam1[3], c->cam1[4], c->cam1[5], c->cam1[6], c->cam1[7]));
+    cam_s = cam_t;
+    InstFeat::global_id_count = 1;                      // one front-end per process at a time (the reference's static)
+    auto* fe = new RefFrontEnd();
+    fe->tracker.reset(new FeatureTracker(""));
+    if (c->dynamic) fe->insts.reset(new InstsFeatManager(""));
+    fe->rows = c->height; fe->cols = c->width;
+    return fe;
+}
+void dvref_front_end_free(void* p) { delete static_cast<RefFrontEnd*>(p); }
+
+static int flatten(const FeatureBackground& fb, dvref_obs* out, int cap) {
+    int n = 0;
+    for (auto& [id, obs] : fb.points)
+        for (auto& [cam, v] : obs) {
+            if (n < cap) {
+                out[n].id = id; out[n].cam = cam;
+                for (int k = 0; k < 7; k++) out[n].v[k] = v(k);
+            }
+            n++;
+        }
+    return n;
+}
+
+static SemanticImage make_image(RefFrontEnd* fe, const unsigned char* gray0, const unsigned char* gray1, double time0, unsigned seq) {
+    SemanticImage img;
+    img.gray0 = cv::Mat(fe->rows, fe->cols, CV_8UC1, (void*)gray0).clone();
+    if (gray1) img.gray1 = cv::Mat(fe->rows, fe->cols, CV_8UC1, (void*)gray1).clone();
+    img.color0 = cv::Mat(fe->rows, fe->cols, CV_8UC3);      // only its size is read on this path
+    img.time0 = time0; img.time1 = time0; img.seg0_time = time0; img.seg1_time = time0;
+    img.seq = seq;
+    return img;
+}
+
+// FeatureTracker::TrackImage (front_end/background_tracker.cpp:52-158) -> number of records
+int dvref_track_image(void* p, const unsigned char* gray0, const unsigned char* gray1, double time0, dvref_obs* out, int cap) {
+    try {
+        auto* fe = static_cast<RefFrontEnd*>(p);
+        SemanticImage img = make_image(fe, gray0, gray1, time0, 0);
+        return flatten(fe->tracker->TrackImage(img), out, cap);
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// One frame of dynamic mode as system/main.cpp:193-252 drives it: reset visibility, AddViodeInstances (instances arrive with
+// track ids), TrackSemanticImage, InstsTrack, Output.  The reference runs InstsTrack on a second thread that races the
+// background thread for InstFeat::global_id_count; here the two run one after the other, background first.
+int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char* gray1, const unsigned char* merge_mask,
+                        const unsigned char* inv_merge_mask, const float* disp, const dvref_box* boxes, int n_boxes, double time0,
+                        unsigned seq, dvref_obs* out, int cap, int* n_out, dvref_inst_obs* iout, int icap, int* n_iout) {
+    try {
+        auto* fe = static_cast<RefFrontEnd*>(p);
+        SemanticImage img = make_image(fe, gray0, gray1, time0, seq);
+        img.gray0_gpu.upload(img.gray0);
+        if (gray1) img.gray1_gpu.upload(img.gray1);
+        img.exist_inst = n_boxes > 0;
+        if (merge_mask) { img.merge_mask = cv::Mat(fe->rows, fe->cols, CV_8UC1, (void*)merge_mask).clone(); img.merge_mask_gpu.upload(img.merge_mask); }
+        if (inv_merge_mask) {
+            img.inv_merge_mask = cv::Mat(fe->rows, fe->cols, CV_8UC1, (void*)inv_merge_mask).clone();
+            img.inv_merge_mask_gpu.upload(img.inv_merge_mask);
+        }
+        img.disp = disp ? cv::Mat(fe->rows, fe->cols, CV_32FC1, (void*)disp).clone() : cv::Mat(fe->rows, fe->cols, CV_32FC1, cv::Scalar(0));
+        for (int i = 0; i < n_boxes; i++) {                                  // basic/semantic_image.cpp:48-59
+            auto b = std::make_shared<Box2D>();
+            b->id = i; b->track_id = (int)boxes[i].track_id; b->class_id = 0; b->score = 1.f;
+            b->min_pt = cv::Point2f((float)boxes[i].x, (float)boxes[i].y);
+            b->max_pt = cv::Point2f((float)(boxes[i].x + boxes[i].w), (float)(boxes[i].y + boxes[i].h));
+            b->rect = cv::Rect2f((float)boxes[i].x, (float)boxes[i].y, (float)boxes[i].w, (float)boxes[i].h);
+            b->roi = std::make_shared<InstRoi>();
+            b->roi->mask_cv = cv::Mat(boxes[i].h, boxes[i].w, CV_8UC1, (void*)boxes[i].mask, (size_t)boxes[i].mask_pitch).clone();
+            b->roi->mask_gpu.upload(b->roi->mask_cv);
+            b->roi->roi_gpu = img.gray0_gpu(b->rect);
+            b->roi->roi_gpu.download(b->roi->roi_gray);
+            img.boxes2d.push_back(b);
+        }
+        for (auto& [inst_id, inst] : fe->insts->instances) {                 // system/main.cpp:198-202
+            inst.is_curr_visible = false;
+            inst.box2d.reset();
+            inst.box3d.reset();
+        }
+        fe->insts->AddViodeInstances(img);                                   // :209
+        *n_out = flatten(fe->tracker->TrackSemanticImage(img), out, cap);    // :250
+        fe->insts->InstsTrack(img);                                          // :247
+        std::map<unsigned int, FeatureInstance> res = fe->insts->Output();   // :254
+        int n = 0;
+        for (auto& [key, fi] : res)
+            for (auto& [fid, f] : fi.features) {
+                if (n < icap) {
+                    dvref_inst_obs& o = iout[n];
+                    o.inst_id = key; o.id = fid; o.is_stereo = f->is_stereo ? 1 : 0; o.reserved = 0;
+                    for (int k = 0; k < 3; k++) { o.point[k] = f->point(k); o.point_right[k] = f->point_right(k); }
+                    for (int k = 0; k < 2; k++) { o.vel[k] = f->vel(k); o.vel_right[k] = f->vel_right(k); }
+                    o.disp = f->disp;
+                }
+                n++;
+            }
+        *n_iout = n;
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// background InstFeat state after a frame (for teacher-forced comparisons): ids, track_cnt, last_points
+int dvref_instance_count(void* p) {
+    auto* fe = static_cast<RefFrontEnd*>(p);
+    return fe->insts ? (int)fe->insts->instances.size() : 0;
+}
+// per-instance bookkeeping: writes up to cap rows of {key, lost_num, is_curr_visible, n_points}
+int dvref_instance_table(void* p, int* rows, int cap) {
+    auto* fe = static_cast<RefFrontEnd*>(p);
+    if (!fe->insts) return 0;
+    std::map<unsigned, const InstFeat*> sorted;
+    for (auto& [k, inst] : fe->insts->instances) sorted[k] = &inst;
+    int n = 0;
+    for (auto& [k, inst] : sorted) {
+        if (n < cap) {
+            rows[4 * n] = (int)k; rows[4 * n + 1] = inst->lost_num; rows[4 * n + 2] = inst->is_curr_visible ? 1 : 0;
+            rows[4 * n + 3] = (int)inst->last_points.size();
+        }
+        n++;
+    }
+    return n;
+}
+
+}  // extern "C"
