@@ -56,7 +56,7 @@ INST_OBS_DTYPE = np.dtype([("inst_id", np.uint32), ("id", np.uint32), ("is_stere
 
 class InstIn(C.Structure):
     _fields_ = [("track_id", C.c_uint32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
-                ("mask", C.c_void_p), ("mask_pitch", C.c_int32)]
+                ("mask", C.c_void_p), ("mask_pitch", C.c_int32), ("disp", C.c_void_p), ("disp_pitch", C.c_int32)]
 
 
 class State(C.Structure):

@@ -10,6 +10,7 @@
 // Order of feature-id assignment: the background step of the frame (dvfe_track_semantic_image) runs first, then
 // the instances in ascending instance id (the reference races the two threads on one counter and iterates an
 // unordered_map; see oracle/cv_front_end.py header).
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -38,6 +39,8 @@ struct InstHost {
     int cur_buf = 0;               // which of the two ROI buffers holds roi_gray
     int roi_w = 0, roi_h = 0;      // size of roi->roi_gray
     long long mask_off = -1;       // offset of this frame's ROI mask in the packed staging (-1: in the slot buffer)
+    const float* disp = nullptr;   // SemanticImage::disp of this frame (host, full image size) or null
+    int disp_pitch = 0;
 };
 
 struct InstStream {
@@ -108,12 +111,14 @@ struct InstCall {
     Staged<uint32_t> inst_id;
     dvfe_inst_obs* d_out = nullptr;      // [NS*cap]
     dvfe_inst_obs* h_out = nullptr;      // pinned
-    int* h_n = nullptr;                  // pinned [NS]
+    int* d_n = nullptr;                  // [NS] record counts of THIS call (snapshot of the point-set counts)
+    int* h_n = nullptr;                  // pinned [NS + 1]: counts, then the step's capacity-overflow word after the ROI detections
     cudaEvent_t ev_packed = nullptr;     // instance kernels of the call are done (compute stream)
     cudaEvent_t ev_up = nullptr;         // masks + descriptors of the call are on the device (upload stream)
     // host side of Output(), fixed when the call is enqueued
     int s0 = 0, s1 = 0;                  // streams whose Output() this call replaces
-    std::vector<std::pair<int, int>> plan;   // (stream, set) of the visible instances in output order
+    struct Planned { int stream, set; const float* disp; int disp_pitch; };
+    std::vector<Planned> plan;           // the visible instances in output order (+ the disparity map Output() reads)
     bool has_records = false;            // the call launched kernels (h_n / h_out are meaningful)
 };
 
@@ -158,8 +163,10 @@ int dvfe_tracker::init_instances() {
     for (int p = 0; p < 2; p++) {
         InstCall& C = I.call[p];
         DVFE_CHECK(dmalloc(&C.d_out, NS * I.cap));
+        DVFE_CHECK(dmalloc(&C.d_n, NS));
         DVFE_CUDA(cudaMallocHost((void**)&C.h_out, NS * I.cap * sizeof(dvfe_inst_obs)));
-        DVFE_CUDA(cudaMallocHost((void**)&C.h_n, NS * sizeof(int)));
+        DVFE_CUDA(cudaMallocHost((void**)&C.h_n, (NS + 1) * sizeof(int)));
+        memset(C.h_n, 0, (NS + 1) * sizeof(int));
         DVFE_CHECK(C.arena.alloc(NS * (sizeof(CropJob) + 2 * sizeof(PyrJob) + 2 * sizeof(LkGroup) + sizeof(ErodeJob) +
                                        sizeof(GfttJob) + 3 + sizeof(double) + sizeof(float2) + sizeof(uint32_t)) + 4096));
         C.arena.take(C.crop, (int)NS);
@@ -191,7 +198,7 @@ void dvfe_tracker::free_instances() {
     free_gftt_scratch(&I.gsc);
     for (int p = 0; p < 2; p++) {
         InstCall& C = I.call[p];
-        cudaFree(C.d_out); cudaFreeHost(C.h_out); cudaFreeHost(C.h_n);
+        cudaFree(C.d_out); cudaFree(C.d_n); cudaFreeHost(C.h_out); cudaFreeHost(C.h_n);
         C.arena.release();
         if (C.h_mask_stage) cudaFreeHost(C.h_mask_stage);
         cudaFree(C.d_mask_stage);
@@ -219,6 +226,34 @@ static void manage_instances(InstStream& S) {
     }
 }
 
+// Every box inside the image with a mask, and enough free slots for the new track ids: checked before anything is changed
+// (and, for the pipelined call, before the background step is enqueued), so a bad call leaves the tracker untouched.
+static int insts_validate(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of) {
+    InstanceState& I = *t->inst;
+    const int W = t->W, H = t->H;
+    for (int stream = s0; stream < s1; stream++) {
+        const InstStream& S = I.streams[stream];
+        const dvfe_inst_in* boxes = boxes_of[stream - s0];
+        std::vector<uint32_t> fresh;
+        for (int b = 0; b < n_of[stream - s0]; b++) {
+            const dvfe_inst_in& bx = boxes[b];
+            if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
+                bx.mask_pitch < bx.w || (bx.disp != nullptr && bx.disp_pitch < (int)(W * sizeof(float)))) {
+                dvfe_set_error("insts_track: stream %d box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask",
+                               stream, b, bx.x, bx.y, bx.w, bx.h, W, H);
+                return DVFE_ERR_INVALID;
+            }
+            if (S.insts.find(bx.track_id) == S.insts.end() && std::find(fresh.begin(), fresh.end(), bx.track_id) == fresh.end())
+                fresh.push_back(bx.track_id);
+        }
+        if (fresh.size() > S.free_slots.size()) {
+            dvfe_set_error("insts_track: more than max_instances=%d live instances in stream %d", I.MI, stream);
+            return DVFE_ERR_CAPACITY;
+        }
+    }
+    return DVFE_OK;
+}
+
 // InstsTrack for the streams [s0, s1): boxes_of[s - s0] / n_of[s - s0] / time_of[s - s0].  Every visible instance of
 // every stream is one job of each batched launch; one descriptor upload, one mask upload, one synchronisation.
 // defer = false: synchronous (the background step has been waited for; ends with a synchronisation and Output() ready).
@@ -227,6 +262,7 @@ static void manage_instances(InstStream& S) {
 static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of,
                                const double* time_of, bool defer) {
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    if (!defer) DVFE_CHECK(insts_validate(t, s0, s1, boxes_of, n_of));      // deferred: done before the background step
     if (!defer) DVFE_CHECK(t->wait_all());
     InstanceState& I = *t->inst;
     const int par = (int)((t->frames - 1) % 2);          // the step these instances belong to
@@ -245,6 +281,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
     bool any_clear = false;
     std::vector<char> exist(s1 - s0, 0);
     C.s0 = s0; C.s1 = s1; C.plan.clear(); C.has_records = false;
+    C.h_n[NS] = 0;
 
     for (int stream = s0; stream < s1; stream++) {
         InstStream& S = I.streams[stream];
@@ -260,19 +297,9 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
         for (auto& kv : S.insts) { kv.second.visible = false; kv.second.has_box = false; }
         for (int b = 0; b < n_boxes; b++) {
             const dvfe_inst_in& bx = boxes[b];
-            if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
-                bx.mask_pitch < bx.w) {
-                dvfe_set_error("insts_track: stream %d box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask",
-                               stream, b, bx.x, bx.y, bx.w, bx.h, W, H);
-                return DVFE_ERR_INVALID;
-            }
             auto it = S.insts.find(bx.track_id);
             if (it == S.insts.end()) {
-                if (S.free_slots.empty()) {
-                    dvfe_set_error("insts_track: more than max_instances=%d live instances in stream %d", MI, stream);
-                    return DVFE_ERR_CAPACITY;
-                }
-                InstHost in;
+                InstHost in;                               // a free slot exists: insts_validate
                 in.track_id = bx.track_id;
                 in.slot = S.free_slots.back();
                 S.free_slots.pop_back();
@@ -282,6 +309,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             InstHost& in = it->second;
             in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
             in.visible = true; in.has_box = true;
+            in.disp = bx.disp; in.disp_pitch = bx.disp_pitch;
             // inst.roi->mask_cv = det_box->roi->mask_cv : packed into the pinned staging, uploaded with one copy below
             const size_t bytes = (size_t)bx.w * bx.h;
             if (mask_used + bytes <= I.mask_stage_cap) {
@@ -359,7 +387,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             J.n = I.pts.n + set; J.next_id = t->d_next_id + stream;
             J.max_cnt = t->cfg.max_dynamic_cnt; J.min_needed = 1;
             J.disc_radius = t->cfg.min_dynamic_dist; J.min_dist = (float)t->cfg.min_dynamic_dist; J.quality = 0.01;
-            J.err = t->d_err;
+            J.err = t->d_err + par;
             // stereo job: TrackRightByPad — full images, points offset by rect.tl()
             LkGroup& R = C.lk_s.h[j];
             memset(&R, 0, sizeof(R));
@@ -399,7 +427,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
         // TrackRightByPad + RightUndistortedPts + RightPtsVelocity (:462-471), then the Output() records
         if (stereo_now) DVFE_CHECK(launch_lk(C.lk_s.d, nv, cap, t->cfg.lk_max_level, t->cfg.flow_back, st));
         DVFE_CHECK(launch_inst_post_pack(V, n_sets, cap, t->cam1, C.dt.d + set0, C.act_vis.d + set0, stereo_now ? 1 : 0,
-                                         C.inst_id.d + set0, C.d_out + o, st));
+                                         C.inst_id.d + set0, C.d_out + o, C.d_n + set0, st));
         C.has_records = true;
     }
     if (any_clear) DVFE_CHECK(launch_clear_sets(I.pts.n + set0, C.clear_flags.d + set0, n_sets, st));
@@ -411,7 +439,8 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             DVFE_CUDA(cudaStreamWaitEvent(os, C.ev_packed, 0));
         }
         const size_t o = set0 * cap;
-        DVFE_CUDA(cudaMemcpyAsync(C.h_n + set0, I.pts.n + set0, n_sets * sizeof(int), cudaMemcpyDeviceToHost, os));
+        DVFE_CUDA(cudaMemcpyAsync(C.h_n + set0, C.d_n + set0, n_sets * sizeof(int), cudaMemcpyDeviceToHost, os));
+        DVFE_CUDA(cudaMemcpyAsync(C.h_n + NS, t->d_err + par, sizeof(int), cudaMemcpyDeviceToHost, os));
         DVFE_CUDA(cudaMemcpyAsync(C.h_out + o, C.d_out + o, (size_t)n_sets * cap * sizeof(dvfe_inst_obs),
                                   cudaMemcpyDeviceToHost, os));
     }
@@ -431,7 +460,7 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
         for (auto& kv : S.insts) {
             const InstHost& in = kv.second;
             if (in.lost_num > 0 || !in.visible) continue;
-            C.plan.emplace_back(stream, (int)(base_set + in.slot));
+            C.plan.push_back({stream, (int)(base_set + in.slot), in.disp, in.disp_pitch});
         }
         S.last_time = time_of[stream - s0];
     }
@@ -450,10 +479,25 @@ int dvfe_tracker::finish_instances(int par) {
     InstCall& C = I.call[par];
     for (int s = C.s0; s < C.s1; s++) I.streams[s].out.clear();
     for (const auto& e : C.plan) {
-        std::vector<dvfe_inst_obs>& out = I.streams[e.first].out;
-        const size_t set = (size_t)e.second;
+        std::vector<dvfe_inst_obs>& out = I.streams[e.stream].out;
+        const size_t set = (size_t)e.set;
         const int n = C.has_records ? C.h_n[set] : 0;
+        const size_t first = out.size();
         out.insert(out.end(), C.h_out + set * I.cap, C.h_out + set * I.cap + n);
+        if (e.disp != nullptr)
+            // feat->disp = prev_img.disp.at<float>(inst.curr_points[i]) (front_end/dynamic_tracker.cpp:547): a lookup in the
+            // caller's full-size map with the ROI-LOCAL position, rounded to the nearest pixel (ties to even) as Mat::at(Point2f)
+            // does.  A table lookup in a host input, done where the records land.
+            for (size_t i = first; i < out.size(); i++) {
+                const long col = lrint(out[i].uv[0]), row = lrint(out[i].uv[1]);
+                out[i].disp = (double)*reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(e.disp) +
+                                                                      (size_t)row * e.disp_pitch + (size_t)col * sizeof(float));
+            }
+    }
+    if (C.has_records && C.h_n[(size_t)B * I.MI] != 0) {
+        dvfe_set_error("corner detection on an instance ROI: more local maxima than the candidate buffer holds; the selection "
+                       "of this frame was truncated");
+        return DVFE_ERR_CAPACITY;
     }
     return DVFE_OK;
 }
@@ -522,6 +566,7 @@ extern "C" int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, co
         off += (size_t)n_boxes[s];
     }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
+    DVFE_CHECK(insts_validate(t, 0, t->B, of.data(), n_boxes));
     DVFE_CHECK(t->semantic_submit(left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0));
     return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0, true);
 }

@@ -214,10 +214,14 @@ int launch_right_post_pack(const PointSetArrays& S, int n_sets, int cap, const C
 // (front_end/dynamic_tracker.cpp:462-471, 521-577).  One record per point at out[set*cap + i]; ids ascend with i.
 __global__ void __launch_bounds__(128) k_inst_post_pack(PointSetArrays S, int cap, CamParams cam1, const double* __restrict__ dt,
                                                         const uint8_t* __restrict__ active, int stereo_now,
-                                                        const uint32_t* __restrict__ inst_id, dvfe_inst_obs* __restrict__ out) {
+                                                        const uint32_t* __restrict__ inst_id, dvfe_inst_obs* __restrict__ out,
+                                                        int* __restrict__ n_out) {
     const int set = blockIdx.y;
     if (!active[set]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // the record count of this call, snapshotted into the call's own buffer: S.n is rewritten by the next step while the
+    // download stream may still be reading
+    if (i == 0) n_out[set] = S.n[set];
     if (i >= S.n[set]) return;
     const size_t k = (size_t)set * cap + i;
     const bool has_r = stereo_now && S.rstatus[k] != 0;
@@ -251,10 +255,10 @@ __global__ void __launch_bounds__(128) k_inst_post_pack(PointSetArrays S, int ca
 
 int launch_inst_post_pack(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam1, const double* d_dt,
                           const uint8_t* d_active, int stereo_now, const uint32_t* d_inst_id, dvfe_inst_obs* out,
-                          cudaStream_t st) {
+                          int* d_n_out, cudaStream_t st) {
     if (n_sets <= 0) return DVFE_OK;
     dim3 grid((cap + 127) / 128, n_sets);
-    DVFE_LAUNCH(k_inst_post_pack, grid, 128, 0, st, S, cap, cam1, d_dt, d_active, stereo_now, d_inst_id, out);
+    DVFE_LAUNCH(k_inst_post_pack, grid, 128, 0, st, S, cap, cam1, d_dt, d_active, stereo_now, d_inst_id, out, d_n_out);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

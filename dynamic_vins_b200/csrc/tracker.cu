@@ -185,7 +185,7 @@ int dvfe_tracker::init() {
         DVFE_CUDA(cudaMemcpy(d_next_id, ones.data(), B * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     DVFE_CHECK(dmalloc(&d_dt, (size_t)B));
-    DVFE_CHECK(dmalloc(&d_err, (size_t)1));
+    DVFE_CHECK(dmalloc(&d_err, (size_t)2));
     prev_time.assign(B, 0.0);
     for (int p = 0; p < 2; p++) {
         DVFE_CHECK(dmalloc(&d_obs[p], (size_t)B * 2 * cap));
@@ -262,7 +262,7 @@ int dvfe_tracker::init() {
                 J.disc_radius = cfg.min_dist;
                 J.min_dist = (float)cfg.min_dist;
                 J.quality = 0.01;
-                J.err = d_err;
+                J.err = d_err + (ph % 2);       // the error word of the step this job table belongs to
             }
             DVFE_CHECK(dmalloc(&d_jobs[ph][kind], (size_t)B));
             DVFE_CUDA(cudaMemcpy(d_jobs[ph][kind], jobs.data(), B * sizeof(GfttJob), cudaMemcpyHostToDevice));
@@ -325,6 +325,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     const bool stereo_now = cfg.stereo && (d_right != nullptr || (level0_in_place && has_right));
     for (int s = 0; s < B; s++) h_dt[par][s] = time0[s] - prev_time[s];       // cur_time - prev_time
     DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt[par], B * sizeof(double), cudaMemcpyHostToDevice, st));
+    // the capacity flag is per step: cleared here, reported by the wait for THIS step only (the buffers of step k-2 have
+    // been read back before slot `par` is reused)
+    DVFE_CUDA(cudaMemsetAsync(d_err + par, 0, sizeof(int), st));
     prof_step[par] = prof;
     auto mark = [&](int i) { if (prof) cudaEventRecord(ev[par][i], st); };
 
@@ -375,7 +378,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     DVFE_CUDA(cudaEventRecord(ev_packed[par], st));
     DVFE_CUDA(cudaStreamWaitEvent(ds, ev_packed[par], 0));
     DVFE_CUDA(cudaMemcpyAsync(h_nobs[par], d_nobs[par], B * sizeof(int), cudaMemcpyDeviceToHost, ds));
-    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par] + B, d_err, sizeof(int), cudaMemcpyDeviceToHost, ds));
+    DVFE_CUDA(cudaMemcpyAsync(h_nobs[par] + B, d_err + par, sizeof(int), cudaMemcpyDeviceToHost, ds));
     DVFE_CUDA(cudaMemcpyAsync(h_obs[par], d_obs[par], (size_t)B * 2 * cap * sizeof(dvfe_obs), cudaMemcpyDeviceToHost, ds));
     if (prof) cudaEventRecord(ev[par][ST_D2H + 1], ds);
     DVFE_CUDA(cudaEventRecord(ev_done[par], ds));
@@ -405,7 +408,7 @@ int dvfe_tracker::wait_one() {
     }
     if (h_nobs[par][B] != 0) {
         dvfe_set_error("corner detection: more local maxima than the candidate buffer holds (W*H/4 + 4096); "
-                       "the selection of some frame was truncated");
+                       "the corner selection of this frame was truncated in at least one stream");
         return DVFE_ERR_CAPACITY;
     }
     return DVFE_OK;

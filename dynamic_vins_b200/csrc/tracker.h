@@ -52,8 +52,8 @@ struct dvfe_tracker {
     dvfe_obs* d_obs[2] = {nullptr, nullptr};         // one per in-flight step
     dvfe_obs* h_obs[2] = {nullptr, nullptr};         // pinned, one per in-flight step
     int* d_nobs[2] = {nullptr, nullptr};
-    int* h_nobs[2] = {nullptr, nullptr};             // [B + 1]: counts, then the sticky device error word
-    int* d_err = nullptr;
+    int* h_nobs[2] = {nullptr, nullptr};             // [B + 1]: counts, then the device error word of that step
+    int* d_err = nullptr;                            // [2]: one capacity-overflow flag per in-flight step
     int out_slot = 0;                                // which h_obs holds the newest completed step
     cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {}, ev_resp[2] = {}, ev_rpyr[2] = {};
     uint8_t *d_region = nullptr, *d_region_tmp = nullptr;

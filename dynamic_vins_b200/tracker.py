@@ -167,30 +167,35 @@ class BatchTracker:
         L.check(L.lib().dvfe_track_semantic_image(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W * self.ch,
                                                   self.W * self.ch, L.ptr(e), L.ptr(t)))
 
-    def insts_track(self, stream: int, boxes: Sequence[dict], time0: float) -> None:
-        """boxes: [{track_id, rect=(x,y,w,h), mask (h,w) uint8}] (SemanticImage::boxes2d)."""
-        arr = (L.InstIn * max(1, len(boxes)))()
-        keep = []
-        for i, b in enumerate(boxes):
-            m = np.ascontiguousarray(b["mask"], np.uint8)
-            keep.append(m)
-            x, y, w, h = b["rect"]
-            arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
-            arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
+    def insts_track(self, stream: int, boxes: Sequence[dict], time0: float, disp=None) -> None:
+        """boxes: [{track_id, rect=(x,y,w,h), mask (h,w) uint8}] (SemanticImage::boxes2d); disp: SemanticImage::disp of the
+        frame (H x W float32) or None."""
+        arr, _counts, keep = self.marshal_boxes([boxes], None if disp is None else [disp])
+        self._keep_sync = keep
         L.check(L.lib().dvfe_insts_track(self._h, stream, arr, len(boxes), float(time0)))
 
     @staticmethod
-    def marshal_boxes(boxes_per_stream: Sequence[Sequence[dict]]):
-        """the dvfe_inst_in array + per-stream counts of a frame's box lists (a C++ caller holds these natively)"""
-        flat = [b for bs in boxes_per_stream for b in bs]
-        arr = (L.InstIn * max(1, len(flat)))()
+    def marshal_boxes(boxes_per_stream: Sequence[Sequence[dict]], disp_per_stream=None):
+        """the dvfe_inst_in array + per-stream counts of a frame's box lists (a C++ caller holds these natively);
+        disp_per_stream: optional per-stream disparity maps (H x W float32)"""
+        n = sum(len(bs) for bs in boxes_per_stream)
+        arr = (L.InstIn * max(1, n))()
         keep = []
-        for i, b in enumerate(flat):
-            m = np.ascontiguousarray(b["mask"], np.uint8)
-            keep.append(m)
-            x, y, w, h = b["rect"]
-            arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
-            arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
+        i = 0
+        for s, bs in enumerate(boxes_per_stream):
+            d = None
+            if disp_per_stream is not None and disp_per_stream[s] is not None:
+                d = np.ascontiguousarray(disp_per_stream[s], np.float32)
+                keep.append(d)
+            for b in bs:
+                m = np.ascontiguousarray(b["mask"], np.uint8)
+                keep.append(m)
+                x, y, w, h = b["rect"]
+                arr[i].track_id, arr[i].x, arr[i].y, arr[i].w, arr[i].h = int(b["track_id"]), x, y, w, h
+                arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
+                if d is not None:
+                    arr[i].disp, arr[i].disp_pitch = d.ctypes.data, d.strides[0]
+                i += 1
         counts = np.asarray([len(bs) for bs in boxes_per_stream], np.int32)
         return arr, counts, keep
 

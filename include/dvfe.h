@@ -83,7 +83,8 @@ typedef struct dvfe_inst_obs {
     double point_right[3];
     double vel_right[2];
     double uv[2];               /* ROI-local pixel position (curr_points) */
-    double disp;                /* 0: no disparity map on this path (reference quirk Q8) */
+    double disp;                /* prev_img.disp.at<float>(curr_points[i]): the caller's map read at the ROI-LOCAL position
+                                 * (front_end/dynamic_tracker.cpp:547, reference quirk Q8); 0 when dvfe_inst_in::disp is NULL */
 } dvfe_inst_obs;
 
 /* One detected instance of a frame: Box2D + InstRoi (basic/box2d.h:24-56), as produced by
@@ -94,6 +95,10 @@ typedef struct dvfe_inst_in {
     int32_t x, y, w, h;         /* Box2D::rect (integer valued) */
     const uint8_t* mask;        /* HOST pointer, h rows x w cols, 255 = object (InstRoi::mask_cv) */
     int32_t mask_pitch;
+    const float* disp;          /* HOST pointer to SemanticImage::disp of this frame (CV_32F, full image size, the same for
+                                 * every box of the stream) or NULL; must stay valid until the step's records are read
+                                 * (dvfe_insts_track returns / dvfe_wait) */
+    int32_t disp_pitch;         /* bytes per row of disp */
 } dvfe_inst_in;
 
 typedef struct dvfe_tracker dvfe_tracker;
