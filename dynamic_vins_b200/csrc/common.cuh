@@ -96,6 +96,9 @@ struct LkGroup {
     int mask_pitch;
     float offx, offy;        // added to pts1 first (InstFeat::TrackRightByPad)
     unsigned* tcache;        // nullable: forward-pass template cache, LK_TCACHE_WORDS words per (point, level)
+    unsigned* tcache_bwd;    // nullable: backward-pass template cache of the temporal call (same layout, indexed by the point's
+                             // index in that call)
+    const int* old_idx;      // nullable: per point, its index in the temporal call of this step (-1: new point)
 };
 // Template cache block of one (point, level): lane-major words, word j of lane l at [j * 32 + l]:
 //   0..13  (Ix, Iy) int16 pairs of the lane's 14 window pixels;  14, 15  the lane's sum I*Ix, sum I*Iy;
@@ -103,3 +106,7 @@ struct LkGroup {
 #define LK_TCACHE_WORDS (17 * 32)
 #define LK_TCACHE_WRITE 1    // forward pass stores its templates (stereo call: template = current left image at the current points)
 #define LK_TCACHE_READ 2     // forward pass loads them (next temporal call: same image, same points)
+// The backward templates of the temporal call (current left image at the tracked positions, levels <= its backward maxLevel)
+// are bit for bit the forward templates of the same step's stereo call at those levels for the points that survive:
+#define LK_TCACHE_WRITE_BWD 4    // backward pass stores its templates in tcache_bwd (temporal call)
+#define LK_TCACHE_READ_BWD 8     // forward pass loads levels <= reuse_max_level from tcache_bwd[old_idx] (stereo call)

@@ -57,16 +57,18 @@ int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cuda
 
 // lk.cu
 int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
-              int back_max_level = 1, double fb_threshold = 0.5, int tcache_flags = 0);
+              int back_max_level = 1, double fb_threshold = 0.5, int tcache_flags = 0, int reuse_max_level = -1);
 
 // gftt.cu
 struct GfttJob {                 // one detection problem (a stream's image, or one instance ROI)
     const uint8_t* img;          // u8 image, pixel (0,0)
     int img_pitch;
     int w, h;
+    int img_bordered;            // 1: img is pixel (0,0) of a padded pyramid level (REFLECT_101 border readable, rows 4-byte aligned)
     const uint8_t* region_mask;  // nullable (all 255)
     int region_pitch;
-    uint8_t* mask;               // detection mask scratch (w x h, pitch mask_pitch): region minus discs
+    uint8_t* mask;               // detection mask scratch (w x h, pitch mask_pitch): region minus discs; only materialised
+                                 // for an external response map (eig_in), the fused path builds it per strip on chip
     int mask_pitch;
     float* eig;                  // unused by the fused path (kept for layout stability)
     const float* eig_in;         // nullable: externally supplied response map (seam op)
@@ -75,8 +77,9 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     unsigned long long* cand3;   // third buffer [cand_cap]
     int cand_cap;
     int* cell_count;             // scratch [n_cells + 1]
-    int* counters;               // [8]: 0 n_precand, 1 masked max (ordered int), 2 overflow flag, 3 n above threshold,
-                                 //      4 n_new, 5 M examined, 6 n_accepted
+    int* counters;               // [8]: 0 n_precand, 1 masked max (ordered int), 2 overflow flag (0..2 are reset by the selection
+                                 //      kernel for the next launch), 3 n above threshold, 4 n_new, 5 M examined, 6 n_accepted,
+                                 //      7 overflow flag of the last launch
     uint8_t* state;              // scratch [cand_cap]
     int* err;                    // nullable: sticky error word (bit 0: candidate buffer overflow)
     // point set the discs come from and new corners are appended to

@@ -40,6 +40,23 @@ __device__ __forceinline__ long long warp_sum_i64(int v) {
     return (long long)shi * 65536ll + (long long)slo;
 }
 
+// Exact sum of 32 int32 lanes as a float (one rounding), scaled.  When every lane is below 2^26 in magnitude the sum fits
+// an int32: one redux and a 32-bit conversion; otherwise the two-halves path.  `small` is warp-uniform.
+__device__ __forceinline__ float warp_sum_f(int v, bool small, float scale) {
+    if (small) return __int2float_rn(__reduce_add_sync(0xffffffffu, v)) * scale;
+    return __ll2float_rn(warp_sum_i64(v)) * scale;
+}
+__device__ __forceinline__ unsigned lk_big(int v) { return (unsigned)(v + (1 << 26)) >> 27; }      // != 0 iff v outside [-2^26, 2^26)
+
+// 8 consecutive bytes at byte offset `o` from the 4-byte aligned `base` (any alignment of o): lo = bytes 0..3, hi = bytes 4..7
+__device__ __forceinline__ void load8o(const uint8_t* __restrict__ base, int o, unsigned& lo, unsigned& hi) {
+    const unsigned* wp = reinterpret_cast<const unsigned*>(base + (o & ~3));
+    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+    const int sh = (o & 3) * 8;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
 __device__ __forceinline__ void lk_weights(float a, float b, int& iw00, int& iw01, int& iw10, int& iw11) {
     iw00 = __float2int_rn((1.f - a) * (1.f - b) * (float)(1 << W_BITS));
     iw01 = __float2int_rn(a * (1.f - b) * (float)(1 << W_BITS));
@@ -99,13 +116,48 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
     return d;
 }
 
-#define LK_WIN_BYTES (24 * 24 + 16)
+// Staged template window: the 24 x 24 bytes around the patch (rows ipy-1.., columns ipx-1..) are copied as the 7 aligned
+// words per row that contain them, so the copy is pure cp.async (no registers, no shifts); the consumer adds the column
+// misalignment (ipx-1) & 3 to its own.  Pitch 7 words (odd: the 21 window rows fall into different banks).
+#define LK_WIN_PITCH 28
+#define LK_WIN_BYTES (24 * LK_WIN_PITCH + 16)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// window origin of the template at `level` for source point `src` (cv::detail::LKTrackerInvoker: prevPt * scale - halfWin)
+__device__ __forceinline__ bool lk_window_origin(float2 src, int level, int lw, int lh, float& prevx, float& prevy, int& ipx, int& ipy) {
+    const float scale = __int_as_float((127 - level) << 23);      // (float)(1./(1 << level))
+    prevx = src.x * scale - DVFE_HALF_WIN;
+    prevy = src.y * scale - DVFE_HALF_WIN;
+    ipx = __float2int_rd(prevx); ipy = __float2int_rd(prevy);
+    return !(ipx < -DVFE_WIN || ipx >= lw || ipy < -DVFE_WIN || ipy >= lh);
+}
+
+// enqueue the asynchronous copy of one level's template window (all lanes; no wait)
+__device__ __forceinline__ void lk_stage_window_async(uint8_t* __restrict__ win, const uint8_t* __restrict__ Ipx, int pitch, int ipx, int ipy,
+                                                      int lane) {
+    const uint8_t* __restrict__ src = Ipx + (ptrdiff_t)(ipy - 1) * pitch + ((ipx - 1) & ~3);
+#pragma unroll
+    for (int t0 = 0; t0 < 24 * 7; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < 24 * 7) {
+            const int r = t / 7, w4 = (t - r * 7) * 4;
+            cp_async4(win + r * LK_WIN_PITCH + w4, src + r * pitch + w4);
+        }
+    }
+}
 
 // Template of one run (7 pixels of window row `ry`, columns x0..x0+6) from the staged 24x24 window:
 // Scharr derivatives at the 8x2 taps the run's bilinear samples touch, computed with dp4a on 4-byte windows
 // (row filter and the vertical 3/10/3 resp. -1/+1 weights folded into the int8 tap weights), then the 14-bit
 // fixed-point bilinear samples of I, Ix, Iy.
-__device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win, int ry, int x0, bool valid, bool interior,
+__device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win, int ry, int x0, int xs, bool valid, bool interior,
                                                 int ipx, int ipy, int lw, int lh, int iw00, int iw01, int iw10, int iw11,
                                                 int (&Ix)[LK_RUN], int (&Iy)[LK_RUN], int& c1, int& c2, int& sA11,
                                                 int& sA12, int& sA22) {
@@ -113,11 +165,11 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
 #pragma unroll
     for (int j = 0; j < 8; j++) { gx0[j] = 0; gx1[j] = 0; gy0[j] = 0; gy1[j] = 0; }
     unsigned Wa[8], Wb[8];                   // 4-byte windows of image rows ry+1 (= window row of the pixels) and ry+2
-    const int sh = (x0 & 3) * 8;
+    const int sh = (xs & 3) * 8;           // xs = x0 + the staged window's column misalignment
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         // image row (ipy - 1 + ry + r): 12 bytes from window column x0 (= image column ipx - 1 + x0)
-        const unsigned* wp = reinterpret_cast<const unsigned*>(win + (ry + r) * 24 + (x0 & ~3));
+        const unsigned* wp = reinterpret_cast<const unsigned*>(win + (ry + r) * LK_WIN_PITCH + (xs & ~3));
         const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
         unsigned R[3];
         R[0] = __funnelshift_r(w0, w1, sh); R[1] = __funnelshift_r(w1, w2, sh); R[2] = __funnelshift_r(w2, w3, sh);
@@ -161,13 +213,13 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
 }
 
 __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const LkGroup* __restrict__ groups, int max_level, int flow_back,
-                                                                                    int back_max_level, double fb_threshold, int tcache_flags) {
-    __shared__ __align__(16) uint8_t s_win[LK_WARPS][LK_WIN_BYTES];
+                                                                                    int back_max_level, double fb_threshold, int tcache_flags,
+                                                                                    int reuse_max_level) {
+    __shared__ __align__(16) uint8_t s_win[LK_WARPS][2][LK_WIN_BYTES];      // two windows per warp: this level / the next one
     const LkGroup& G = groups[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * LK_WARPS + warp;
     if (i >= *G.n) return;
-    uint8_t* __restrict__ win = s_win[warp];
     const float FLT_SCALE = 1.f / (1 << 20);
 
     // this lane's two runs: run r -> window row r / 3, first column 7 * (r % 3)
@@ -182,6 +234,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
 
     float2 p2 = make_float2(0.f, 0.f), rev = p1;
     int status = 1;
+    // index of this point in the temporal call of the same step, whose backward pass left its templates in tcache_bwd
+    const int old_i = ((tcache_flags & LK_TCACHE_READ_BWD) && G.old_idx != nullptr && G.tcache_bwd != nullptr) ? G.old_idx[i] : -1;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         // pass 0: forward  img1 -> img2 from p1;  pass 1: backward img2 -> img1 from p2, initial guess p1
@@ -191,25 +245,56 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
         const int lmax = pass ? (back_max_level < top ? back_max_level : top) : (max_level < top ? max_level : top);
         float outx = pass ? p1.x : 0.f, outy = pass ? p1.y : 0.f;      // nextPts[ptidx]
         int st = 1;
+        // The template windows of a pass depend only on the source point: the window of the next level is fetched with
+        // cp.async while this level iterates, so only the first window of a pass is waited for.
+        const bool stage = !(pass == 0 && G.tcache != nullptr && (tcache_flags & LK_TCACHE_READ));
+        // forward levels whose template comes from the temporal call's backward pass need no window either
+        const int cached_below = (pass == 0 && old_i >= 0) ? reuse_max_level : -1;
+        if (stage) {
+            const PyrLevel L = G.desc.lv[lmax];
+            float fx, fy; int wx, wy;
+            __syncwarp();
+            if (lmax > cached_below && lk_window_origin(src, lmax, L.w, L.h, fx, fy, wx, wy))
+                lk_stage_window_async(s_win[warp][0], pyrI + L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX, L.pitch, wx, wy, lane);
+            cp_async_commit();
+        } else if (lane < 17) {
+            // cached templates: 17 lines of 128 B per level; pull the lower levels towards L2 while the top level iterates
+            const unsigned* __restrict__ tb = G.tcache + (size_t)i * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS + lane * 32;
+            for (int l = lmax - 1; l >= 0; --l) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + l * LK_TCACHE_WORDS));
+        }
 #pragma unroll 1
         for (int level = lmax; level >= 0; --level) {
             const PyrLevel L = G.desc.lv[level];
             const uint8_t* __restrict__ Ipx = pyrI + L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;
             const uint8_t* __restrict__ Jpx = pyrJ + L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;
             const float scale = __int_as_float((127 - level) << 23);      // (float)(1./(1 << level))
-            float prevx = src.x * scale, prevy = src.y * scale;
+            uint8_t* __restrict__ win = s_win[warp][(lmax - level) & 1];
+            if (stage) {
+                if (level > 0) {
+                    const PyrLevel Ln = G.desc.lv[level - 1];
+                    float fx, fy; int wx, wy;
+                    if (level - 1 > cached_below && lk_window_origin(src, level - 1, Ln.w, Ln.h, fx, fy, wx, wy))
+                        lk_stage_window_async(s_win[warp][(lmax - level + 1) & 1], pyrI + Ln.offset + (size_t)DVFE_PADY * Ln.pitch + DVFE_PADX,
+                                              Ln.pitch, wx, wy, lane);
+                    cp_async_commit();
+                    cp_async_wait<1>();          // everything but the group just committed: this level's window is in
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+            }
+            float prevx, prevy;
+            int ipx, ipy;
+            const bool in_range = lk_window_origin(src, level, L.w, L.h, prevx, prevy, ipx, ipy);
             float nextx, nexty;
             if (level == lmax) {
                 if (pass) { nextx = outx * scale; nexty = outy * scale; }   // OPTFLOW_USE_INITIAL_FLOW
-                else { nextx = prevx; nexty = prevy; }
+                else { nextx = src.x * scale; nexty = src.y * scale; }
             } else {
                 nextx = outx * 2.f; nexty = outy * 2.f;
             }
             outx = nextx; outy = nexty;
-
-            prevx -= DVFE_HALF_WIN; prevy -= DVFE_HALF_WIN;
-            const int ipx = __float2int_rd(prevx), ipy = __float2int_rd(prevy);
-            if (ipx < -DVFE_WIN || ipx >= L.w || ipy < -DVFE_WIN || ipy >= L.h) {
+            if (!in_range) {
                 if (level == 0) st = 0;
                 continue;
             }
@@ -219,50 +304,56 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
             // The forward template of a stereo call (current left image at the current points) is bit for bit the
             // forward template of the next temporal call (same image, now `prev`, same points): the stereo call
             // stores it, the temporal call loads it instead of rebuilding it (4 of the 12 templates of a frame).
-            unsigned* __restrict__ tc = (pass == 0 && G.tcache != nullptr && level < DVFE_MAX_PYR_LEVELS)
-                                            ? G.tcache + ((size_t)i * DVFE_MAX_PYR_LEVELS + level) * LK_TCACHE_WORDS + lane : nullptr;
-            if (tc != nullptr && (tcache_flags & LK_TCACHE_READ)) {
+            // Where this (pass, level)'s template comes from / goes to.  src_tc: load instead of building; dst_tc: store.
+            const size_t tco = ((size_t)i * DVFE_MAX_PYR_LEVELS + level) * LK_TCACHE_WORDS + lane;
+            const unsigned* __restrict__ src_tc = nullptr;
+            unsigned* __restrict__ dst_tc = nullptr;
+            if (pass == 0) {
+                if (G.tcache != nullptr && (tcache_flags & LK_TCACHE_READ)) src_tc = G.tcache + tco;
+                else if (level <= cached_below)
+                    src_tc = G.tcache_bwd + ((size_t)old_i * DVFE_MAX_PYR_LEVELS + level) * LK_TCACHE_WORDS + lane;
+                if (G.tcache != nullptr && (tcache_flags & LK_TCACHE_WRITE)) dst_tc = G.tcache + tco;
+            } else if (G.tcache_bwd != nullptr && (tcache_flags & LK_TCACHE_WRITE_BWD)) {
+                dst_tc = G.tcache_bwd + tco;
+            }
+            if (src_tc != nullptr) {
 #pragma unroll
                 for (int j = 0; j < LK_RUN; j++) {
-                    const int w0 = (int)tc[j * 32], w1 = (int)tc[(LK_RUN + j) * 32];
+                    const int w0 = (int)src_tc[j * 32], w1 = (int)src_tc[(LK_RUN + j) * 32];
                     Ix0[j] = (w0 << 16) >> 16; Iy0[j] = w0 >> 16;
                     Ix1[j] = (w1 << 16) >> 16; Iy1[j] = w1 >> 16;
                 }
-                c1 = (int)tc[14 * 32]; c2 = (int)tc[15 * 32];
-                const unsigned m = tc[16 * 32];
+                c1 = (int)src_tc[14 * 32]; c2 = (int)src_tc[15 * 32];
+                const unsigned m = src_tc[16 * 32];
                 A11 = __uint_as_float(__shfl_sync(0xffffffffu, m, 0));
                 A12 = __uint_as_float(__shfl_sync(0xffffffffu, m, 1));
                 A22 = __uint_as_float(__shfl_sync(0xffffffffu, m, 2));
             } else {
-                // ---- stage the 24x24 window of I around the patch (rows ipy-1.., columns ipx-1..) ----
-                __syncwarp();
-                for (int t = lane; t < 24 * 6; t += 32) {          // 24 rows x 6 words, rows are 4-byte aligned in smem
-                    const int r = t / 6, c4 = (t - r * 6) * 4;
-                    *reinterpret_cast<unsigned*>(win + r * 24 + c4) = load4(Ipx + (ipy - 1 + r) * L.pitch, ipx - 1 + c4);
-                }
-                __syncwarp();
-
+                const int wm = (ipx - 1) & 3;          // column misalignment of the staged window
                 const float a = prevx - (float)ipx, b = prevy - (float)ipy;
                 int iw00, iw01, iw10, iw11;
                 lk_weights(a, b, iw00, iw01, iw10, iw11);
                 const bool interior = ipx >= 0 && ipy >= 0 && ipx + 22 <= L.w && ipy + 22 <= L.h;
                 int sA11 = 0, sA12 = 0, sA22 = 0;
-                lk_template_run(win, ry0, rx0, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
+                lk_template_run(win, ry0, rx0, rx0 + wm, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
                                 sA11, sA12, sA22);
-                lk_template_run(win, ry1, rx1, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
+                lk_template_run(win, ry1, rx1, rx1 + wm, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
                                 sA11, sA12, sA22);
-                A11 = __ll2float_rn(warp_sum_i64(sA11)) * FLT_SCALE;
-                A12 = __ll2float_rn(warp_sum_i64(sA12)) * FLT_SCALE;
-                A22 = __ll2float_rn(warp_sum_i64(sA22)) * FLT_SCALE;
-                if (tc != nullptr && (tcache_flags & LK_TCACHE_WRITE)) {
-#pragma unroll
-                    for (int j = 0; j < LK_RUN; j++) {
-                        tc[j * 32] = __byte_perm((unsigned)Ix0[j], (unsigned)Iy0[j], 0x5410);
-                        tc[(LK_RUN + j) * 32] = __byte_perm((unsigned)Ix1[j], (unsigned)Iy1[j], 0x5410);
-                    }
-                    tc[14 * 32] = (unsigned)c1; tc[15 * 32] = (unsigned)c2;
-                    tc[16 * 32] = __float_as_uint(lane == 0 ? A11 : (lane == 1 ? A12 : A22));
+                {
+                    const bool small = !__any_sync(0xffffffffu, (lk_big(sA11) | lk_big(sA12) | lk_big(sA22)) != 0u);
+                    A11 = warp_sum_f(sA11, small, FLT_SCALE);
+                    A12 = warp_sum_f(sA12, small, FLT_SCALE);
+                    A22 = warp_sum_f(sA22, small, FLT_SCALE);
                 }
+            }
+            if (dst_tc != nullptr && dst_tc != src_tc) {
+#pragma unroll
+                for (int j = 0; j < LK_RUN; j++) {
+                    dst_tc[j * 32] = __byte_perm((unsigned)Ix0[j], (unsigned)Iy0[j], 0x5410);
+                    dst_tc[(LK_RUN + j) * 32] = __byte_perm((unsigned)Ix1[j], (unsigned)Iy1[j], 0x5410);
+                }
+                dst_tc[14 * 32] = (unsigned)c1; dst_tc[15 * 32] = (unsigned)c2;
+                dst_tc[16 * 32] = __float_as_uint(lane == 0 ? A11 : (lane == 1 ? A12 : A22));
             }
             float D = A11 * A22 - A12 * A12;
             const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * DVFE_WIN * DVFE_WIN);
@@ -272,7 +363,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
             }
             D = 1.f / D;
             nextx -= DVFE_HALF_WIN; nexty -= DVFE_HALF_WIN;
-            const int roff0 = ry0 * L.pitch, roff1 = ry1 * L.pitch;
+            // byte offsets of this lane's two runs inside the search window (rows are 16-byte aligned, so the alignment of a
+            // linear offset is the alignment of its column)
+            const int off0 = ry0 * L.pitch + rx0, off1 = ry1 * L.pitch + rx1;
             float pdx = 0.f, pdy = 0.f;
 #pragma unroll 1
             for (int it = 0; it < 30; it++) {
@@ -286,29 +379,32 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 lk_weights(a, b, iw00, iw01, iw10, iw11);
                 const int W01 = (iw00 & 0xffff) | (iw01 << 16);
                 const int W23 = (iw10 & 0xffff) | (iw11 << 16);
-                const uint8_t* __restrict__ Jw = Jpx + iny * L.pitch;
+                const int o = iny * L.pitch + inx;
                 // sum (J - I) * Ix = sum J * Ix - sum I * Ix
                 int sb1 = -c1, sb2 = -c2;
                 {
                     unsigned A_lo, A_hi, B_lo, B_hi;
-                    load8(Jw + roff0, inx + rx0, A_lo, A_hi);
-                    load8(Jw + roff0 + L.pitch, inx + rx0, B_lo, B_hi);
+                    load8o(Jpx, o + off0, A_lo, A_hi);
+                    load8o(Jpx, o + off0 + L.pitch, B_lo, B_hi);
                     LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, Ix0, Iy0);
                 }
                 {
                     unsigned A_lo, A_hi, B_lo, B_hi;
-                    load8(Jw + roff1, inx + rx1, A_lo, A_hi);
-                    load8(Jw + roff1 + L.pitch, inx + rx1, B_lo, B_hi);
+                    load8o(Jpx, o + off1, A_lo, A_hi);
+                    load8o(Jpx, o + off1 + L.pitch, B_lo, B_hi);
                     LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, Ix1, Iy1);
                 }
-                const float b1 = __ll2float_rn(warp_sum_i64(sb1)) * FLT_SCALE;
-                const float b2 = __ll2float_rn(warp_sum_i64(sb2)) * FLT_SCALE;
+                const bool small = !__any_sync(0xffffffffu, (lk_big(sb1) | lk_big(sb2)) != 0u);
+                const float b1 = warp_sum_f(sb1, small, FLT_SCALE);
+                const float b2 = warp_sum_f(sb2, small, FLT_SCALE);
                 const float dx = (A12 * b2 - A22 * b1) * D;
                 const float dy = (A12 * b1 - A11 * b2) * D;
                 nextx += dx; nexty += dy;
                 outx = nextx + DVFE_HALF_WIN; outy = nexty + DVFE_HALF_WIN;
                 if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
-                if (it > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                // std::abs(delta.x + prevDelta.x) < 0.01 (float sum against the double 0.01): the floats below 0.01 are exactly
+                // those below the first float above it, 0x3C23D70B
+                if (it > 0 && fabsf(dx + pdx) < __int_as_float(0x3C23D70B) && fabsf(dy + pdy) < __int_as_float(0x3C23D70B)) {
                     outx -= dx * 0.5f; outy -= dy * 0.5f;
                     break;
                 }
@@ -344,10 +440,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
 }
 
 int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,
-              int back_max_level, double fb_threshold, int tcache_flags) {
+              int back_max_level, double fb_threshold, int tcache_flags, int reuse_max_level) {
     if (n_groups <= 0 || max_pts <= 0) return DVFE_OK;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, n_groups);
-    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back, back_max_level, fb_threshold, tcache_flags);
+    DVFE_LAUNCH(k_lk_track, grid, LK_WARPS * 32, 0, st, d_groups, max_level, flow_back, back_max_level, fb_threshold, tcache_flags,
+                reuse_max_level);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

@@ -179,7 +179,7 @@ extern "C" int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch
             cudaMemcpy(n_out, d_n.p, sizeof(int), cudaMemcpyDeviceToHost);
             if (*n_out > 0) cudaMemcpy(corners_out, d_pts.p, sizeof(float2) * (*n_out), cudaMemcpyDeviceToHost);
             if (n_candidates_out) *n_candidates_out = counters[3];
-            if (counters[2]) { dvfe_set_error("op_good_features: candidate buffer overflow"); rc = DVFE_ERR_CAPACITY; }
+            if (counters[7]) { dvfe_set_error("op_good_features: candidate buffer overflow"); rc = DVFE_ERR_CAPACITY; }
         }
     }
     free_gftt_scratch(&sc);

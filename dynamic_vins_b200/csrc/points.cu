@@ -60,7 +60,11 @@ int launch_lift(const CamParams& cam, const float2* pts, int n, float offx, floa
 
 // ---- ReduceVector after the temporal LK: keep status != 0, preserve order; track_cnt++ ---------------
 // One block per point set; in-place (destination index <= source index, chunks are read before written).
-__global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int cap, const uint8_t* __restrict__ active) {
+// old_idx (nullable): old_idx[set*cap + j] = the index the survivor at j had before the compaction, -1 for the free slots behind
+// the survivors (the points the detection appends there are new): lets the stereo LK pick up the templates the temporal LK's
+// backward pass built for the same point.
+__global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int cap, const uint8_t* __restrict__ active,
+                                                         int* __restrict__ old_idx) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int set = blockIdx.x;
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int c
             const int j = off + __popc(ballot & ((1u << lane) - 1));
             S.pts[o + j] = p; S.un[o + j] = un; S.ids[o + j] = id; S.track_cnt[o + j] = tc + 1;
             S.rprev_un[o + j] = rp; S.rprev_valid[o + j] = rv;
+            if (old_idx != nullptr) old_idx[o + j] = i;
         }
         __syncthreads();
         if (tid == 0) {
@@ -97,12 +102,14 @@ __global__ void __launch_bounds__(256) k_compact_tracked(PointSetArrays S, int c
         }
         __syncthreads();
     }
+    if (old_idx != nullptr)
+        for (int j = s_base + tid; j < cap; j += 256) old_idx[o + j] = -1;
     if (tid == 0) S.n[set] = s_base;
 }
 
-int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st, const uint8_t* d_active) {
+int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st, const uint8_t* d_active, int* d_old_idx) {
     if (n_sets <= 0) return DVFE_OK;
-    DVFE_LAUNCH(k_compact_tracked, n_sets, 256, 0, st, S, cap, d_active);
+    DVFE_LAUNCH(k_compact_tracked, n_sets, 256, 0, st, S, cap, d_active, d_old_idx);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }

@@ -18,7 +18,8 @@ struct PointSetArrays {
     int* n;                 // [n_sets]
 };
 
-int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st, const uint8_t* d_active = nullptr);
+int launch_compact(const PointSetArrays& S, int n_sets, int cap, cudaStream_t st, const uint8_t* d_active = nullptr,
+                   int* d_old_idx = nullptr);
 struct CamParams;
 int launch_left_post(const PointSetArrays& S, int n_sets, int cap, const CamParams& cam, const double* d_dt,
                      const float2* d_offset, cudaStream_t st, const uint8_t* d_active = nullptr);

@@ -2,6 +2,7 @@
 // FeatureTracker::TrackImage / TrackSemanticImage (dynamic_vins/src/front_end/background_tracker.cpp:52-158,
 // 757-837) and the seam-level operators.  Host code only orchestrates launches; no pixel or point
 // arithmetic happens on the CPU and there is no fallback when no CUDA device is present.
+#include <limits.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -95,6 +96,12 @@ int alloc_gftt_scratch(GfttScratch* sc, int n_jobs, int w, int h, float min_dist
     DVFE_CHECK(dmalloc(&sc->state, (size_t)n_jobs * sc->cand_cap));
     DVFE_CHECK(dmalloc(&sc->cell_count, (size_t)n_jobs * 2 * (sc->n_cells + 1)));
     DVFE_CHECK(dmalloc(&sc->counters, (size_t)n_jobs * 8));
+    {
+        // counters 0..2 (n_precand, masked max as an ordered int, overflow) start reset; the selection kernel re-arms them
+        std::vector<int> init((size_t)n_jobs * 8, 0);
+        for (int j = 0; j < n_jobs; j++) init[(size_t)j * 8 + 1] = INT_MIN;
+        DVFE_CUDA(cudaMemcpy(sc->counters, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     return DVFE_OK;
 }
 
@@ -211,8 +218,11 @@ int dvfe_tracker::init() {
     if (staged_upload)
         for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
-    if (cfg.stereo)
+    if (cfg.stereo) {
         DVFE_CHECK(dmalloc(&d_tcache, (size_t)B * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS));
+        DVFE_CHECK(dmalloc(&d_tcache_bwd, (size_t)B * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS));
+        DVFE_CHECK(dmalloc(&d_old_idx, (size_t)B * cap));
+    }
     // LK groups: [phase][temporal raw | temporal semantic | stereo]
     std::vector<LkGroup> g(B);
     for (int ph = 0; ph < 6; ph++) {
@@ -236,6 +246,8 @@ int dvfe_tracker::init() {
                 }
                 G.n = bg.n + s;
                 G.tcache = d_tcache ? d_tcache + (size_t)s * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS : nullptr;
+                G.tcache_bwd = d_tcache_bwd ? d_tcache_bwd + (size_t)s * cap * DVFE_MAX_PYR_LEVELS * LK_TCACHE_WORDS : nullptr;
+                G.old_idx = d_old_idx ? d_old_idx + o : nullptr;
             }
             DVFE_CHECK(dmalloc(&d_groups[ph][kind], (size_t)B));
             DVFE_CUDA(cudaMemcpy(d_groups[ph][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
@@ -252,6 +264,7 @@ int dvfe_tracker::init() {
                 J.img = left_slot(ph) + (size_t)s * desc.bytes + L0.offset + (size_t)DVFE_PADY * L0.pitch + DVFE_PADX;
                 J.img_pitch = L0.pitch;
                 J.w = W; J.h = H;
+                J.img_bordered = 1;
                 if (kind == 1) { J.region_mask = d_region + (size_t)s * P; J.region_pitch = W; }
                 gftt_job_bind_scratch(&J, gsc, s);
                 const size_t o = (size_t)s * cap;
@@ -283,7 +296,8 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
-    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFree(t->d_err); cudaFree(t->d_tcache);
+    cudaFree(t->d_next_id); cudaFree(t->d_dt); cudaFree(t->d_err); cudaFree(t->d_tcache); cudaFree(t->d_tcache_bwd);
+    cudaFree(t->d_old_idx);
     for (int p = 0; p < 2; p++) {
         cudaFree(t->d_obs[p]); cudaFree(t->d_nobs[p]);
         if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
@@ -340,14 +354,17 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
     DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_in_place));
     mark(ST_PYRAMID + 1);
+    // The temporal call's backward templates (current left image at the tracked positions, levels <= its backward maxLevel)
+    // are the stereo call's forward templates at those levels for the survivors: stored by the former, picked up through
+    // the compaction's old-index map by the latter.
+    const int site_t = semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL;
+    const bool reuse = k > 0 && stereo_now && cfg.flow_back && d_tcache_bwd != nullptr;
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
-        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st,
-                             lk_back_level[semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL],
-                             lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL],
-                             tcache_valid ? LK_TCACHE_READ : 0));
+        DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level[site_t],
+                             lk_fb_thresh[site_t], (tcache_valid ? LK_TCACHE_READ : 0) | (reuse ? LK_TCACHE_WRITE_BWD : 0)));
     mark(ST_LK_TEMPORAL + 1);
     if (k > 0)   // ReduceVector x4 + track_cnt++
-        DVFE_CHECK(launch_compact(bg, B, cap, st));
+        DVFE_CHECK(launch_compact(bg, B, cap, st, nullptr, reuse ? d_old_idx : nullptr));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
     DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, prof ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
@@ -369,7 +386,8 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
     if (stereo_now)   // FeatureTrackByLK(gray0, gray1, curr_points) — left points are kept when the match fails
         DVFE_CHECK(launch_lk(d_groups[ph][2], B, cap, cfg.lk_max_level, cfg.flow_back, st,
                              lk_back_level[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO],
-                             lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO], LK_TCACHE_WRITE));
+                             lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO],
+                             LK_TCACHE_WRITE | (reuse ? LK_TCACHE_READ_BWD : 0), reuse ? lk_back_level[site_t] : -1));
     tcache_valid = stereo_now && d_tcache != nullptr;
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs[par], d_nobs[par], st));

@@ -68,6 +68,8 @@ struct dvfe_tracker {
     InstanceState* inst = nullptr;
     unsigned* d_tcache = nullptr;                    // LK template cache [B][cap][DVFE_MAX_PYR_LEVELS][LK_TCACHE_WORDS] (stereo only)
     bool tcache_valid = false;                       // the last step ran the stereo LK on the points `bg` holds now
+    unsigned* d_tcache_bwd = nullptr;                // backward templates of the temporal call, same layout (stereo only)
+    int* d_old_idx = nullptr;                        // [B][cap] index of each point in the temporal call of the step, -1 = new
     // backward LK maxLevel / forward-backward threshold per call site [DVFE_LK_*]: the CPU FeatureTrackByLK pair
     // (feature_utils.cpp:51,57: 1, 0.5) everywhere except TrackSemanticImage's right image, which the reference tracks with
     // the cv::cuda call pattern (TrackRightGPU, background_tracker.cpp:801: 3 levels, 1.0 px)
