@@ -158,6 +158,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+class stdout_to_stderr:
+    """fd-level redirect of stdout to stderr (native libraries write their banners with printf): stdout carries exactly one
+    JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def bind_to_gpu_cpus(gpu_index: int) -> str:
     """Best effort: run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers the
     e2e leg uploads from live on that GPU's NUMA node (matters when 8 ranks upload at once)."""
@@ -238,7 +255,9 @@ def run_dvfe(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():                   # whatever the libraries print while they come up goes to stderr
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     all_cpus = os.sched_getaffinity(0)
     numa_note = bind_to_gpu_cpus(local)      # pinned host buffers are then first-touched on the GPU's NUMA node
 

@@ -804,6 +804,20 @@ __global__ void k_gftt_assign_ids(const GfttJob* __restrict__ jobs, int n_jobs) 
     }
 }
 
+// per-device function attribute of the selection kernel; called at tracker creation so that it never falls inside a graph
+// capture, and (cheaply) before every launch for the seam ops
+int gftt_prepare_device() {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        DVFE_CUDA(cudaFuncSetAttribute(k_gftt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_DYN_SMEM));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    return DVFE_OK;
+}
+#define DVFE_CHECK_RC(call) do { int rc__ = (call); if (rc__ != DVFE_OK) return rc__; } while (0)
+
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
                 cudaStream_t st, cudaEvent_t* marks, cudaEvent_t after_response) {
     (void)h_jobs;
@@ -836,8 +850,7 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
     }
     GFTT_MARK();
     if (after_response) cudaEventRecord(after_response, st);
-    // per device attribute; setting it again is a no-op
-    DVFE_CUDA(cudaFuncSetAttribute(k_gftt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_DYN_SMEM));
+    DVFE_CHECK_RC(gftt_prepare_device());
     DVFE_LAUNCH(k_gftt_select, n_jobs, NMS_THREADS, NMS_DYN_SMEM, st, d_jobs);
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
 #undef GFTT_MARK

@@ -34,6 +34,7 @@ struct ErodeJob {
 // pyramid.cu
 int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
                           bool level0_in_place = false);
+int launch_pyr_level0(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st);
 // Frame ingest (prep.cu): optional fixed-point cv::remap (undistortion maps) + optional BGR -> gray, B images per launch,
 // written at dst_pitch (straight into level 0 of a padded pyramid, or dense).
 struct IngestArgs {
@@ -98,6 +99,7 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
 // after_response (nullable): recorded between the response kernel and the (few-CTA) selection kernel
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
                 cudaStream_t st, cudaEvent_t* marks = nullptr, cudaEvent_t after_response = nullptr);
+int gftt_prepare_device();
 int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st);
 int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n, int max_pts, int radius,
                      cudaStream_t st);

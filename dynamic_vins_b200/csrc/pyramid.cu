@@ -197,14 +197,23 @@ int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cu
     return DVFE_OK;
 }
 
+// the caller's dense images -> the interior of level 0 of the padded pyramids
+int launch_pyr_level0(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st) {
+    const dim3 blk(32, 8);
+    const PyrLevel& L = desc.lv[0];
+    dim3 grid(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, n_img);
+    DVFE_LAUNCH(k_pyr_level0, grid, blk, 0, st, set, L, spitch);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
 // level0_in_place: level 0's interior has already been written (H2D straight into the padded layout)
 int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
                           bool level0_in_place) {
     const dim3 blk(32, 8);
     if (!level0_in_place) {
-        const PyrLevel& L = desc.lv[0];
-        dim3 grid(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, n_img);
-        DVFE_LAUNCH(k_pyr_level0, grid, blk, 0, st, set, L, spitch);
+        const int rc = launch_pyr_level0(set, n_img, desc, spitch, st);
+        if (rc != DVFE_OK) return rc;
     }
     for (int l = 0; l < desc.n_levels; l++) {
         const PyrLevel& D = desc.lv[l];

@@ -180,6 +180,8 @@ int dvfe_tracker::init() {
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_packed[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_resp[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_rpyr[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_r0[p], cudaEventDisableTiming));
+        DVFE_CUDA(cudaEventCreateWithFlags(&ev_begin[p], cudaEventDisableTiming));
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_done[p], cudaEventDisableTiming));
     }
     const size_t P = (size_t)W * H;
@@ -211,10 +213,12 @@ int dvfe_tracker::init() {
         DVFE_CUDA(cudaEventCreateWithFlags(&ev_inst[p], cudaEventDisableTiming));
     }
     DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
+    DVFE_CHECK(gftt_prepare_device());
     // pitched host->device DMA straight into the padded level 0 runs at full PCIe rate only for rows that are a
     // multiple of 64 bytes; other widths go through a dense staging buffer (one linear copy) and the copy kernel
     staged_upload = (W % 64) != 0;
     if (const char* e = getenv("DVFE_STAGED_UPLOAD")) staged_upload = atoi(e) != 0;      // experiment / override
+    if (const char* e = getenv("DVFE_GRAPHS")) use_graphs = atoi(e) != 0;                // A/B: 0 = plain launches
     if (staged_upload)
         for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
@@ -293,6 +297,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     if (t->cs) cudaStreamSynchronize(t->cs);
     if (t->ds) cudaStreamSynchronize(t->ds);
     if (t->rs) cudaStreamSynchronize(t->rs);
+    t->drop_graphs();
     for (int s = 0; s < 3; s++) cudaFree(t->pyrL[s]);
     for (int s = 0; s < 2; s++) cudaFree(t->pyrR[s]);
     free_point_sets(&t->bg);
@@ -303,6 +308,8 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
         if (t->ev_packed[p]) cudaEventDestroy(t->ev_packed[p]);
         if (t->ev_resp[p]) cudaEventDestroy(t->ev_resp[p]);
         if (t->ev_rpyr[p]) cudaEventDestroy(t->ev_rpyr[p]);
+        if (t->ev_r0[p]) cudaEventDestroy(t->ev_r0[p]);
+        if (t->ev_begin[p]) cudaEventDestroy(t->ev_begin[p]);
         cudaFreeHost(t->h_dt[p]); cudaFreeHost(t->h_obs[p]); cudaFreeHost(t->h_nobs[p]);
         if (t->ev_up[p]) cudaEventDestroy(t->ev_up[p]);
         if (t->ev_done[p]) cudaEventDestroy(t->ev_done[p]);
@@ -332,19 +339,23 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
 // submit() only enqueues: optional device-side copy into level 0, pyramids, LK, detection, post-processing and the
 // D2H of the records of step k, all on the compute stream; nothing blocks the host.  Two steps may be in flight,
 // so the H2D of step k+1 (upload stream) overlaps the kernels of step k.
-int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
-                         const double* time0, bool semantic, bool level0_in_place, bool has_right) {
-    const long k = frames;
+void dvfe_tracker::drop_graphs() {
+    for (auto& kv : step_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    step_graphs.clear();
+}
+
+// The kernels of one frame step on the compute stream `st` (+ the right pyramid on `rs`, forked and joined by events).
+// No host-dependent state is read: the same call with the same arguments enqueues the same work, which is what lets
+// submit() capture it into a graph.
+int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, bool semantic,
+                                  bool level0_in_place, bool stereo_now, long k, bool with_marks) {
     const int ph = (int)(k % 6), par = (int)(k % 2);
-    const bool stereo_now = cfg.stereo && (d_right != nullptr || (level0_in_place && has_right));
-    for (int s = 0; s < B; s++) h_dt[par][s] = time0[s] - prev_time[s];       // cur_time - prev_time
+    auto mark = [&](int i) { if (with_marks) cudaEventRecord(ev[par][i], st); };
     DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt[par], B * sizeof(double), cudaMemcpyHostToDevice, st));
     // the capacity flag is per step: cleared here, reported by the wait for THIS step only (the buffers of step k-2 have
     // been read back before slot `par` is reused)
     DVFE_CUDA(cudaMemsetAsync(d_err + par, 0, sizeof(int), st));
-    prof_step[par] = prof;
-    auto mark = [&](int i) { if (prof) cudaEventRecord(ev[par][i], st); };
-
     mark(0);
     // left pyramid now; the right pyramid is built on its own stream while the selection kernel (one CTA per
     // stream) leaves most SMs idle, and joins before the stereo LK
@@ -367,7 +378,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
         DVFE_CHECK(launch_compact(bg, B, cap, st, nullptr, reuse ? d_old_idx : nullptr));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
-    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, prof ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
+    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, with_marks ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
                            stereo_now ? ev_resp[par] : nullptr));
     if (stereo_now) {
         PyrImgSet rset;
@@ -388,10 +399,69 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
                              lk_back_level[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO],
                              lk_fb_thresh[semantic ? DVFE_LK_SEMANTIC_STEREO : DVFE_LK_RAW_STEREO],
                              LK_TCACHE_WRITE | (reuse ? LK_TCACHE_READ_BWD : 0), reuse ? lk_back_level[site_t] : -1));
-    tcache_valid = stereo_now && d_tcache != nullptr;
     mark(ST_LK_STEREO + 1);
     DVFE_CHECK(launch_right_post_pack(bg, B, cap, cam1, d_dt, stereo_now ? 1 : 0, d_obs[par], d_nobs[par], st));
     mark(ST_PACK + 1);
+    return DVFE_OK;
+}
+
+int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
+                         const double* time0, bool semantic, bool level0_in_place, bool has_right) {
+    const long k = frames;
+    const int ph = (int)(k % 6), par = (int)(k % 2);
+    const bool stereo_now = cfg.stereo && (d_right != nullptr || (level0_in_place && has_right));
+    for (int s = 0; s < B; s++) h_dt[par][s] = time0[s] - prev_time[s];       // cur_time - prev_time
+    prof_step[par] = prof;
+    // everything step k-1 (background and instances) put on the compute stream lies before this point
+    DVFE_CUDA(cudaEventRecord(ev_begin[par], st));
+    if (use_graphs && !prof) {
+        // The captured step never sees the caller's image pointers: device-resident input is copied into level 0 here,
+        // left on the compute stream, right on its own stream behind the last readers of that slot (the stereo LKs of step
+        // k-2, all of which precede the start of step k-1), and the graph runs as if level 0 had arrived in place.
+        if (!level0_in_place) {
+            PyrImgSet set;
+            set.src[0] = d_left; set.src[1] = nullptr; set.dst[0] = left_slot(k); set.dst[1] = nullptr;
+            set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
+            DVFE_CHECK(launch_pyr_level0(set, B, desc, pitch, st));
+            if (stereo_now) {
+                set.src[0] = d_right; set.dst[0] = right_slot(k);
+                if (k >= 1) DVFE_CUDA(cudaStreamWaitEvent(rs, ev_begin[1 - par], 0));
+                DVFE_CHECK(launch_pyr_level0(set, B, desc, pitch, rs));
+                DVFE_CUDA(cudaEventRecord(ev_r0[par], rs));
+                DVFE_CUDA(cudaStreamWaitEvent(st, ev_r0[par], 0));
+            }
+        }
+        const unsigned flags = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | (k > 0 ? 8u : 0u) | (tcache_valid ? 16u : 0u);
+        const StepKey key(ph, flags);
+        auto it = step_graphs.find(key);
+        if (it == step_graphs.end()) {
+            if (step_graphs.size() >= 64) drop_graphs();          // a caller cycling through many input buffers
+            const unsigned long long before = g_dvfe_launches;
+            cudaGraph_t g = nullptr;
+            DVFE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            const int rc = enqueue_compute(nullptr, nullptr, 0, 0, semantic, true, stereo_now, k, false);
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            const unsigned n_kernels = (unsigned)(g_dvfe_launches - before);
+            g_dvfe_launches = before;                              // nothing ran yet
+            if (rc != DVFE_OK || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                if (rc != DVFE_OK) return rc;
+                dvfe_set_error("stream capture of the frame step failed: %s", cudaGetErrorString(ce));
+                return DVFE_ERR_CUDA;
+            }
+            StepGraph sg;
+            sg.n_kernels = n_kernels;
+            const cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { dvfe_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return DVFE_ERR_CUDA; }
+            it = step_graphs.emplace(key, sg).first;
+        }
+        DVFE_CUDA(cudaGraphLaunch(it->second.exec, st));
+        g_dvfe_launches += it->second.n_kernels;
+    } else {
+        DVFE_CHECK(enqueue_compute(d_left, d_right, stream_stride, pitch, semantic, level0_in_place, stereo_now, k, prof));
+    }
+    tcache_valid = stereo_now && d_tcache != nullptr;
     // records go home on the download stream so that the next step's kernels do not queue behind the copy
     DVFE_CUDA(cudaEventRecord(ev_packed[par], st));
     DVFE_CUDA(cudaStreamWaitEvent(ds, ev_packed[par], 0));
@@ -656,6 +726,7 @@ extern "C" int dvfe_set_lk_mode_site(dvfe_tracker* t, int site, int back_max_lev
     if (IS_GROUP(t)) return grp_set_lk_mode(t, site, back_max_level, fb_threshold);
     for (int i = 0; i < 4; i++)
         if (site < 0 || site == i) { t->lk_back_level[i] = back_max_level; t->lk_fb_thresh[i] = fb_threshold; }
+    t->drop_graphs();                 // the captured steps carry the old parameters
     return DVFE_OK;
 }
 
@@ -790,6 +861,7 @@ extern "C" int dvfe_set_stream(dvfe_tracker* t, void* cuda_stream) {
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
     DVFE_CHECK(t->wait_all());
     DVFE_CUDA(cudaStreamSynchronize(t->st));
+    t->drop_graphs();
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     t->st = (cudaStream_t)cuda_stream;
     t->own_stream = false;

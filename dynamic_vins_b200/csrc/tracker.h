@@ -1,5 +1,7 @@
 // Host-side tracker object behind the opaque `dvfe_tracker` handle of include/dvfe.h.
 #pragma once
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -55,7 +57,7 @@ struct dvfe_tracker {
     int* h_nobs[2] = {nullptr, nullptr};             // [B + 1]: counts, then the device error word of that step
     int* d_err = nullptr;                            // [2]: one capacity-overflow flag per in-flight step
     int out_slot = 0;                                // which h_obs holds the newest completed step
-    cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {}, ev_resp[2] = {}, ev_rpyr[2] = {};
+    cudaEvent_t ev_up[2] = {}, ev_packed[2] = {}, ev_done[2] = {}, ev_resp[2] = {}, ev_rpyr[2] = {}, ev_r0[2] = {}, ev_begin[2] = {};
     uint8_t *d_region = nullptr, *d_region_tmp = nullptr;
     uint8_t* d_inv_in[2] = {nullptr, nullptr};       // uploaded inv_merge_mask, one per in-flight step
     int* d_exist = nullptr;
@@ -75,6 +77,16 @@ struct dvfe_tracker {
     // the cv::cuda call pattern (TrackRightGPU, background_tracker.cpp:801: 3 levels, 1.0 px)
     int lk_back_level[4] = {1, 1, 1, 3};
     double lk_fb_thresh[4] = {0.5, 0.5, 0.5, 1.0};
+
+    // The compute part of a frame step is a fixed launch sequence for a given buffer phase, input location and mode: it is
+    // captured once into a CUDA graph and replayed (one launch per step and stream group instead of ~20).
+    typedef std::tuple<int, unsigned> StepKey;       // buffer phase, mode flags (the caller's image pointers stay outside)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned n_kernels = 0; };
+    std::map<StepKey, StepGraph> step_graphs;
+    bool use_graphs = true;
+    void drop_graphs();
+    int enqueue_compute(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, bool semantic,
+                        bool level0_in_place, bool stereo_now, long k, bool with_marks);
 
     // per-stage device timers (one event set per in-flight step)
     enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT_MASK, ST_GFTT_DISCS, ST_GFTT_RESPONSE, ST_GFTT_SELECT, ST_LEFT_POST,

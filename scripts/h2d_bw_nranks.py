@@ -35,7 +35,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from bench import stdout_to_stderr
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     n = args.bytes // args.streams
     host = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(args.streams)]
     for h in host:
