@@ -56,7 +56,12 @@ INST_OBS_DTYPE = np.dtype([("inst_id", np.uint32), ("id", np.uint32), ("is_stere
 
 class InstIn(C.Structure):
     _fields_ = [("track_id", C.c_uint32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
-                ("mask", C.c_void_p), ("mask_pitch", C.c_int32), ("disp", C.c_void_p), ("disp_pitch", C.c_int32)]
+                ("mask", C.c_void_p), ("mask_pitch", C.c_int32), ("disp", C.c_void_p), ("disp_pitch", C.c_int32), ("label_bit", C.c_int32)]
+
+
+class InstInfo(C.Structure):
+    _fields_ = [("track_id", C.c_uint32), ("lost_num", C.c_int32), ("is_curr_visible", C.c_int32), ("has_box", C.c_int32),
+                ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32)]
 
 
 class State(C.Structure):
@@ -72,7 +77,7 @@ SYMBOLS = [
     "dvfe_insts_track", "dvfe_insts_track_batch", "dvfe_get_features", "dvfe_insts_output", "dvfe_get_state", "dvfe_set_state",
     "dvfe_op_build_pyramid", "dvfe_op_lk", "dvfe_op_min_eigen_val", "dvfe_op_good_features",
     "dvfe_op_disc_mask", "dvfe_op_erode_rect", "dvfe_op_lift_projective", "dvfe_op_bgr_to_gray", "dvfe_op_merge_masks",
-    "dvfe_op_remap", "dvfe_set_input", "dvfe_set_undistort_maps", "dvfe_track_dynamic_async", "dvfe_op_punch_out",
+    "dvfe_op_remap", "dvfe_set_input", "dvfe_set_undistort_maps", "dvfe_track_dynamic_async", "dvfe_op_punch_out", "dvfe_insts_table", "dvfe_track_dynamic_ex",
 ]
 
 _lib = None
@@ -128,6 +133,9 @@ def lib() -> C.CDLL:
         L.dvfe_track_dynamic_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]
         L.dvfe_op_punch_out.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.dvfe_track_dynamic_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+        L.dvfe_insts_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.dvfe_set_input.argtypes = [C.c_void_p, C.c_int]
         L.dvfe_set_undistort_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.dvfe_op_merge_masks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

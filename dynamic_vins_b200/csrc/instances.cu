@@ -39,6 +39,7 @@ struct InstHost {
     int cur_buf = 0;               // which of the two ROI buffers holds roi_gray
     int roi_w = 0, roi_h = 0;      // size of roi->roi_gray
     long long mask_off = -1;       // offset of this frame's ROI mask in the packed staging (-1: in the slot buffer)
+    int label_bit = -1;            // >= 0: the ROI mask is bit `label_bit` of the frame's label image (device)
     const float* disp = nullptr;   // SemanticImage::disp of this frame (host, full image size) or null
     int disp_pitch = 0;
 };
@@ -228,7 +229,7 @@ static void manage_instances(InstStream& S) {
 
 // Every box inside the image with a mask, and enough free slots for the new track ids: checked before anything is changed
 // (and, for the pipelined call, before the background step is enqueued), so a bad call leaves the tracker untouched.
-static int insts_validate(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of) {
+static int insts_validate(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of, bool labels = false) {
     InstanceState& I = *t->inst;
     const int W = t->W, H = t->H;
     for (int stream = s0; stream < s1; stream++) {
@@ -237,9 +238,10 @@ static int insts_validate(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* c
         std::vector<uint32_t> fresh;
         for (int b = 0; b < n_of[stream - s0]; b++) {
             const dvfe_inst_in& bx = boxes[b];
-            if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !bx.mask ||
-                bx.mask_pitch < bx.w || (bx.disp != nullptr && bx.disp_pitch < (int)(W * sizeof(float)))) {
-                dvfe_set_error("insts_track: stream %d box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask",
+            const bool mask_ok = labels ? (bx.label_bit >= 0 && bx.label_bit < 8) : (bx.mask != nullptr && bx.mask_pitch >= bx.w);
+            if (bx.w < 1 || bx.h < 1 || bx.x < 0 || bx.y < 0 || bx.x + bx.w > W || bx.y + bx.h > H || !mask_ok ||
+                (bx.disp != nullptr && bx.disp_pitch < (int)(W * sizeof(float)))) {
+                dvfe_set_error("insts_track: stream %d box %d (%d,%d,%d,%d) is outside the %dx%d image or has no mask / label bit",
                                stream, b, bx.x, bx.y, bx.w, bx.h, W, H);
                 return DVFE_ERR_INVALID;
             }
@@ -259,10 +261,12 @@ static int insts_validate(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* c
 // defer = false: synchronous (the background step has been waited for; ends with a synchronisation and Output() ready).
 // defer = true: enqueue only, behind the background step just submitted; the records come home on the download stream and
 // dvfe_tracker::wait_one() finishes the call (finish_instances).  Nothing on the host side depends on device results.
+// labels: the ROI masks are cut out of the label images the background step of this frame received (DVFE_DYN_LABELS) on the
+// device, inside the erosion that reads them; no mask bytes cross the bus.
 static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_in* const* boxes_of, const int* n_of,
-                               const double* time_of, bool defer) {
+                               const double* time_of, bool defer, bool labels = false) {
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
-    if (!defer) DVFE_CHECK(insts_validate(t, s0, s1, boxes_of, n_of));      // deferred: done before the background step
+    if (!defer) DVFE_CHECK(insts_validate(t, s0, s1, boxes_of, n_of, labels));      // deferred: done before the background step
     if (!defer) DVFE_CHECK(t->wait_all());
     InstanceState& I = *t->inst;
     const int par = (int)((t->frames - 1) % 2);          // the step these instances belong to
@@ -310,6 +314,8 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             in.x = bx.x; in.y = bx.y; in.w = bx.w; in.h = bx.h;
             in.visible = true; in.has_box = true;
             in.disp = bx.disp; in.disp_pitch = bx.disp_pitch;
+            in.label_bit = labels ? bx.label_bit : -1;
+            if (labels) { in.mask_off = -1; continue; }
             // inst.roi->mask_cv = det_box->roi->mask_cv : packed into the pinned staging, uploaded with one copy below
             const size_t bytes = (size_t)bx.w * bx.h;
             if (mask_used + bytes <= I.mask_stage_cap) {
@@ -375,9 +381,15 @@ static int insts_track_streams(dvfe_tracker* t, int s0, int s1, const dvfe_inst_
             }
             // detection job (:418-446)
             ErodeJob& e = C.erode.h[j];
-            e.src = in.mask_off >= 0 ? C.d_mask_stage + in.mask_off : I.roi_mask + set * P;
             e.tmp = I.roi_mask_tmp + set * P; e.dst = I.roi_mask_er + set * P;
             e.w = in.w; e.h = in.h; e.k = 5;
+            if (in.label_bit >= 0) {       // full_mask(rect) read in place from the label image of this step
+                e.src = t->lab_ptr[par] + (size_t)stream * t->lab_stride[par] + (size_t)in.y * t->lab_pitch[par] + in.x;
+                e.spitch = t->lab_pitch[par]; e.label_bit = in.label_bit;
+            } else {
+                e.src = in.mask_off >= 0 ? C.d_mask_stage + in.mask_off : I.roi_mask + set * P;
+                e.spitch = in.w; e.label_bit = -1;
+            }
             GfttJob& J = C.gftt.h[j];
             memset(&J, 0, sizeof(J));
             J.img = c.dst; J.img_pitch = in.w; J.w = in.w; J.h = in.h;
@@ -503,7 +515,8 @@ int dvfe_tracker::finish_instances(int par) {
 }
 
 int grp_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv, size_t stride,
-                            int pitch, const int* exist, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0);
+                            int pitch, const int* exist, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0,
+                            unsigned flags);
 int grp_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* boxes, int n, double time0);
 int grp_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0);
 int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
@@ -553,9 +566,16 @@ extern "C" int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* boxes
 extern "C" int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,
                                         size_t stream_stride, int pitch, const int* exist_inst, const dvfe_inst_in* boxes,
                                         const int* n_boxes, const double* time0) {
-    if (!t || !left || !time0 || !exist_inst || !n_boxes) { dvfe_set_error("track_dynamic_async: null argument"); return DVFE_ERR_INVALID; }
+    return dvfe_track_dynamic_ex(t, left, right, inv_merge_mask, stream_stride, pitch, exist_inst, boxes, n_boxes, time0, 0u);
+}
+
+extern "C" int dvfe_track_dynamic_ex(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* mask,
+                                     size_t stream_stride, int pitch, const int* exist_inst, const dvfe_inst_in* boxes,
+                                     const int* n_boxes, const double* time0, unsigned flags) {
+    const bool labels = (flags & DVFE_DYN_LABELS) != 0;
+    if (!t || !left || !time0 || !n_boxes || (!exist_inst && !labels)) { dvfe_set_error("track_dynamic: null argument"); return DVFE_ERR_INVALID; }
     if (!t->groups.empty())
-        return grp_track_dynamic_async(t, left, right, inv_merge_mask, stream_stride, pitch, exist_inst, boxes, n_boxes, time0);
+        return grp_track_dynamic_async(t, left, right, mask, stream_stride, pitch, exist_inst, boxes, n_boxes, time0, flags);
     if (!t->inst) { dvfe_set_error("track_dynamic_async: max_instances must be > 0 at create"); return DVFE_ERR_INVALID; }
     if (pitch < t->W * t->in_ch) { dvfe_set_error("track_dynamic_async: bad pitch"); return DVFE_ERR_INVALID; }
     std::vector<const dvfe_inst_in*> of(t->B);
@@ -566,9 +586,11 @@ extern "C" int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, co
         off += (size_t)n_boxes[s];
     }
     DVFE_CUDA(cudaSetDevice(t->cfg.device));
-    DVFE_CHECK(insts_validate(t, 0, t->B, of.data(), n_boxes));
-    DVFE_CHECK(t->semantic_submit(left, right, inv_merge_mask, stream_stride, pitch, exist_inst, time0));
-    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0, true);
+    DVFE_CHECK(insts_validate(t, 0, t->B, of.data(), n_boxes, labels));
+    std::vector<int> exist(t->B);
+    for (int s = 0; s < t->B; s++) exist[s] = labels ? (n_boxes[s] > 0 ? 1 : 0) : exist_inst[s];     // SetMaskAndRoi: exist_inst = !boxes2d.empty()
+    DVFE_CHECK(t->semantic_submit(left, right, mask, stream_stride, pitch, exist.data(), time0, flags));
+    return insts_track_streams(t, 0, t->B, of.data(), n_boxes, time0, true, labels);
 }
 
 extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out) {
@@ -585,5 +607,27 @@ extern "C" int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out
     *n_out = (int)v.size();
     if ((int)v.size() > cap) { dvfe_set_error("insts_output: %d records, capacity %d", (int)v.size(), cap); return DVFE_ERR_CAPACITY; }
     if (!v.empty() && out) memcpy(out, v.data(), v.size() * sizeof(dvfe_inst_obs));
+    return DVFE_OK;
+}
+
+extern "C" int dvfe_insts_table(dvfe_tracker* t, int stream, dvfe_inst_info* out, int cap, int* n_out) {
+    if (t && !t->groups.empty()) {
+        dvfe_tracker* leaf; int local;
+        DVFE_CHECK(grp_route(t, stream, &leaf, &local));
+        return dvfe_insts_table(leaf, local, out, cap, n_out);
+    }
+    if (!t || !t->inst || stream < 0 || stream >= t->B || !n_out) {
+        dvfe_set_error("insts_table: bad argument");
+        return DVFE_ERR_INVALID;
+    }
+    const InstStream& S = t->inst->streams[stream];
+    *n_out = (int)S.insts.size();
+    if (*n_out > cap) { dvfe_set_error("insts_table: %d instances, capacity %d", *n_out, cap); return DVFE_ERR_CAPACITY; }
+    int i = 0;
+    for (const auto& kv : S.insts) {
+        const InstHost& in = kv.second;
+        if (out) out[i] = dvfe_inst_info{in.track_id, in.lost_num, in.visible ? 1 : 0, in.has_box ? 1 : 0, in.x, in.y, in.w, in.h};
+        i++;
+    }
     return DVFE_OK;
 }

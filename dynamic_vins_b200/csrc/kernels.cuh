@@ -25,10 +25,12 @@ struct CropJob {
     uint8_t* dst;            // dense w x h
 };
 struct ErodeJob {
-    const uint8_t* src;      // dense w x h
+    const uint8_t* src;      // w x h at pitch `spitch`
     uint8_t* tmp;
     uint8_t* dst;
     int w, h, k;
+    int spitch;
+    int label_bit;           // < 0: src is the mask itself; >= 0: src is a label image, mask = bit `label_bit` set ? 255 : 0
 };
 
 // pyramid.cu
@@ -105,8 +107,9 @@ int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, 
                      cudaStream_t st);
 
 // morph.cu
+// label_mode: src is a label image (0 = background); the eroded image is inv_merge_mask = (label == 0 ? 255 : 0)
 int launch_erode_rect(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, uint8_t* tmp, int w, int h, int k,
-                      int n_img, size_t img_stride, const int* enable, cudaStream_t st);
+                      int n_img, size_t img_stride, const int* enable, cudaStream_t st, int label_mode = 0);
 
 int launch_erode_jobs(const ErodeJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st);
 

@@ -319,6 +319,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     for (int i = 0; i < 2; i++) { cudaFree(t->d_raw[i]); cudaFree(t->d_map1[i]); cudaFree(t->d_map2[i]); }
     cudaFree(t->d_region); cudaFree(t->d_region_tmp); cudaFree(t->d_exist);
     for (int p = 0; p < 2; p++) {
+        cudaFree(t->d_labels[p]);
         cudaFree(t->d_inv_in[p]); cudaFreeHost(t->h_exist[p]);
         if (t->ev_inst[p]) cudaEventDestroy(t->ev_inst[p]);
     }
@@ -734,38 +735,56 @@ extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_t
     return dvfe_set_lk_mode_site(t, -1, back_max_level, fb_threshold);
 }
 
-int dvfe_tracker::semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask,
-                                  size_t stream_stride, int pitch, const int* exist_inst, const double* time0) {
+int dvfe_tracker::semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* mask,
+                                  size_t stream_stride, int pitch, const int* exist_inst, const double* time0, unsigned flags) {
     while (frames - completed >= 2) DVFE_CHECK(wait_one());      // buffers of step k-2 are free again
     const size_t P = (size_t)W * H;
     const int par = (int)(frames % 2);
     const bool prep = prep_active();
-    // the region mask is one byte per pixel whatever the image format
+    const bool device = (flags & DVFE_DYN_DEVICE_INPUT) != 0, labels = (flags & DVFE_DYN_LABELS) != 0;
+    // the region mask / label image is one byte per pixel whatever the image format
     const size_t mask_stride = prep ? stream_stride / (size_t)in_ch : stream_stride;
     const int mask_pitch = prep ? pitch / in_ch : pitch;
-    // inv_merge_mask -> device on the upload stream, ahead of the images (one copy when every stream has one)
     bool all = true;
     for (int s = 0; s < B; s++) {
         h_exist[par][s] = exist_inst[s] ? 1 : 0;
         all = all && exist_inst[s];
-        if (exist_inst[s] && !inv_merge_mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
+        if (exist_inst[s] && !mask) { dvfe_set_error("track_semantic_image: exist_inst set but no mask"); return DVFE_ERR_INVALID; }
     }
-    if (all && mask_pitch == W && mask_stride == P) {
-        DVFE_CUDA(cudaMemcpyAsync(d_inv_in[par], inv_merge_mask, (size_t)B * P, cudaMemcpyHostToDevice, cs));
-    } else {
-        for (int s = 0; s < B; s++)
-            if (exist_inst[s])
-                DVFE_CUDA(cudaMemcpy2DAsync(d_inv_in[par] + s * P, W, inv_merge_mask + s * mask_stride, mask_pitch, W, (size_t)H,
-                                            cudaMemcpyHostToDevice, cs));
+    const uint8_t* d_mask = mask;            // where the erosion reads the mask / label image from
+    size_t d_mask_stride = mask_stride;
+    int d_mask_pitch = mask_pitch;
+    if (!device) {
+        // mask -> device on the upload stream, ahead of the images (one copy when every stream has one)
+        if (labels && !d_labels[par]) DVFE_CUDA(cudaMalloc((void**)&d_labels[par], (size_t)B * P));
+        uint8_t* dst = labels ? d_labels[par] : d_inv_in[par];
+        if (all && mask_pitch == W && mask_stride == P) {
+            DVFE_CUDA(cudaMemcpyAsync(dst, mask, (size_t)B * P, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int s = 0; s < B; s++)
+                if (exist_inst[s])
+                    DVFE_CUDA(cudaMemcpy2DAsync(dst + s * P, W, mask + s * mask_stride, mask_pitch, W, (size_t)H, cudaMemcpyHostToDevice, cs));
+        }
+        d_mask = dst; d_mask_stride = P; d_mask_pitch = W;
+        if (prep) DVFE_CHECK(upload_prepared(left, right, stream_stride, pitch));
+        else if (staged_upload) DVFE_CHECK(upload_staged(left, right, stream_stride, pitch));
+        else DVFE_CHECK(upload_in_place(left, right, stream_stride, pitch));          // records ev_up; st waits for it
+    } else if (prep) {
+        DVFE_CHECK(ingest(left, stream_stride, pitch, 0, st));
+        if (right) DVFE_CHECK(ingest(right, stream_stride, pitch, 1, st));
     }
-    if (prep) DVFE_CHECK(upload_prepared(left, right, stream_stride, pitch));
-    else if (staged_upload) DVFE_CHECK(upload_staged(left, right, stream_stride, pitch));
-    else DVFE_CHECK(upload_in_place(left, right, stream_stride, pitch));          // records ev_up; st waits for it
+    lab_ptr[par] = labels ? d_mask : nullptr; lab_stride[par] = d_mask_stride; lab_pitch[par] = d_mask_pitch;
     DVFE_CUDA(cudaMemcpyAsync(d_exist, h_exist[par], B * sizeof(int), cudaMemcpyHostToDevice, st));
-    // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772)
+    // region mask = exist_inst ? erode(inv_merge_mask, mask_morphology_size) : all 255   (:764-772); with a label image
+    // inv_merge_mask = (no instance bit set ? 255 : 0) is formed while it is read (basic/semantic_image.cpp:31-38)
     const int k = cfg.use_mask_morphology ? cfg.mask_morphology_size : 1;
-    DVFE_CHECK(launch_erode_rect(d_inv_in[par], W, d_region, W, d_region_tmp, W, H, k < 1 ? 1 : k, B, P, d_exist, st));
-    if (!prep && staged_upload)
+    if (d_mask != nullptr)
+        DVFE_CHECK(launch_erode_rect(d_mask, d_mask_pitch, d_region, W, d_region_tmp, W, H, k < 1 ? 1 : k, B, d_mask_stride, d_exist,
+                                     st, labels ? 1 : 0));
+    else
+        DVFE_CHECK(launch_erode_rect(d_inv_in[par], W, d_region, W, d_region_tmp, W, H, 1, B, P, d_exist, st));   // all 255
+    if (device && !prep) return submit(left, right, stream_stride, pitch, time0, true, false, right != nullptr);
+    if (!device && !prep && staged_upload)
         return submit(d_stage[par], right ? d_stage[par] + B * P : nullptr, P, W, time0, true, false, right != nullptr);
     return submit(nullptr, nullptr, 0, 0, time0, true, true, right != nullptr);
 }

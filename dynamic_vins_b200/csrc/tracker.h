@@ -121,8 +121,14 @@ struct dvfe_tracker {
     int submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, const double* time0,
                bool semantic, bool level0_in_place, bool has_right);
     // TrackSemanticImage of one frame, enqueued only (uploads on the copy stream, mask erosion + the frame step)
-    int semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* inv_merge_mask, size_t stream_stride,
-                        int pitch, const int* exist_inst, const double* time0);
+    // flags: DVFE_DYN_DEVICE_INPUT (the three pointers are device memory, nothing is uploaded), DVFE_DYN_LABELS (the mask is a
+    // label image: the region is everything no instance bit is set on)
+    int semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* mask, size_t stream_stride,
+                        int pitch, const int* exist_inst, const double* time0, unsigned flags = 0);
+    uint8_t* d_labels[2] = {nullptr, nullptr};       // uploaded label images, one per in-flight step (allocated on first use)
+    const uint8_t* lab_ptr[2] = {nullptr, nullptr};  // the label images of the in-flight steps (device), for the ROI masks
+    size_t lab_stride[2] = {0, 0};
+    int lab_pitch[2] = {0, 0};
     int finish_instances(int par);                   // instances.cu: host side of a deferred InstsTrack
     int wait_one();                                  // oldest in-flight step -> outputs readable
     int wait_all();

@@ -227,6 +227,20 @@ class SynthStream:
         return fr
 
 
+def label_image(frame: SynthFrame):
+    """The frame's instance masks as ONE u8 label image: bit b set = the pixel belongs to boxes[b] (the form
+    `dvfe_track_dynamic_ex(..., DVFE_DYN_LABELS)` takes; what an instance-segmentation network's mask stack collapses to).
+    Returns (labels, boxes with `label_bit` set).  At most 8 boxes."""
+    assert len(frame.boxes) <= 8
+    lab = np.zeros(frame.gray0.shape, np.uint8)
+    boxes = []
+    for b, box in enumerate(frame.boxes):
+        x, y, w, h = box["rect"]
+        lab[y:y + h, x:x + w] |= ((box["mask"] != 0).astype(np.uint8) << b)
+        boxes.append(dict(box, label_bit=b))
+    return lab, boxes
+
+
 def pingpong_positions(n_unique: int, n_steps: int) -> List[int]:
     """0,1,..,n-1,n-2,..,1,0,1,.. : temporally coherent motion from a finite set of frames."""
     if n_unique <= 1:

@@ -195,6 +195,7 @@ class BatchTracker:
                 arr[i].mask, arr[i].mask_pitch = m.ctypes.data, m.strides[0]
                 if d is not None:
                     arr[i].disp, arr[i].disp_pitch = d.ctypes.data, d.strides[0]
+                arr[i].label_bit = int(b.get("label_bit", -1))
                 i += 1
         counts = np.asarray([len(bs) for bs in boxes_per_stream], np.int32)
         return arr, counts, keep
@@ -230,6 +231,37 @@ class BatchTracker:
         n = C.c_int(0)
         L.check(L.lib().dvfe_insts_output(self._h, stream, L.ptr(self._iobs), len(self._iobs), C.byref(n)))
         return self._iobs[:n.value].copy()
+
+    DYN_DEVICE_INPUT, DYN_LABELS = 1, 2
+
+    def track_dynamic_labels_async(self, left, right, labels, boxes_per_stream, time0, device: bool = False) -> None:
+        """SemanticImage::SetMaskAndRoi on the device: `labels` holds one u8 label image per stream (bit b = the instance whose
+        box has label_bit == b).  Host arrays, or (device=True) device addresses `left`, `right`, `labels` of dense
+        [B][H][W] buffers.  Pipelined like track_dynamic_async; results after the matching wait()."""
+        arr, counts, keep = boxes_per_stream if isinstance(boxes_per_stream, tuple) else self.marshal_boxes(boxes_per_stream)
+        assert len(counts) == self.B
+        t = self._times(time0)
+        flags = self.DYN_LABELS | (self.DYN_DEVICE_INPUT if device else 0)
+        if device:
+            l, r, m = C.c_void_p(left), (C.c_void_p(right) if right else None), C.c_void_p(labels)
+            self._keep = (arr, counts, keep, t, getattr(self, "_keep", None) and self._keep[:4])
+            L.check(L.lib().dvfe_track_dynamic_ex(self._h, l, r, m, self.H * self.W * self.ch, self.W * self.ch, None, arr,
+                                                  L.ptr(counts), L.ptr(t), flags))
+            return
+        l = self._batch(left, self.B, self.H, self.W, self.ch)
+        r = self._batch(right, self.B, self.H, self.W, self.ch)
+        m = self._batch(labels, self.B, self.H, self.W)
+        self._keep = (l, r, m, arr, counts, keep, t, getattr(self, "_keep", None) and self._keep[:7])
+        L.check(L.lib().dvfe_track_dynamic_ex(self._h, L.ptr(l), L.ptr(r), L.ptr(m), self.H * self.W * self.ch, self.W * self.ch,
+                                              None, arr, L.ptr(counts), L.ptr(t), flags))
+
+    def insts_table(self, stream: int = 0) -> list:
+        """InstsFeatManager::instances after the last InstsTrack: [(track_id, lost_num, is_curr_visible, has_box, rect)]"""
+        cap = max(1, int(self.cfg.max_instances))
+        arr = (L.InstInfo * cap)()
+        n = C.c_int(0)
+        L.check(L.lib().dvfe_insts_table(self._h, stream, arr, cap, C.byref(n)))
+        return [(int(a.track_id), int(a.lost_num), bool(a.is_curr_visible), bool(a.has_box), (a.x, a.y, a.w, a.h)) for a in arr[:n.value]]
 
     # ---- state ---------------------------------------------------------------------------------
     def get_state(self, stream: int = 0) -> dict:

@@ -99,6 +99,8 @@ typedef struct dvfe_inst_in {
                                  * every box of the stream) or NULL; must stay valid until the step's records are read
                                  * (dvfe_insts_track returns / dvfe_wait) */
     int32_t disp_pitch;         /* bytes per row of disp */
+    int32_t label_bit;          /* with DVFE_DYN_LABELS: the bit of the frame's label image that marks this instance's pixels
+                                 * (`mask` is then ignored and may be NULL); otherwise unused */
 } dvfe_inst_in;
 
 typedef struct dvfe_tracker dvfe_tracker;
@@ -192,10 +194,36 @@ int dvfe_insts_track(dvfe_tracker* t, int stream, const dvfe_inst_in* insts, int
  * (n_insts[0] boxes of stream 0, then n_insts[1] of stream 1, ...), time0[s] per stream. */
 int dvfe_insts_track_batch(dvfe_tracker* t, const dvfe_inst_in* insts, const int* n_insts, const double* time0);
 
+/* One frame of dynamic mode for all streams, enqueued (pair with dvfe_wait): TrackSemanticImage + the caller's per-frame
+ * instance reset + AddViodeInstances + InstsTrack (system/main.cpp:193-254).  dvfe_track_dynamic_async is the flags = 0 form.
+ *   DVFE_DYN_DEVICE_INPUT  left / right / mask are DEVICE pointers (frames decoded or rendered on the GPU): nothing is uploaded
+ *   DVFE_DYN_LABELS        SemanticImage::SetMaskAndRoi on the device (basic/semantic_image.cpp:20-63): `mask` is ONE label image
+ *                          per stream (u8, layout of `left` at 1 byte/px) in which bit b of a pixel says that the pixel belongs
+ *                          to the instance whose box carries label_bit == b (up to 8 instances per frame, overlaps allowed).
+ *                          inv_merge_mask (no bit set -> 255) and every box's ROI mask full_mask(rect) are derived on the device;
+ *                          the per-box host masks and the inv_merge_mask upload disappear. */
+#define DVFE_DYN_DEVICE_INPUT 1u
+#define DVFE_DYN_LABELS 2u
+int dvfe_track_dynamic_ex(dvfe_tracker* t, const uint8_t* left, const uint8_t* right, const uint8_t* mask, size_t stream_stride,
+                          int pitch, const int* exist_inst, const dvfe_inst_in* boxes, const int* n_boxes, const double* time0,
+                          unsigned flags);
+
 /* FeatureBackground of stream s of the last step: n_out records, sorted by (id, cam). */
 int dvfe_get_features(dvfe_tracker* t, int stream, dvfe_obs* out, int cap, int* n_out);
 /* InstsFeatManager::Output() (front_end/dynamic_tracker.cpp:521-577), sorted by (inst_id, id). */
 int dvfe_insts_output(dvfe_tracker* t, int stream, dvfe_inst_obs* out, int cap, int* n_out);
+
+/* The instance table after the last InstsTrack of a stream: InstsFeatManager::instances (front_end/dynamic_tracker.h:83)
+ * with the fields the caller's per-frame code reads (system/main.cpp:198-242: is_curr_visible, box2d) and the bookkeeping
+ * ManageInstances keeps (lost_num, front_end/dynamic_tracker.cpp:499-514).  Rows in ascending track id. */
+typedef struct dvfe_inst_info {
+    uint32_t track_id;
+    int32_t lost_num;
+    int32_t is_curr_visible;
+    int32_t has_box;            /* box2d != nullptr */
+    int32_t x, y, w, h;         /* box2d->rect of the last frame the instance was seen in */
+} dvfe_inst_info;
+int dvfe_insts_table(dvfe_tracker* t, int stream, dvfe_inst_info* out, int cap, int* n_out);
 
 /* ---- tracker state (InstFeat bg members, front_end/instance_feature.h:103-137) --------------- */
 typedef struct dvfe_state {

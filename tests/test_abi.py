@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(L.Camera) == 64
     assert C.sizeof(L.Config) == 14 * 4 + 2 * 64 + 8
     assert C.sizeof(L.InstObs) == L.INST_OBS_DTYPE.itemsize == 16 + 13 * 8
-    assert C.sizeof(L.InstIn) == 56 and L.InstIn.disp.offset == 40
+    assert C.sizeof(L.InstIn) == 56 and L.InstIn.disp.offset == 40 and L.InstIn.label_bit.offset == 52
 
 
 def test_version_and_launch_counter():
