@@ -55,6 +55,9 @@ def parse_args():
                     help="stream groups of the end-to-end leg (PCIe-bound: one group = fewer, larger uploads, +1.6 %%)")
     ap.add_argument("--dyn-groups", type=int, default=2, help="stream groups of the dynamic-mode workload (c3): PCIe-bound, 2 is best")
     ap.add_argument("--frames", type=int, default=6, help="unique frames per stream (played back ping-pong)")
+    ap.add_argument("--motion-scale", type=float, default=1.0,
+                    help="camera motion per frame relative to the default scene (1-4 px + 0.2 deg): > 1 makes points leave the "
+                         "image and fail the round-trip test, i.e. feature churn (new corners per step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -192,7 +195,7 @@ def bind_to_gpu_cpus(gpu_index: int) -> str:
     return "not bound"
 
 
-def gpu_frames(stream, T: int, device):
+def gpu_frames(stream, T: int, device, motion_scale: float = 1.0):
     """The `T` unique stereo frames of one synthetic stream, rendered on the GPU with the same formulas as
     dynamic_vins_b200.synth.SynthStream._view (float64).  Returns uint8 tensor [T][2][H][W]."""
     import torch
@@ -203,7 +206,8 @@ def gpu_frames(stream, T: int, device):
                             torch.arange(W, device=device, dtype=torch.float64), indexing="ij")
     out = torch.empty((T, 2, H, W), dtype=torch.uint8, device=device)
     cx, cy = W / 2.0, H / 2.0
-    for k in range(T):
+    for kk in range(T):
+        k = kk * motion_scale
         th = stream.omega * k
         sc = 1.0 + stream.dscale * k
         c, s = np.cos(th) * sc, np.sin(th) * sc
@@ -218,7 +222,7 @@ def gpu_frames(stream, T: int, device):
             ax = xs - x0; ay = ys - y0
             v = ((1 - ax) * (1 - ay) * canvas[y0, x0] + ax * (1 - ay) * canvas[y0, x0 + 1]
                  + (1 - ax) * ay * canvas[y0 + 1, x0] + ax * ay * canvas[y0 + 1, x0 + 1])
-            out[k, cam] = v.round().clamp(0, 255).to(torch.uint8)
+            out[kk, cam] = v.round().clamp(0, 255).to(torch.uint8)
     return out
 
 
@@ -226,7 +230,8 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
     """Compulsory HBM bytes of one launch group, SURVEY.md §8(d) (P = W*H pixels per image):
        pyramid     read P + write the padded level 0 (P) + levels 1..3 (0.328 P), per image, 2 images per stream
        lk_*        both pyramids of the pair read once (2 * 1.328 P) + 17 B per point (8 in, 8 out, 1 status)
-       gftt_response  read P (image) + P (mask); the response map stays on chip; 8 B per pre-candidate written
+       gftt_response  read P (image) + 8 B per tracked point (the detection mask is built on chip from the point list and the
+                      response map stays on chip); 8 B per pre-candidate written
     """
     P = float(W * H)
     pyr = sum(1.0 / 4 ** l for l in range(n_levels))
@@ -235,13 +240,33 @@ def algorithmic_bytes(stage: str, S: int, W: int, H: int, n_pts_total: int, n_le
     if stage in ("lk_temporal", "lk_stereo"):
         return S * 2 * P * pyr + 17.0 * n_pts_total
     if stage == "gftt_response":
-        return S * (P + P) + 8.0 * 20000 * S       # image + mask read, ~20 k pre-candidates written per stream
+        return S * P + 8.0 * n_pts_total + 8.0 * 20000 * S       # image + point list read, ~20 k pre-candidates written per stream
     if stage == "gftt_mask_fill":
         return S * P
     return 0.0
 
 
 # ----------------------------------------------------------------------------------------------------
+def shared_config(args) -> dict:
+    """The workload, identically for both arms (`--impl dvfe` and `--impl reference`)."""
+    from dynamic_vins_b200 import synth
+    c = synth.CONFIGS[WORKLOAD]
+    return {"workload": WORKLOAD, "streams_per_gpu": args.streams, "width": c["width"], "height": c["height"],
+            "stereo": bool(c["stereo"]), "max_cnt": c["max_cnt"], "min_dist": c["min_dist"], "lk": "21x21, maxLevel 3, fwd+bwd",
+            "unique_frames_per_stream": args.frames, "motion_scale": args.motion_scale, "l2": "inputs_larger_than_L2"}
+
+
+def kernel_sources_sha() -> str:
+    """identifies the kernels an ncu capture belongs to: sha1 over dynamic_vins_b200/csrc/*.{cu,cuh,h,cpp}"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "dynamic_vins_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_dvfe(args):
     import torch
     import torch.distributed as dist
@@ -274,7 +299,7 @@ def run_dvfe(args):
     frames = torch.empty((T, 2, S, H, W), dtype=torch.uint8, device=dev)
     for s in range(S):
         st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + rank * S + s, stereo=stereo)
-        frames[:, :, s] = gpu_frames(st, T, dev)
+        frames[:, :, s] = gpu_frames(st, T, dev, args.motion_scale)
     torch.cuda.synchronize()
     order = synth.pingpong_positions(T, args.warmup + args.steps)
     times = [np.full(S, 0.05 * (i + 1)) for i in range(len(order))]
@@ -301,6 +326,7 @@ def run_dvfe(args):
         for i in range(args.warmup):
             f = frames[order[i]]
             trk.track_image_device(f[0].data_ptr(), f[1].data_ptr() if stereo else 0, P, W, times[i])
+        ids_before = sum(int(trk.get_state(s)["next_id"]) for s in range(S))
         trk.profile(True)
         for i in range(args.warmup, args.warmup + args.steps):
             f = frames[order[i]]
@@ -308,6 +334,7 @@ def run_dvfe(args):
         trk.wait(); trk.wait()
         torch.cuda.synchronize()
         prof, prof_steps = trk.profile_read()
+        new_corners_per_step = (sum(int(trk.get_state(s)["next_id"]) for s in range(S)) - ids_before) / max(args.steps, 1)
         n_left = sum(int((trk.features(s)["cam"] == 0).sum()) for s in range(S))
     trk.close()
 
@@ -344,6 +371,22 @@ def run_dvfe(args):
     host = torch.empty((T, 2, S, H, W), dtype=torch.uint8, pin_memory=True)
     host.copy_(frames)
     host_np = host.numpy()
+    # the ceiling of the e2e leg: the same bytes per step copied from the same pinned buffer with nothing else going on, every
+    # rank at once (what scripts/h2d_bw_nranks.py measures stand-alone)
+    n_cam = 2 if stereo else 1
+    scratch = torch.empty((n_cam, S, H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            scratch.copy_(host[0, :n_cam], non_blocking=True)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for i in range(20):
+            scratch.copy_(host[order[i] % T, :n_cam], non_blocking=True)
+        p1.record(stream)
+        barrier()
+        ms_probe = p0.elapsed_time(p1) / 20
+    del scratch
     trk = make_tracker(max(1, min(args.e2e_groups, S)))
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
@@ -365,10 +408,10 @@ def run_dvfe(args):
         n_obs_e2e = sum(len(trk.features(s)) for s in range(S))
     trk.close()
 
-    t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_value, ms_e2e, ms_probe], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_value, ms_e2e = float(t[0]), float(t[1])
+    ms_value, ms_e2e, ms_probe = float(t[0]), float(t[1]), float(t[2])
     total_frames = world * S * args.steps
     value = total_frames / (ms_value * 1e-3)
     e2e = total_frames / (ms_e2e * 1e-3)
@@ -385,30 +428,39 @@ def run_dvfe(args):
         dom = max(stage_ms, key=stage_ms.get)
         n_levels = 4
         ab = algorithmic_bytes(dom, S, W, H, n_left, n_levels)
-        traffic = None
-        try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        # dram bytes, sm / l1tex % and warp instructions of the same kernel from the committed `ncu --set full` capture; they
+        # belong to the kernel sources they were captured from: a capture of other sources is not quoted
+        traffic, sm_l1, ncu_note = None, {}, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("_kernel_sources_sha") == kernel_sources_sha():
+                traffic, sm_l1 = tj.get(dom), tj.get("_sm_l1", {}).get(dom, {})
+                ncu_note = tj.get("_source")
+            else:
+                ncu_note = "profiles/traffic.json was captured from other kernel sources (%s, now %s): not quoted" % (
+                    tj.get("_kernel_sources_sha"), kernel_sources_sha())
         except Exception:
             pass
         achieved = ab / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-        sm_l1 = {}
-        try:      # sm__throughput / l1tex__throughput % of peak of the same kernel, from the committed ncu --set full capture
-            sm_l1 = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("_sm_l1", {}).get(dom, {})
-        except Exception:
-            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "stream_groups": G,
-                       "e2e_stream_groups": max(1, min(args.e2e_groups, S)), "width": W, "height": H, "stereo": stereo,
-                       "max_cnt": c["max_cnt"], "min_dist": c["min_dist"], "lk": "21x21, maxLevel 3, fwd+bwd",
-                       "arithmetic": "u8 pixels, int32/int64 patch sums, fp32 2x2 solve, fp64 box sums and undistortion",
-                       "unique_frames_per_stream": T, "l2": "inputs_larger_than_L2",
-                       "tracked_points_per_step": n_left, "observations_per_step": n_obs},
+            "config": shared_config(args),
+            "run_info": {"stream_groups": G, "e2e_stream_groups": max(1, min(args.e2e_groups, S)),
+                         "arithmetic": "u8 pixels, int32/int64 patch sums, fp32 2x2 solve, fp64 box sums and undistortion",
+                         "tracked_points_per_step": n_left, "observations_per_step": n_obs,
+                         "new_corners_per_step": new_corners_per_step,
+                         "step": "one CUDA graph launch per stream group (%d kernels each) + the level-0 copies" % (launches // max(1, args.steps * G))},
             "clocks": clock_info,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int((2 if stereo else 1) * S * P), "d2h_bytes_per_step": int(S * (2 * c["max_cnt"] * 64 + 4))},
+                    "h2d_bytes_per_step": int((2 if stereo else 1) * S * P), "d2h_bytes_per_step": int(S * (2 * c["max_cnt"] * 64 + 4)),
+                    # the host->device link is the roof of this leg: the step's bytes against a bare copy of the same bytes
+                    # from the same pinned buffer, all ranks copying at once (scripts/h2d_bw_nranks.py stand-alone)
+                    "roofline": {"bound": "pcie_h2d", "achieved": (2 if stereo else 1) * S * P / (ms_e2e / args.steps * 1e-3) / 1e9,
+                                 "peak": (2 if stereo else 1) * S * P / (ms_probe * 1e-3) / 1e9, "unit": "GB/s per GPU",
+                                 "frac": ms_probe / (ms_e2e / args.steps),
+                                 "peak_source": "bare pinned->device copies of one step's bytes, measured in this run, slowest rank"}},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -419,10 +471,12 @@ def run_dvfe(args):
                          # warp instructions per launch (ncu, static) / live launch time, against 4 issue slots x 148 SMs x SM clock
                          "issue_slot_frac": (sm_l1["warp_inst"] / (stage_ms[dom] * 1e-3) / (4 * 148 * (clock_info.get("sm_mhz") or 1965.0) * 1e6)
                                              if sm_l1.get("warp_inst") and stage_ms[dom] > 0 else None),
-                         "note": "issue/latency-bound integer kernel (see profiles/ncu_r1_v6_summary.md); traffic above the "
-                                 "algorithmic bytes is the forward-template cache the stereo call writes for the next temporal call"},
+                         "ncu_capture": ncu_note,
+                         "note": "issue-bound integer kernel: one warp per point, ~70 % of the issue slots busy (profiles/"
+                                 "ncu_r2_summary.md); traffic above the algorithmic bytes is the template cache the stereo call "
+                                 "writes for the next temporal call"},
         }
-        out["config"]["host_placement"] = numa_note
+        out["run_info"]["host_placement"] = numa_note
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)      # the CPU baseline may use every host core
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
@@ -435,9 +489,11 @@ def run_dvfe(args):
 
 def run_dvfe_dynamic(args):
     """BASELINE.json configs[2]: dynamic mode (TrackSemanticImage + InstsTrack + Output) on S streams of 1280x720
-    stereo with 8 instance masks each.  Host buffers in, records out, through the pipelined dvfe_track_dynamic_async +
-    dvfe_wait: the number reported is end to end (there is no device-resident variant of the instance interface).  8 distinct synthetic streams are
-    replicated to S streams (the numpy scene generator is slow); single GPU only."""
+    stereo with 8 instance masks each, pipelined (two frames in flight), records read back every step.  Three legs:
+      value         frames AND the per-stream label image resident in HBM (dvfe_track_dynamic_ex, DEVICE_INPUT | LABELS)
+      e2e           pinned host images + one label image per stream in, records out (LABELS): 3 images per stream cross the bus
+      e2e_masks     the interface of round 1: host images + inv_merge_mask + one host ROI mask per box
+    8 distinct synthetic streams are replicated to S streams (the numpy scene generator is slow); single GPU only."""
     import torch
     from dynamic_vins_b200 import BatchTracker, lib, make_config, synth
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -448,49 +504,77 @@ def run_dvfe_dynamic(args):
     S, T = args.streams, min(args.frames, 6)
     base = [synth.make_stream(WORKLOAD, s) for s in range(min(8, S))]
     frames = [[st.frame(k) for st in base] for k in range(T)]
-    def stack(k, attr):     # pinned host memory, like the headline workload's e2e leg
-        a = np.stack([getattr(frames[k][s % len(base)], attr) for s in range(S)])
+    labs = [[synth.label_image(fr) for fr in frames[k]] for k in range(T)]
+    def stack(k, get):     # pinned host memory, like the headline workload's e2e leg
+        a = np.stack([get(k, s % len(base)) for s in range(S)])
         return torch.from_numpy(a).pin_memory().numpy()
-    Ls = [stack(k, "gray0") for k in range(T)]; Rs = [stack(k, "gray1") for k in range(T)]
-    Ms = [stack(k, "inv_merge_mask") for k in range(T)]
+    Ls = [stack(k, lambda k, j: frames[k][j].gray0) for k in range(T)]
+    Rs = [stack(k, lambda k, j: frames[k][j].gray1) for k in range(T)]
+    Ms = [stack(k, lambda k, j: frames[k][j].inv_merge_mask) for k in range(T)]
+    LABs = [stack(k, lambda k, j: labs[k][j][0]) for k in range(T)]
+    dL = [torch.from_numpy(a).cuda() for a in Ls]; dR = [torch.from_numpy(a).cuda() for a in Rs]
+    dLAB = [torch.from_numpy(a).cuda() for a in LABs]
     # the dvfe_inst_in arrays a C++ caller holds natively (Box2D + InstRoi), built once per unique frame
     boxes = [BatchTracker.marshal_boxes([frames[k][s % len(base)].boxes for s in range(S)]) for k in range(T)]
-    cfg = make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S,
-                      max_dynamic_cnt=c["max_dynamic_cnt"], min_dynamic_dist=c["min_dynamic_dist"],
-                      use_mask_morphology=c["use_mask_morphology"], mask_morphology_size=c["mask_morphology_size"],
-                      max_instances=8, device=local, n_groups=max(1, min(args.dyn_groups, S)))
-    trk = BatchTracker(cfg)
+    lboxes = [BatchTracker.marshal_boxes([labs[k][s % len(base)][1] for s in range(S)]) for k in range(T)]
     order = synth.pingpong_positions(T, args.warmup + args.steps)
     ones = [1] * S
-    def step(i):       # pipelined: frame i is enqueued, then the records of frame i-1 are waited for
-        k = order[i]
-        trk.track_dynamic_async(Ls[k], Rs[k], Ms[k], ones, boxes[k], 0.05 * (i + 1))
-        if i > 0:
-            trk.wait()
-    for i in range(args.warmup):
-        step(i)
-    launches0 = lib().dvfe_kernel_launches()
-    t0 = time.perf_counter()
-    for i in range(args.warmup, args.warmup + args.steps):
-        step(i)
-    trk.wait()
-    dt = time.perf_counter() - t0
-    n_inst = sum(len(trk.insts_output(s)) for s in range(S))
-    n_bg = sum(int((trk.features(s)["cam"] == 0).sum()) for s in range(S))
-    value = S * args.steps / dt
+
+    def run(kind, groups):
+        cfg = make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True, n_streams=S,
+                          max_dynamic_cnt=c["max_dynamic_cnt"], min_dynamic_dist=c["min_dynamic_dist"],
+                          use_mask_morphology=c["use_mask_morphology"], mask_morphology_size=c["mask_morphology_size"],
+                          max_instances=8, device=local, n_groups=max(1, min(groups, S)))
+        trk = BatchTracker(cfg)
+        def step(i):       # pipelined: frame i is enqueued, then the records of frame i-1 are waited for
+            k = order[i]
+            if kind == "device":
+                trk.track_dynamic_labels_async(dL[k].data_ptr(), dR[k].data_ptr(), dLAB[k].data_ptr(), lboxes[k], 0.05 * (i + 1), device=True)
+            elif kind == "labels":
+                trk.track_dynamic_labels_async(Ls[k], Rs[k], LABs[k], lboxes[k], 0.05 * (i + 1))
+            else:
+                trk.track_dynamic_async(Ls[k], Rs[k], Ms[k], ones, boxes[k], 0.05 * (i + 1))
+            if i > 0:
+                trk.wait()
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        launches0 = lib().dvfe_kernel_launches()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, args.warmup + args.steps):
+            step(i)
+        trk.wait()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res = dict(ms=dt / args.steps * 1e3, fps=S * args.steps / dt, launches=int(lib().dvfe_kernel_launches() - launches0),
+                   n_inst=sum(len(trk.insts_output(s)) for s in range(S)),
+                   n_bg=sum(int((trk.features(s)["cam"] == 0).sum()) for s in range(S)), groups=cfg.n_groups,
+                   records=[(trk.features(s).tobytes(), trk.insts_output(s).tobytes()) for s in range(min(S, 8))])
+        trk.close()
+        return res
+
+    dev = run("device", args.groups)
+    lab = run("labels", args.dyn_groups)
+    msk = run("masks", args.dyn_groups)
+    assert dev["records"] == lab["records"] == msk["records"], "the three input forms must give identical records"
     mask_bytes = sum(int(b["mask"].size) for s_ in range(S) for b in frames[0][s_ % len(base)].boxes)
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    P = c["width"] * c["height"]
+    out = {"metric": METRIC, "value": dev["fps"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic",
            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "width": c["width"], "height": c["height"], "stereo": True,
                       "mode": "dynamic: TrackSemanticImage + InstsTrack(8 instances) + Output", "max_cnt": c["max_cnt"],
-                      "max_dynamic_cnt": c["max_dynamic_cnt"], "background_points_per_step": n_bg,
-                      "instance_points_per_step": n_inst, "stream_groups": cfg.n_groups,
-                      "timing": "wall clock around the pipelined host-buffer calls (dvfe_track_dynamic_async + dvfe_wait)"},
-           "e2e": {"value": value, "unit": UNIT, "ms_per_step": dt / args.steps * 1e3,
-                   "h2d_bytes_per_step": int(3 * S * c["width"] * c["height"] + mask_bytes), "d2h_bytes_per_step": None},
-           "gpu_launches": int(lib().dvfe_kernel_launches() - launches0)}
-    trk.close()
+                      "max_dynamic_cnt": c["max_dynamic_cnt"], "background_points_per_step": dev["n_bg"],
+                      "instance_points_per_step": dev["n_inst"], "stream_groups": dev["groups"], "e2e_stream_groups": lab["groups"],
+                      "timing": "wall clock around the pipelined calls (dvfe_track_dynamic_ex + dvfe_wait), device synchronised "
+                                "on both sides; value = frames and label images resident in HBM",
+                      "identical_records_all_input_forms": True},
+           "e2e": {"value": lab["fps"], "unit": UNIT, "ms_per_step": lab["ms"], "h2d_bytes_per_step": int(3 * S * P),
+                   "d2h_bytes_per_step": None, "input": "pinned host gray0, gray1 and one u8 label image per stream"},
+           "e2e_host_masks": {"value": msk["fps"], "unit": UNIT, "ms_per_step": msk["ms"],
+                              "h2d_bytes_per_step": int(3 * S * P + mask_bytes),
+                              "input": "pinned host gray0, gray1, inv_merge_mask + one host ROI mask per box (round-1 interface)"},
+           "gpu_launches": dev["launches"]}
     print(json.dumps(out), flush=True)
 
 
@@ -518,7 +602,8 @@ def cpu_baseline(budget_s: float) -> dict:
     import cv2
     st, fe = _oracle_frontend(0)
     T = 6
-    frames = [st.frame(k) for k in range(T)]
+    ms = float(os.environ.get("DVFE_BENCH_MOTION", "1"))
+    frames = [st.frame(k, pos=k * ms) for k in range(T)]
     from dynamic_vins_b200.synth import pingpong_positions
     order = pingpong_positions(T, 100000)
     # warm-up
@@ -589,7 +674,8 @@ def _ref_worker(wid: int, T: int, conn, workload: str):
     cv2.setNumThreads(1)
     apply_overrides()
     st, fe = _oracle_frontend(wid, workload)
-    frames = [st.frame(k) for k in range(T)]
+    ms = float(os.environ.get("DVFE_BENCH_MOTION", "1"))
+    frames = [st.frame(k, pos=k * ms) for k in range(T)]
     from dynamic_vins_b200.synth import pingpong_positions
     i = 0
     conn.send("ready")
@@ -649,9 +735,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "width": c["width"], "height": c["height"],
-                      "stereo": bool(c["stereo"]), "max_cnt": c["max_cnt"], "min_dist": c["min_dist"],
-                      "lk": "21x21, maxLevel 3, fwd+bwd", "unique_frames_per_stream": args.frames},
+           "config": shared_config(args),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "port",
                             "sample": f"{n_workers} processes x {args.steps} frames, one {WORKLOAD} stream each "
                                       f"(cv2 {cv2.__version__}, 1 thread per process)"},
@@ -681,6 +765,7 @@ if __name__ == "__main__":
         os.environ["DVFE_BENCH_MAX_CNT"] = str(a.max_cnt)
     if a.min_dist:
         os.environ["DVFE_BENCH_MIN_DIST"] = str(a.min_dist)
+    os.environ["DVFE_BENCH_MOTION"] = repr(a.motion_scale)
     apply_overrides()
     if a.impl == "reference":
         run_reference(a)

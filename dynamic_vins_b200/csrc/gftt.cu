@@ -18,7 +18,10 @@
 // rejected once a stronger neighbour is accepted), which yields exactly the sequential result, and the
 // first K accepted corners in rank order are the reference's output.
 #include <float.h>
+#include <string.h>
 #include <math.h>
+
+#include <cuda.h>
 
 #include "kernels.cuh"
 
@@ -127,7 +130,9 @@ __global__ void __launch_bounds__(128) k_disc_mask_op(uint8_t* mask, int pitch, 
 #endif
 constexpr int kRsUnroll = RS_UNROLL;
 #define RS_TILE_ROWS (RS_ROWS + 6)
-#define RS_TILE_PITCH 40          // 34 columns (28 + 2 x 3 halo) at any 4-byte alignment: 10 words
+#define RS_TILE_PITCH 64          // 34 columns (28 + 2 x 3 halo) starting at any byte of a 16-byte aligned row segment: the TMA box
+                                  // must START on a 16-byte boundary of the tensor row (a misaligned start coordinate raises an
+                                  // illegal-instruction fault: scripts/probes/tma_probe.cu), so the box is 64 bytes wide
 
 #ifndef RS_OPT_I2F
 #define RS_OPT_I2F 1
@@ -141,9 +146,10 @@ __device__ __forceinline__ float u8_to_float(unsigned v) {
 #endif
 }
 
-struct RespSmem {
-    uint8_t img[RS_TILE_ROWS * RS_TILE_PITCH];   // rows y0-3 .. y1+2 of the strip, columns xb-3 .. xb+30 (+ alignment)
+struct __align__(128) RespSmem {
+    uint8_t img[RS_TILE_ROWS * RS_TILE_PITCH];   // rows y0-3 .. y1+2 of the strip, columns xb-3 .. xb+30 (+ alignment); TMA box
     unsigned bits[64];                           // detection mask of rows y0 .. y1-1: bit l = column xb + l - 2 is unmasked
+    unsigned long long mbar;                     // completion barrier of the TMA tile load
 };
 
 struct RespCtx {                 // per-strip constants of the marching stencil
@@ -259,6 +265,7 @@ __device__ __forceinline__ void rs_cp_async4(void* smem_dst, const void* gmem_sr
 // rows), region mask, the points whose discs are cut out of it.
 struct RespIn {
     const uint8_t* __restrict__ img; int pitch, w, h; bool bordered;
+    const CUtensorMap* tmap; int tma_x, tma_y;      // non-null: the tile is box (tma_x, tma_y) of this 2-D tensor (TMA load)
     const uint8_t* __restrict__ region; int region_pitch;     // nullable
     const float2* __restrict__ pts; int n_pts, radius;        // discs (n_pts = 0: none)
 };
@@ -271,12 +278,25 @@ __device__ __forceinline__ void resp_strip(RespSmem& sm, const RespIn& in, int x
     const int y1 = min(y0 + rows, h), rows_n = y1 - y0, n_t = rows_n + 6;
     // ---- 1. the strip's pixels: rows y0-3 .. y1+2, columns xb-3 .. xb+30 ----
     int coff;                                      // tile column of image column xb-3
-    if (in.bordered) {
+    if (in.tmap != nullptr) {
+        // One TMA box load (cp.async.bulk.tensor, 64 x 54 bytes) instead of 17 cp.async per lane: lane 0 arms the barrier
+        // with the box size and issues it; everybody waits on the barrier after the mask is built.
+        coff = in.tma_x & 15;
+        const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sm.mbar);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(RS_TILE_ROWS * RS_TILE_PITCH) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(sm.img)), "l"((unsigned long long)in.tmap), "r"(in.tma_x & ~15), "r"(in.tma_y),
+                           "r"(mbar) : "memory");
+        }
+    } else if (in.bordered) {
         const int x_al = (xb - 3) & ~3;
         coff = (xb - 3) - x_al;
         const uint8_t* __restrict__ src = in.img + (ptrdiff_t)(y0 - 3) * in.pitch + x_al;
-        for (int t = lane; t < n_t * (RS_TILE_PITCH / 4); t += 32) {
-            const int r = t / (RS_TILE_PITCH / 4), w4 = (t - r * (RS_TILE_PITCH / 4)) * 4;
+        for (int t = lane; t < n_t * 10; t += 32) {            // 10 aligned words hold the 34 columns
+            const int r = t / 10, w4 = (t - r * 10) * 4;
             rs_cp_async4(sm.img + r * RS_TILE_PITCH + w4, src + (ptrdiff_t)r * in.pitch + w4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -341,7 +361,14 @@ __device__ __forceinline__ void resp_strip(RespSmem& sm, const RespIn& in, int x
     } else {
         need = (1ull << (rows_n + 5)) - 1ull;          // every row: y0-3 .. y1+1
     }
-    if (in.bordered) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (in.tmap != nullptr) {
+        __syncwarp();                      // the barrier initialised by lane 0 is visible
+        const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sm.mbar);
+        asm volatile("{\n\t.reg .pred p;\n\tRS_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra RS_DONE;\n\tbra RS_WAIT;\n\tRS_DONE:\n\t}"
+                     ::"r"(mbar) : "memory");
+    } else if (in.bordered) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncwarp();
     if (need == 0ull) return;
 
@@ -386,7 +413,11 @@ __device__ __forceinline__ void resp_strip(RespSmem& sm, const RespIn& in, int x
 
 // rows = strip height: RS_ROWS when the launch has enough warps to fill the GPU, RS_ROWS_SMALL for small batches (a single
 // camera), where three times as many, shorter strips cut the latency of the serial march
-__global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_gftt_response(const GfttJob* __restrict__ jobs, int rows) {
+// tmap (use_tma != 0): level 0 of the padded pyramids of ALL jobs of the launch as one 2-D u8 tensor (rows of `img_pitch` bytes,
+// job j's pixel (0,0) at row j * tma_rows_per_job + DVFE_PADY, column DVFE_PADX)
+__global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_gftt_response(const GfttJob* __restrict__ jobs, int rows,
+                                                                                 const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                                                 int tma_rows_per_job) {
     __shared__ RespSmem s_resp[RS_WARPS];
     const GfttJob& J = jobs[blockIdx.z];
     if (!gftt_job_active(J) || J.eig_in != nullptr) return;
@@ -394,6 +425,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_gftt_response(
     if (xb >= J.w || y0 >= J.h) return;
     RespIn in;
     in.img = J.img; in.pitch = J.img_pitch; in.w = J.w; in.h = J.h; in.bordered = J.img_bordered != 0;
+    in.tmap = (use_tma && in.bordered) ? &tmap : nullptr;
+    in.tma_x = DVFE_PADX + xb - 3; in.tma_y = (int)blockIdx.z * tma_rows_per_job + DVFE_PADY + y0 - 3;
     in.region = J.region_mask; in.region_pitch = J.region_pitch;
     in.pts = J.pts; in.n_pts = *J.n; in.radius = J.disc_radius;
     resp_strip<false, true>(s_resp[threadIdx.x >> 5], in, xb, y0, rows, nullptr, J.counters, J.cand, J.cand_cap);
@@ -405,6 +438,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_min_eigen_val(
     if (xb >= w || y0 >= h) return;
     RespIn in;
     in.img = img; in.pitch = pitch; in.w = w; in.h = h; in.bordered = false;
+    in.tmap = nullptr; in.tma_x = 0; in.tma_y = 0;
     in.region = nullptr; in.region_pitch = 0; in.pts = nullptr; in.n_pts = 0; in.radius = 0;
     resp_strip<true, false>(s_resp[threadIdx.x >> 5], in, xb, y0, RS_ROWS, eig, nullptr, nullptr, 0);
 }
@@ -819,7 +853,7 @@ int gftt_prepare_device() {
 #define DVFE_CHECK_RC(call) do { int rc__ = (call); if (rc__ != DVFE_OK) return rc__; } while (0)
 
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
-                cudaStream_t st, cudaEvent_t* marks, cudaEvent_t after_response) {
+                cudaStream_t st, cudaEvent_t* marks, cudaEvent_t after_response, const void* level0_tmap, int tma_rows_per_job) {
     (void)h_jobs;
     if (n_jobs <= 0) return DVFE_OK;
     int mi = 0;
@@ -846,7 +880,10 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
         const long warps = (long)gx * RS_WARPS * ((max_h + RS_ROWS - 1) / RS_ROWS) * n_jobs;
         const int rows = warps >= 148L * 16 ? RS_ROWS : RS_ROWS_SMALL;       // fewer than 16 warps per SM: shorter strips
         dim3 blk(RS_WARPS * 32), grid(gx, (max_h + rows - 1) / rows, n_jobs);
-        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs, rows);
+        CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        if (level0_tmap != nullptr) memcpy(&tm, level0_tmap, sizeof(tm));
+        DVFE_LAUNCH(k_gftt_response, grid, blk, 0, st, d_jobs, rows, tm, level0_tmap != nullptr ? 1 : 0, tma_rows_per_job);
     }
     GFTT_MARK();
     if (after_response) cudaEventRecord(after_response, st);
@@ -855,6 +892,34 @@ int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int ma
     DVFE_LAUNCH(k_gftt_assign_ids, (n_jobs + 127) / 128, 128, 0, st, d_jobs, n_jobs);
 #undef GFTT_MARK
     DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libdvfe does not link libcuda)
+int dvfe_make_level0_tmap(void* out, const uint8_t* base, int pitch, long n_rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            dvfe_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return DVFE_ERR_CUDA;
+        }
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};                       // bytes between rows (dimension 1)
+    const cuuint32_t box[2] = {RS_TILE_PITCH, RS_TILE_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dvfe_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DVFE_ERR_CUDA; }
     return DVFE_OK;
 }
 

@@ -99,8 +99,14 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
 };
 // marks (nullable): 3 events recorded after the mask fill, the discs and the response kernel;
 // after_response (nullable): recorded between the response kernel and the (few-CTA) selection kernel
+// level0_tmap (nullable): a CUtensorMap (128 bytes, dvfe_make_level0_tmap) over level 0 of the padded pyramids the jobs' images
+// live in, job j at tensor row j * tma_rows_per_job: the response kernel then loads its tiles with TMA
 int launch_gftt(const GfttJob* d_jobs, const GfttJob* h_jobs, int n_jobs, int max_w, int max_h, int max_pts,
-                cudaStream_t st, cudaEvent_t* marks = nullptr, cudaEvent_t after_response = nullptr);
+                cudaStream_t st, cudaEvent_t* marks = nullptr, cudaEvent_t after_response = nullptr,
+                const void* level0_tmap = nullptr, int tma_rows_per_job = 0);
+// 2-D u8 tensor map over `n_rows` rows of `pitch` bytes at `base` with the response kernel's tile as box; out = 128 bytes.
+// Returns DVFE_OK, or an error when the driver entry point is unavailable (the caller then launches without TMA).
+int dvfe_make_level0_tmap(void* out, const uint8_t* base, int pitch, long n_rows);
 int gftt_prepare_device();
 int launch_min_eigen_val(const uint8_t* img, int pitch, int w, int h, float* eig, cudaStream_t st);
 int launch_disc_mask(uint8_t* mask, int pitch, int w, int h, const float2* pts, const int* n, int max_pts, int radius,

@@ -214,6 +214,15 @@ int dvfe_tracker::init() {
     }
     DVFE_CHECK(alloc_gftt_scratch(&gsc, B, W, H, (float)cfg.min_dist));
     DVFE_CHECK(gftt_prepare_device());
+    {
+        // level 0 of every stream of a left slot as one 2-D byte tensor: a pyramid is a whole number of level-0 rows
+        const PyrLevel& L0 = desc.lv[0];
+        const long rows = (long)B * (long)(desc.bytes / (unsigned)L0.pitch);
+        use_tma = true;
+        for (int s = 0; s < 3 && use_tma; s++)
+            use_tma = dvfe_make_level0_tmap(tmapL[s], pyrL[s] + L0.offset, L0.pitch, rows) == DVFE_OK;
+        if (const char* e = getenv("DVFE_TMA")) use_tma = use_tma && atoi(e) != 0;          // A/B: 0 = cp.async staging
+    }
     // pitched host->device DMA straight into the padded level 0 runs at full PCIe rate only for rows that are a
     // multiple of 64 bytes; other widths go through a dense staging buffer (one linear copy) and the copy kernel
     staged_upload = (W % 64) != 0;
@@ -380,7 +389,8 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
     DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, with_marks ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
-                           stereo_now ? ev_resp[par] : nullptr));
+                           stereo_now ? ev_resp[par] : nullptr, use_tma ? tmapL[k % 3] : nullptr,
+                           (int)(desc.bytes / (unsigned)desc.lv[0].pitch)));
     if (stereo_now) {
         PyrImgSet rset;
         rset.src[0] = d_right; rset.src[1] = nullptr;

@@ -97,6 +97,10 @@ struct dvfe_tracker {
     double prof_ms[ST_COUNT] = {};
     long prof_steps = 0;
 
+    // TMA descriptors (CUtensorMap, 128 B each) over level 0 of the three left pyramid sets: the corner response loads its
+    // tiles with cp.async.bulk.tensor; use_tma is false when the driver cannot encode them (then cp.async is used)
+    alignas(64) unsigned char tmapL[3][128] = {};
+    bool use_tma = false;
     uint8_t* left_slot(long k) const { return pyrL[k % 3]; }
     uint8_t* right_slot(long k) const { return pyrR[k % 2]; }
 
