@@ -228,6 +228,7 @@ int dvfe_tracker::init() {
     staged_upload = (W % 64) != 0;
     if (const char* e = getenv("DVFE_STAGED_UPLOAD")) staged_upload = atoi(e) != 0;      // experiment / override
     if (const char* e = getenv("DVFE_GRAPHS")) use_graphs = atoi(e) != 0;                // A/B: 0 = plain launches
+    if (const char* e = getenv("DVFE_REUSE")) use_reuse = atoi(e) != 0;
     if (staged_upload)
         for (int p = 0; p < 2; p++) DVFE_CHECK(dmalloc(&d_stage[p], 2 * B * P));
 
@@ -379,7 +380,7 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
     // are the stereo call's forward templates at those levels for the survivors: stored by the former, picked up through
     // the compaction's old-index map by the latter.
     const int site_t = semantic ? DVFE_LK_SEMANTIC_TEMPORAL : DVFE_LK_RAW_TEMPORAL;
-    const bool reuse = k > 0 && stereo_now && cfg.flow_back && d_tcache_bwd != nullptr;
+    const bool reuse = use_reuse && k > 0 && stereo_now && cfg.flow_back && d_tcache_bwd != nullptr;
     if (k > 0)   // bg.TrackLeft / FeatureTrackByLK(prev.gray0, gray0, last_points)
         DVFE_CHECK(launch_lk(d_groups[ph][semantic ? 1 : 0], B, cap, cfg.lk_max_level, cfg.flow_back, st, lk_back_level[site_t],
                              lk_fb_thresh[site_t], (tcache_valid ? LK_TCACHE_READ : 0) | (reuse ? LK_TCACHE_WRITE_BWD : 0)));
@@ -437,6 +438,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
             if (stereo_now) {
                 set.src[0] = d_right; set.dst[0] = right_slot(k);
                 if (k >= 1) DVFE_CUDA(cudaStreamWaitEvent(rs, ev_begin[1 - par], 0));
+                // ... and behind the upload of this step when the source is the tracker's own staging buffer (widths whose rows
+                // are not a multiple of 64 bytes); for caller-resident images the event is an old, completed one
+                DVFE_CUDA(cudaStreamWaitEvent(rs, ev_up[par], 0));
                 DVFE_CHECK(launch_pyr_level0(set, B, desc, pitch, rs));
                 DVFE_CUDA(cudaEventRecord(ev_r0[par], rs));
                 DVFE_CUDA(cudaStreamWaitEvent(st, ev_r0[par], 0));

@@ -183,6 +183,17 @@ def test_erode_bit_exact():
         assert crc(ops.erode_rect(m, k)) == int(g[f"erode{k}_crc"])
     fr = synth.make_stream("c3_zed_dynamic", 0).frame(0)
     assert np.array_equal(ops.erode_rect(fr.inv_merge_mask, 20), cvfe.erode_mask(fr.inv_merge_mask, 20))
+    # the kernels take a word-wise AND path on binary masks and fall back to the byte-wise minimum otherwise: arbitrary u8
+    # data, widths that are not a multiple of 4, binary masks with a few grey pixels, all-255 and all-0 masks
+    rng = np.random.default_rng(12)
+    for (h, w) in ((37, 53), (64, 96), (5, 7), (90, 121)):
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        binary = (rng.random((h, w)) > 0.2).astype(np.uint8) * 255
+        mixed = binary.copy()
+        mixed[rng.integers(0, h, 6), rng.integers(0, w, 6)] = 97
+        for m2 in (grey, binary, mixed, np.full((h, w), 255, np.uint8), np.zeros((h, w), np.uint8)):
+            for k in (1, 2, 3, 4, 5, 7, 20):
+                assert np.array_equal(ops.erode_rect(m2, k), cvfe.erode_mask(m2, k)), (h, w, k)
 
 
 def test_lift_projective_bit_exact():

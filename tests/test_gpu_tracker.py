@@ -704,3 +704,36 @@ def test_dynamic_pipelined_equals_synchronous(groups):
         assert sync.features(s).tobytes() == pipe.features(s).tobytes()
         assert sync.insts_output(s).tobytes() == pipe.insts_output(s).tobytes()
     sync.close(); pipe.close()
+
+
+def test_graph_replay_equals_plain_launches_with_staged_upload():
+    """The frame step replayed as a CUDA graph must order the right image's level-0 copy behind the upload of the tracker's
+    staging buffer (widths whose rows are not a multiple of 64 bytes go through it).  24 C2-shaped streams make the upload
+    long enough (22 MB) that a copy kernel that does not wait for it reads an unwritten buffer: the first frames after a cold
+    start then lose every stereo match.  Graph replay (default) vs plain launches (DVFE_GRAPHS=0), pipelined, byte for byte."""
+    name, B, T = "c2_kitti_stereo", 24, 4
+    src = [synth.make_stream(name, 70 + s) for s in range(4)]
+    frames = [[s.frame(k) for s in src] for k in range(T)]
+    L = [np.stack([frames[k][s % 4].gray0 for s in range(B)]) for k in range(T)]
+    R = [np.stack([frames[k][s % 4].gray1 for s in range(B)]) for k in range(T)]
+    out = {}
+    for graphs in ("0", "1"):
+        os.environ["DVFE_GRAPHS"] = graphs
+        try:
+            trk = BatchTracker(cfg_of(name, n_streams=B, n_groups=2))
+        finally:
+            del os.environ["DVFE_GRAPHS"]
+        rec = []
+        trk.track_image_async(L[0], R[0], frames[0][0].time0)
+        for k in range(1, T):
+            trk.track_image_async(L[k], R[k], frames[k][0].time0)
+            trk.wait()
+            rec.append([trk.features(s).tobytes() for s in range(B)])
+        trk.wait()
+        rec.append([trk.features(s).tobytes() for s in range(B)])
+        trk.close()
+        out[graphs] = rec
+    assert out["0"] == out["1"]
+    from dynamic_vins_b200 import _lib
+    n_right = int((np.frombuffer(out["1"][1][0], dtype=_lib.OBS_DTYPE)["cam"] == 1).sum())
+    assert n_right > 100, "stereo matches of the second frame are missing"
