@@ -382,7 +382,7 @@ def run_dvfe(args):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
         for i in range(20):
-            scratch.copy_(host[order[i] % T, :n_cam], non_blocking=True)
+            scratch.copy_(host[order[i % len(order)] % T, :n_cam], non_blocking=True)
         p1.record(stream)
         barrier()
         ms_probe = p0.elapsed_time(p1) / 20
