@@ -136,3 +136,32 @@ def punch_out(merge_mask, inv_merge_mask, roi_mask, rect):
     assert r.shape == (rh, rw)
     L.check(L.lib().dvfe_op_punch_out(L.ptr(m), L.ptr(iv), w, h, L.ptr(r), r.strides[0], int(x), int(y), int(rw), int(rh)))
     return m, iv
+
+
+def reject_with_f(cam: dict, cur_pts, prev_pts, col: int, row: int, f_threshold: float = 1.0):
+    """InstsFeatManager::RejectWithF (front_end/dynamic_tracker.cpp:831-849) -> status u8 (empty when fewer than 7 points)."""
+    c = L.Camera(**{k: float(cam[k]) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")})
+    a = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    if len(a) != len(b):
+        raise ValueError("reject_with_f: cur_pts and prev_pts must have the same length")
+    st = np.zeros(max(len(a), 1), np.uint8)
+    n = C.c_int(0)
+    L.check(L.lib().dvfe_op_reject_with_f(C.byref(c), L.ptr(a), L.ptr(b), len(a), int(col), int(row), float(f_threshold), L.ptr(st),
+                                          C.byref(n)))
+    return st[:n.value].copy()
+
+
+def detect_extra_points(roi_mask, disp, box_xy, fx: float, fy: float, cx: float, cy: float, baseline: float):
+    """InstFeat::DetectExtraPoints (front_end/instance_feature.cpp:413-461) -> (n, 3) float64 (x, y, depth)."""
+    m = _u8(roi_mask)
+    rows, cols = m.shape
+    d = np.ascontiguousarray(disp, np.float32)
+    step = int(max(np.sqrt(0.8 * rows * cols / 1000.), 2.))
+    cap = ((cols + step - 1) // step) * ((rows + step - 1) // step)
+    out = np.zeros((cap, 3), np.float64)
+    n = C.c_int(0)
+    L.check(L.lib().dvfe_op_detect_extra_points(L.ptr(m), rows, cols, m.strides[0], L.ptr(d), d.shape[1], d.shape[0], d.strides[0] // 4,
+                                                int(box_xy[0]), int(box_xy[1]), float(fx), float(fy), float(cx), float(cy), float(baseline),
+                                                L.ptr(out), cap, C.byref(n)))
+    return out[:n.value].copy()

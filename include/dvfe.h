@@ -321,6 +321,27 @@ int dvfe_track_dynamic_async(dvfe_tracker* t, const uint8_t* left, const uint8_t
 int dvfe_set_input(dvfe_tracker* t, int channels);
 int dvfe_set_undistort_maps(dvfe_tracker* t, int cam, const int16_t* map1, const uint16_t* map2);
 
+/* ---- epipolar outlier rejection and extra points --------------------------------------
+ * InstsFeatManager::RejectWithF (front_end/dynamic_tracker.cpp:831-849; FeatureTracker::RejectWithF,
+ * front_end/background_tracker.cpp:520-550, is the same call): cur_pts / prev_pts are n distorted pixel positions (x, y);
+ * both are lifted with `cam` (PinholeCamera::liftProjective), re-projected with kFocalLength = 460 about (col/2, row/2),
+ * narrowed to float and given to cv::findFundamentalMat(cur, prev, FM_RANSAC, f_threshold, 0.99, status).
+ * status[n] receives the inlier bytes; *n_status = n, or 0 when n < 7 (OpenCV then leaves `status` empty).  The sample order
+ * is that of cv::RNG(-1), the 7-point models are solved in fp64; see dynamic_vins_b200/csrc/geometry.cu for what is and is not
+ * reproducible about OpenCV's null-space basis (ties between roots of one sample, LMedS with 8 <= n <= 13). */
+int dvfe_op_reject_with_f(const dvfe_camera* cam, const float* cur_pts, const float* prev_pts, int n, int col, int row,
+                          double f_threshold, uint8_t* status, int* n_status);
+
+/* InstFeat::DetectExtraPoints (front_end/instance_feature.cpp:413-461): samples the ROI mask (rows x cols, box2d->rect.tl() =
+ * (box_x, box_y)) on the reference's grid (step = max(sqrt(0.8*rows*cols/1000), 2)), reads the CV_32F disparity map at the
+ * full-image position and emits (x, y, depth) = ((c-cx)*depth/fx, (r-cy)*depth/fy, fx*baseline/disparity) for samples with
+ * mask != 0, disparity > 0 and not NaN, 0.1 < depth <= 100 (float arithmetic, CameraInfo's float intrinsics), in row-major sample
+ * order.  out = 3 doubles per point (extra_points3d is a vector<Vec3d>), cap points; *n_out = the count (DVFE_ERR_CAPACITY if
+ * it exceeds cap). */
+int dvfe_op_detect_extra_points(const uint8_t* roi_mask, int rows, int cols, int mask_pitch, const float* disp, int disp_w,
+                                int disp_h, int disp_pitch, int box_x, int box_y, float fx, float fy, float cx, float cy,
+                                float baseline, double* out, int cap, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,8 +13,25 @@
 #include <cstring>
 #include <stdexcept>
 
+// InstsFeatManager::RejectWithF is a private member (never called by the reference itself): the checker reaches it by
+// parsing the reference's class declarations with `private` spelled `public` in THIS translation unit only (standard headers
+// are included before).  The reference's own translation units are compiled untouched.
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include "dvshim_cv.hpp"
+#include "dvshim_eigen.hpp"
+#define private public
 #include "front_end/background_tracker.h"
 #include "front_end/dynamic_tracker.h"
+#undef private
 #include "front_end/feature_utils.h"
 #include "front_end/front_end_parameters.h"
 #include "camodocal/camera_models/PinholeCamera.h"
@@ -72,6 +89,10 @@ void dvref_set_hooks(void* lk, void* gftt, void* erode, void* circle, void* bgr2
     h.erode_rect = reinterpret_cast<decltype(h.erode_rect)>(erode);
     h.circle_filled = reinterpret_cast<decltype(h.circle_filled)>(circle);
     h.bgr2gray = reinterpret_cast<decltype(h.bgr2gray)>(bgr2gray);
+}
+void dvref_set_hook_fundamental(void* fm) {
+    auto& h = dvshim::hooks();
+    h.find_fundamental_mat = reinterpret_cast<decltype(h.find_fundamental_mat)>(fm);
 }
 
 // ---- camodocal::PinholeCamera ------------------------------------------------------------------------------------
@@ -340,6 +361,45 @@ int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char
             }
         *n_iout = n;
         return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// InstsFeatManager::RejectWithF on a free-standing instance holding (curr_points, last_points); needs a dynamic-mode front end
+// (cam_t.cam0 and fe_para::kFThreshold are the globals dvref_front_end_new set).  Returns the size of the status vector.
+int dvref_reject_with_f(void* p, const float* cur, const float* prev, int n, int col, int row, unsigned char* status) {
+    try {
+        auto* fe = static_cast<RefFrontEnd*>(p);
+        if (!fe->insts) throw std::runtime_error("dvref_reject_with_f needs a dynamic-mode front end");
+        InstFeat inst;
+        for (int i = 0; i < n; i++) {
+            inst.curr_points.emplace_back(cur[2 * i], cur[2 * i + 1]);
+            inst.last_points.emplace_back(prev[2 * i], prev[2 * i + 1]);
+        }
+        const std::vector<uchar> st = fe->insts->RejectWithF(inst, col, row);
+        for (size_t i = 0; i < st.size(); i++) status[i] = st[i];
+        return (int)st.size();
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// InstFeat::DetectExtraPoints on a free-standing instance: ROI mask + box, full-size CV_32F disparity map; cam_s = {fx, fy, cx,
+// cy, baseline} (CameraInfo's float members).  out = 3 doubles per point; returns the count.
+int dvref_detect_extra_points(const unsigned char* mask, int rows, int cols, const float* disp, int disp_rows, int disp_cols, int box_x,
+                              int box_y, const float* cam, double* out, int cap) {
+    try {
+        cam_s.fx0 = cam[0]; cam_s.fy0 = cam[1]; cam_s.cx0 = cam[2]; cam_s.cy0 = cam[3]; cam_s.baseline = cam[4];
+        InstFeat inst;
+        inst.roi = std::make_shared<InstRoi>();
+        inst.roi->mask_cv = cv::Mat(rows, cols, CV_8UC1, const_cast<unsigned char*>(mask)).clone();
+        inst.roi->roi_gray = cv::Mat(rows, cols, CV_8UC1, cv::Scalar(0));
+        inst.box2d = std::make_shared<Box2D>();
+        inst.box2d->rect = cv::Rect2f((float)box_x, (float)box_y, (float)cols, (float)rows);
+        cv::Mat d(disp_rows, disp_cols, CV_32FC1, const_cast<float*>(disp));
+        inst.DetectExtraPoints(d);
+        const int n = (int)inst.extra_points3d.size();
+        for (int i = 0; i < n && i < cap; i++) {
+            out[3 * i] = inst.extra_points3d[i].x(); out[3 * i + 1] = inst.extra_points3d[i].y(); out[3 * i + 2] = inst.extra_points3d[i].z();
+        }
+        return n;
     } catch (const std::exception& e) { return fail(e); }
 }
 

@@ -103,7 +103,21 @@ def _gray(src, dst, rows, cols, ss, ds):
     _view(dst, rows, cols, ds)[:] = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY)
 
 
+_FM_T = C.CFUNCTYPE(C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_double, C.c_double, _u8p)
+
+
+def _fundamental(p1, p2, n, method, param1, param2, mask):
+    a = np.ctypeslib.as_array(p1, (n, 2)).copy()
+    b = np.ctypeslib.as_array(p2, (n, 2)).copy()
+    F, m = cv2.findFundamentalMat(a, b, method, param1, param2)
+    if F is None or m is None:          # OpenCV leaves the mask unwritten: reported as zeros (already zero-filled by the shim)
+        return 0
+    np.ctypeslib.as_array(mask, (n,))[:] = m.ravel()
+    return 1
+
+
 _CALLBACKS = (_LK_T(_lk), _GFTT_T(_gftt), _ERODE_T(_erode), _CIRCLE_T(_circle), _GRAY_T(_gray))   # keep alive
+_FM_CALLBACK = _FM_T(_fundamental)
 _lib = None
 
 
@@ -142,6 +156,10 @@ def lib():
                                           C.POINTER(InstObs), C.c_int, C.POINTER(C.c_int)]
         L.dvref_instance_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dvref_set_hooks(*[C.cast(cb, C.c_void_p) for cb in _CALLBACKS])
+        L.dvref_set_hook_fundamental(C.cast(_FM_CALLBACK, C.c_void_p))
+        L.dvref_reject_with_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.dvref_detect_extra_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -324,7 +342,31 @@ class RefFrontEnd:
                 vel_right=np.array(o.vel_right[:]), is_stereo=bool(o.is_stereo), disp=float(o.disp))
         return {"features": self._points(obs, n.value), "instances": dict(sorted(insts.items()))}
 
+    def reject_with_f(self, cur_pts, prev_pts, col: int, row: int) -> np.ndarray:
+        """InstsFeatManager::RejectWithF on (curr_points, last_points) with this front end's cam0; F_threshold = 1.0"""
+        a = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        st = np.zeros(max(len(a), 1), np.uint8)
+        n = lib().dvref_reject_with_f(self.h, _ptr(a), _ptr(b), len(a), int(col), int(row), _ptr(st))
+        if n < 0:
+            raise RuntimeError(lib().dvref_last_error().decode())
+        return st[:n].copy()
+
     def instance_table(self) -> np.ndarray:
         rows = np.zeros((256, 4), np.int32)
         n = lib().dvref_instance_table(self.h, _ptr(rows), 256)
         return rows[:n]
+
+
+def detect_extra_points(mask, disp, box_xy, fx, fy, cx, cy, baseline) -> np.ndarray:
+    """InstFeat::DetectExtraPoints (front_end/instance_feature.cpp:413-461), reference-compiled -> (n, 3) float64"""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    disp = np.ascontiguousarray(disp, np.float32)
+    cam = np.array([fx, fy, cx, cy, baseline], np.float32)
+    cap = mask.size
+    out = np.zeros((cap, 3), np.float64)
+    n = lib().dvref_detect_extra_points(_ptr(mask), mask.shape[0], mask.shape[1], _ptr(disp), disp.shape[0], disp.shape[1],
+                                        int(box_xy[0]), int(box_xy[1]), _ptr(cam), _ptr(out), cap)
+    if n < 0:
+        raise RuntimeError(lib().dvref_last_error().decode())
+    return out[:n].copy()

@@ -362,6 +362,9 @@ struct Hooks {
     void (*circle_filled)(uchar* img, int rows, int cols, int step, int cx, int cy, int radius, int color) = nullptr;
     // cv::cvtColor(src BGR, dst gray, COLOR_BGR2GRAY)
     void (*bgr2gray)(const uchar* src, uchar* dst, int rows, int cols, int src_step, int dst_step) = nullptr;
+    // cv::findFundamentalMat(points1, points2, method, param1, param2, mask): fills mask[n], returns 1 when a matrix was found
+    int (*find_fundamental_mat)(const float* pts1, const float* pts2, int n, int method, double param1, double param2,
+                                uchar* mask) = nullptr;
 };
 Hooks& hooks();
 }  // namespace dvshim
@@ -442,7 +445,15 @@ inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int le
 
 // ---- declared for parsing only ------------------------------------------------------------------------------------
 inline Mat findHomography(const std::vector<Point2f>&, const std::vector<Point2f>&, int = 0, double = 3) { dvshim_unreachable("cv::findHomography"); }
-inline Mat findFundamentalMat(const std::vector<Point2f>&, const std::vector<Point2f>&, int, double, double, std::vector<uchar>&) { dvshim_unreachable("cv::findFundamentalMat"); }
+inline Mat findFundamentalMat(const std::vector<Point2f>& points1, const std::vector<Point2f>& points2, int method, double param1,
+                              double param2, std::vector<uchar>& mask) {
+    if (!dvshim::hooks().find_fundamental_mat) dvshim_unreachable("cv::findFundamentalMat (no hook registered)");
+    if (points1.size() < 7) return Mat();          // cv::findFundamentalMat: "if( npoints < 7 ) return Mat();" — the mask is not created
+    mask.assign(points1.size(), 0);
+    dvshim::hooks().find_fundamental_mat(points1.empty() ? nullptr : &points1[0].x, points2.empty() ? nullptr : &points2[0].x,
+                                         (int)points1.size(), method, param1, param2, mask.empty() ? nullptr : mask.data());
+    return Mat();      // the callers on the parity path (RejectWithF) use the mask only
+}
 inline bool solve(const Mat&, const Mat&, Mat&, int = DECOMP_LU) { dvshim_unreachable("cv::solve"); }
 inline void convertMaps(const Mat&, const Mat&, Mat&, Mat&, int, bool = false) { dvshim_unreachable("cv::convertMaps"); }
 template <class A, class B>

@@ -531,3 +531,325 @@ void spec_bgr_to_gray(const uint8_t* bgr, int w, int h, int sstride, uint8_t* ds
             dst[(size_t)y * dstride + x] = (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * cv::findFundamentalMat(points1, points2, cv::FM_RANSAC, param1, param2, mask) as InstsFeatManager::RejectWithF calls it
+ * (dynamic_vins/src/front_end/dynamic_tracker.cpp:846; FeatureTracker::RejectWithF, background_tracker.cpp:520-550, is the
+ * same call, commented out).  The algorithm lives in OpenCV (modules/calib3d/src/{fundam,ptsetreg}.cpp), absent from
+ * /root/reference; restated from its published source and pinned against cv2 4.13.0 in tests/test_oracle_pinned.py:
+ *   n < 7        no model, the mask stays empty (returns 0)
+ *   n == 7       the 7-point solver runs once, mask = all ones
+ *   8 <= n < 15  LMedS  (createLMeDSPointSetRegistrator(cb, 7, confidence)): 7-point samples, the model with the smallest
+ *                median (element count/2 after nth_element) error wins, inliers within sigma = 2.5*1.4826*(1+5/(n-7))*sqrt(med)
+ *   n >= 15      RANSAC (createRANSACPointSetRegistrator(cb, 7, threshold, confidence), maxIters 1000)
+ * Samples: cv::RNG(uint64(-1)) (multiply-with-carry, 4164903690), `uniform(0, n)` = next() % n, duplicates redrawn, a sample is
+ * rejected when its last point is collinear with two earlier ones in either image (haveCollinearPoints).
+ * 7-point solver (run7Point): F = lambda*f1 + (1-lambda)*f2 over the null space {f1, f2} of the 7 x 9 epipolar system, lambda
+ * from det F = 0 (cv::solveCubic), each F scaled to F[8] = 1.
+ * What is NOT reproducible about OpenCV here: it takes {f1, f2} from LAPACK's SVD, i.e. an arbitrary orthonormal basis of the
+ * null space; any other basis gives the same F set (to rounding) but numbers the up-to-3 roots differently, so (a) F differs
+ * from cv2's in the last digits and (b) a tie in inlier count between two roots of ONE sample may be won by the other root.
+ * This restatement takes the null space from Gauss-Jordan elimination with complete pivoting.  For 8 <= n <= 13 the LMedS
+ * median is one of the 7 sample points' own residuals (rounding noise), so OpenCV's winner is itself arbitrary there.
+ * The mask it returns equals cv2's in every seeded trial of the pinned test for n == 14 and n >= 15. */
+typedef struct { uint64_t state; } fm_rng;
+static unsigned fm_rng_next(fm_rng* r) {
+    r->state = (uint64_t)(unsigned)r->state * 4164903690u + (unsigned)(r->state >> 32);
+    return (unsigned)r->state;
+}
+static int fm_rng_uniform(fm_rng* r, int a, int b) { return a == b ? a : (int)(fm_rng_next(r) % (unsigned)(b - a) + a); }
+
+static int fm_solve_cubic(const double* c, double* x) {       /* c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0, cv::solveCubic */
+    double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+    if (a0 == 0) {
+        if (a1 == 0) {
+            if (a2 == 0) return a3 == 0 ? -1 : 0;
+            x[0] = -a3 / a2;
+            return 1;
+        }
+        double d = a2 * a2 - 4 * a1 * a3;
+        if (d >= 0) {
+            d = sqrt(d);
+            double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+            if (fabs(q1) > fabs(q2)) { x[0] = q1 / a1; x[1] = a3 / q1; }
+            else { x[0] = q2 / a1; x[1] = a3 / q2; }
+            return d > 0 ? 2 : 1;
+        }
+        return 0;
+    }
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+    double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    double Qcubed = Q * Q * Q;
+    double d = Qcubed - R * R;
+    if (d > 0) {
+        double theta = acos(R / sqrt(Qcubed));
+        double sqrtQ = sqrt(Q);
+        double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+        x[0] = t0 * cos(t1) - t2;
+        x[1] = t0 * cos(t1 + (2. * 3.1415926535897932384626433832795 / 3)) - t2;
+        x[2] = t0 * cos(t1 + (4. * 3.1415926535897932384626433832795 / 3)) - t2;
+        return 3;
+    }
+    if (d == 0) {
+        if (R >= 0) { x[0] = -2 * pow(R, 1. / 3) - a1 / 3; x[1] = pow(R, 1. / 3) - a1 / 3; }
+        else { x[0] = 2 * pow(-R, 1. / 3) - a1 / 3; x[1] = -pow(-R, 1. / 3) - a1 / 3; }
+        return x[0] == x[1] ? 1 : 2;
+    }
+    d = sqrt(-d);
+    double e = pow(d + fabs(R), 1. / 3);
+    if (R > 0) e = -e;
+    x[0] = (e + Q / e) - a1 * (1. / 3);
+    return 1;
+}
+
+/* null space of the 7 x 9 system by Gauss-Jordan elimination with complete pivoting: f1, f2 = the solutions with the two
+ * free unknowns set to (1, 0) and (0, 1).  Returns 0 when the rank is below 7. */
+static int fm_null_space(double A[7][9], double* f1, double* f2) {
+    int perm[9];
+    for (int j = 0; j < 9; j++) perm[j] = j;
+    for (int k = 0; k < 7; k++) {
+        int pr = k, pc = k;
+        double best = -1.0;
+        for (int i = k; i < 7; i++)
+            for (int j = k; j < 9; j++)
+                if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pr = i; pc = j; }
+        if (!(best > 0.0)) return 0;
+        if (pr != k) for (int j = 0; j < 9; j++) { double t = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = t; }
+        if (pc != k) {
+            for (int i = 0; i < 7; i++) { double t = A[i][k]; A[i][k] = A[i][pc]; A[i][pc] = t; }
+            int t = perm[k]; perm[k] = perm[pc]; perm[pc] = t;
+        }
+        const double inv = 1.0 / A[k][k];
+        for (int j = k; j < 9; j++) A[k][j] *= inv;
+        for (int i = 0; i < 7; i++) {
+            if (i == k) continue;
+            const double m = A[i][k];
+            if (m == 0.0) continue;
+            for (int j = k; j < 9; j++) A[i][j] -= m * A[k][j];
+        }
+    }
+    for (int i = 0; i < 7; i++) { f1[perm[i]] = -A[i][7]; f2[perm[i]] = -A[i][8]; }
+    f1[perm[7]] = 1.0; f1[perm[8]] = 0.0;
+    f2[perm[7]] = 0.0; f2[perm[8]] = 1.0;
+    return 1;
+}
+
+static int fm_run7(const float* m1, const float* m2, double* F /* up to 3 x 9 */) {
+    double A[7][9], f1[9], f2[9], c[4], r[3] = {0, 0, 0};
+    for (int i = 0; i < 7; i++) {
+        const double x0 = m1[2 * i], y0 = m1[2 * i + 1], x1 = m2[2 * i], y1 = m2[2 * i + 1];
+        A[i][0] = x1 * x0; A[i][1] = x1 * y0; A[i][2] = x1;
+        A[i][3] = y1 * x0; A[i][4] = y1 * y0; A[i][5] = y1;
+        A[i][6] = x0; A[i][7] = y0; A[i][8] = 1;
+    }
+    if (!fm_null_space(A, f1, f2)) return 0;
+    for (int i = 0; i < 9; i++) f1[i] -= f2[i];
+    double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+    c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+    c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) + f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+           f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) + f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+           f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+    t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+    c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+    c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) + f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+           f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) + f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+           f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+    const int n = fm_solve_cubic(c, r);
+    if (n < 1 || n > 3) return n < 0 ? 0 : n;
+    for (int k = 0; k < n; k++, F += 9) {
+        double lambda = r[k], mu = 1.;
+        const double s = f1[8] * r[k] + f2[8];
+        if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; F[8] = 1.; }
+        else F[8] = 0.;
+        for (int i = 0; i < 8; i++) F[i] = f1[i] * lambda + f2[i] * mu;
+    }
+    return n;
+}
+
+static int fm_collinear(const float* p, int count) {          /* haveCollinearPoints: only the last point is tested */
+    const int i = count - 1;
+    for (int j = 0; j < i; j++) {
+        const double dx1 = p[2 * j] - p[2 * i], dy1 = p[2 * j + 1] - p[2 * i + 1];
+        for (int k = 0; k < j; k++) {
+            const double dx2 = p[2 * k] - p[2 * i], dy2 = p[2 * k + 1] - p[2 * i + 1];
+            if (fabs(dx2 * dy1 - dy2 * dx1) <= FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return 1;
+        }
+    }
+    return 0;
+}
+
+static int fm_get_subset(const float* m1, const float* m2, int count, fm_rng* rng, int max_attempts, float* s1, float* s2) {
+    int idx[7];
+    for (int iters = 0; iters < max_attempts; iters++) {
+        for (int i = 0; i < 7; i++) {
+            int v, dup;
+            do {
+                v = fm_rng_uniform(rng, 0, count);
+                dup = 0;
+                for (int j = 0; j < i; j++) dup |= idx[j] == v;
+            } while (dup);
+            idx[i] = v;
+            s1[2 * i] = m1[2 * v]; s1[2 * i + 1] = m1[2 * v + 1];
+            s2[2 * i] = m2[2 * v]; s2[2 * i + 1] = m2[2 * v + 1];
+        }
+        if (!fm_collinear(s1, 7) && !fm_collinear(s2, 7)) return 1;
+    }
+    return 0;
+}
+
+static void fm_errors(const float* m1, const float* m2, int n, const double* F, float* err) {   /* FMEstimatorCallback::computeError */
+    for (int i = 0; i < n; i++) {
+        const double x1 = m1[2 * i], y1 = m1[2 * i + 1], x2 = m2[2 * i], y2 = m2[2 * i + 1];
+        double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+        const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+        a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+        const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+        const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+        err[i] = (float)(e1 > e2 ? e1 : e2);
+    }
+}
+
+static int fm_update_iters(double p, double ep, int model_points, int max_iters) {              /* RANSACUpdateNumIters */
+    p = p > 0. ? p : 0.; p = p < 1. ? p : 1.;
+    ep = ep > 0. ? ep : 0.; ep = ep < 1. ? ep : 1.;
+    double num = 1. - p > DBL_MIN ? 1. - p : DBL_MIN;
+    double denom = 1. - pow(1. - ep, model_points);
+    if (denom < DBL_MIN) return 0;
+    num = log(num); denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)lrint(num / denom);
+}
+
+static int fm_float_cmp(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* returns 0: no model (n < 7 or nothing found), else 1; F9 = the winning model (n == 7: the first root), mask[n] = inliers */
+int spec_find_fundamental_mat(const float* m1, const float* m2, int n, double thresh, double conf, double* F9, uint8_t* mask) {
+    const int max_iters = 1000;
+    double F[27];
+    if (n < 7) return 0;
+    if (n == 7) {
+        const int k = fm_run7(m1, m2, F);
+        memset(mask, 1, (size_t)n);               /* mask.setTo(1) whatever the solver returns */
+        if (k <= 0) return 0;
+        memcpy(F9, F, sizeof(double) * 9);
+        return 1;
+    }
+    if (thresh <= 0) thresh = 3;
+    if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
+    float* err = (float*)malloc(sizeof(float) * (size_t)n * 2);
+    float* srt = err + n;
+    float s1[14], s2[14];
+    fm_rng rng = {(uint64_t)-1};
+    int found = 0;
+    if (n >= 15) {
+        int niters = max_iters, max_good = 0;
+        const float t = (float)(thresh * thresh);
+        for (int iter = 0; iter < niters; iter++) {
+            if (!fm_get_subset(m1, m2, n, &rng, 10000, s1, s2)) break;
+            const int k = fm_run7(s1, s2, F);
+            for (int i = 0; i < k; i++) {
+                fm_errors(m1, m2, n, F + 9 * i, err);
+                int good = 0;
+                for (int j = 0; j < n; j++) good += err[j] <= t;
+                if (good > (max_good > 6 ? max_good : 6)) {
+                    for (int j = 0; j < n; j++) mask[j] = err[j] <= t;
+                    memcpy(F9, F + 9 * i, sizeof(double) * 9);
+                    max_good = good;
+                    found = 1;
+                    niters = fm_update_iters(conf, (double)(n - good) / n, 7, niters);
+                }
+            }
+        }
+    } else {
+        int niters = fm_update_iters(conf, 0.45, 7, max_iters);
+        if (niters < 3) niters = 3;
+        double min_median = DBL_MAX;
+        for (int iter = 0; iter < niters; iter++) {
+            if (!fm_get_subset(m1, m2, n, &rng, 1000, s1, s2)) break;
+            const int k = fm_run7(s1, s2, F);
+            for (int i = 0; i < k; i++) {
+                fm_errors(m1, m2, n, F + 9 * i, err);
+                memcpy(srt, err, sizeof(float) * (size_t)n);
+                qsort(srt, (size_t)n, sizeof(float), fm_float_cmp);
+                const double median = srt[n / 2];
+                if (median < min_median) { min_median = median; memcpy(F9, F + 9 * i, sizeof(double) * 9); found = 1; }
+            }
+        }
+        if (found) {
+            double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(min_median);
+            if (sigma < 0.001) sigma = 0.001;
+            const float t = (float)(sigma * sigma);
+            fm_errors(m1, m2, n, F9, err);
+            for (int j = 0; j < n; j++) mask[j] = err[j] <= t;
+        }
+    }
+    free(err);
+    return found;
+}
+
+/* InstsFeatManager::RejectWithF (dynamic_tracker.cpp:831-849): both point lists lifted with cam0 (liftProjective, z = 1),
+ * re-projected with the virtual focal length kFocalLength = 460 (utils/parameters.h:42) about (col/2, row/2), narrowed to
+ * float, then findFundamentalMat(un_cur, un_prev, FM_RANSAC, F_threshold, 0.99, status).  Returns the size of `status`
+ * (n, or 0 when findFundamentalMat leaves it empty). */
+int spec_reject_with_f(const double* cam, const float* cur_pts, const float* prev_pts, int n, int col, int row, double f_threshold,
+                       uint8_t* status, float* un_out /* nullable: 4 n floats, un_cur then un_prev */) {
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3], k1 = cam[4], k2 = cam[5], p1 = cam[6], p2 = cam[7];
+    const double iK11 = 1.0 / fx, iK13 = -cx / fx, iK22 = 1.0 / fy, iK23 = -cy / fy;
+    const int nod = (k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0);
+    float* un = (float*)malloc(sizeof(float) * 4 * (size_t)(n > 0 ? n : 1));
+    for (int s = 0; s < 2; s++) {
+        const float* pts = s ? prev_pts : cur_pts;
+        for (int i = 0; i < n; i++) {
+            const double u = (double)pts[2 * i], v = (double)pts[2 * i + 1];
+            const double mxd = iK11 * u + iK13, myd = iK22 * v + iK23;
+            double mxu = mxd, myu = myd;
+            if (!nod) {
+                for (int it = 0; it < 8; it++) {
+                    const double x = mxu, y = myu;
+                    const double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2;
+                    const double rad = k1 * rho2 + k2 * rho2 * rho2;
+                    const double dux = x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2);
+                    const double duy = y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2);
+                    mxu = mxd - dux; myu = myd - duy;
+                }
+            }
+            un[(size_t)s * 2 * n + 2 * i] = (float)(460.0 * mxu / 1.0 + col / 2.0);
+            un[(size_t)s * 2 * n + 2 * i + 1] = (float)(460.0 * myu / 1.0 + row / 2.0);
+        }
+    }
+    if (un_out) memcpy(un_out, un, sizeof(float) * 4 * (size_t)n);
+    double F9[9];
+    const int ok = spec_find_fundamental_mat(un, un + 2 * (size_t)n, n, f_threshold, 0.99, F9, status);
+    free(un);
+    if (n < 7) return 0;
+    if (!ok && n > 7) memset(status, 0, (size_t)n);   /* OpenCV creates the mask and leaves it unwritten when no model is found: 0 here */
+    return n;
+}
+
+/* InstFeat::DetectExtraPoints (front_end/instance_feature.cpp:413-461): the instance mask is sampled on a `step` grid,
+ * step = max(sqrt(0.8*rows*cols/1000), 2) truncated to int; a sample with mask > 0.5 and a finite positive disparity gives
+ * depth = fx*baseline/disparity (float), kept when 0.1 < depth <= 100, x = (c-cx)*depth/fx, y = (r-cy)*depth/fy in float
+ * arithmetic with the float camera constants of CameraInfo.  Returns the number of points (row-major sample order). */
+int spec_detect_extra_points(const uint8_t* mask, int rows, int cols, int mask_pitch, const float* disp, int disp_pitch_elems,
+                             int box_x, int box_y, float fx, float fy, float cx, float cy, float baseline, double* out /* 3 per point */) {
+    double s = sqrt(0.8 * rows * cols / 1000.);
+    const int step = (int)(s > 2. ? s : 2.);
+    int n = 0;
+    for (int i = 0; i < rows; i += step)
+        for (int j = 0; j < cols; j += step) {
+            if (mask[(size_t)i * mask_pitch + j] <= 0.5) continue;
+            const int r = i + box_y, c = j + box_x;
+            const float disparity = disp[(size_t)r * disp_pitch_elems + c];
+            if (disparity <= 0) continue;
+            if (disparity != disparity) continue;
+            const float depth = fx * baseline / disparity;
+            if (depth <= 0.1 || depth > 100) continue;
+            const float x3 = (c - cx) * depth / fx, y3 = (r - cy) * depth / fy;
+            out[3 * n] = x3; out[3 * n + 1] = y3; out[3 * n + 2] = depth;
+            n++;
+        }
+    return n;
+}

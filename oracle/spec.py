@@ -154,3 +154,43 @@ def bgr_to_gray(bgr):
     out = np.zeros((h, w), np.uint8)
     lib().spec_bgr_to_gray(_p(bgr, C.c_uint8), w, h, 3 * w, _p(out, C.c_uint8), w)
     return out
+
+
+def find_fundamental_mat(pts1, pts2, thresh=1.0, conf=0.99):
+    """cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, conf, mask): (F 3x3 | None, mask u8[n] | None)."""
+    a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    n = len(a)
+    F = np.zeros(9, np.float64)
+    mask = np.zeros(max(n, 1), np.uint8)
+    lib().spec_find_fundamental_mat.restype = C.c_int
+    ok = lib().spec_find_fundamental_mat(_p(a, C.c_float), _p(b, C.c_float), n, C.c_double(thresh), C.c_double(conf),
+                                         _p(F, C.c_double), _p(mask, C.c_uint8))
+    return (F.reshape(3, 3), mask[:n].copy()) if ok else (None, None)
+
+
+def reject_with_f(cam, cur_pts, prev_pts, col, row, f_threshold=1.0, return_un=False):
+    """InstsFeatManager::RejectWithF: status u8[n] (empty when n < 7)."""
+    c = np.array([cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")], np.float64)
+    a = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    n = len(a)
+    st = np.zeros(max(n, 1), np.uint8)
+    un = np.zeros((2, max(n, 1), 2), np.float32)
+    lib().spec_reject_with_f.restype = C.c_int
+    k = lib().spec_reject_with_f(_p(c, C.c_double), _p(a, C.c_float), _p(b, C.c_float), n, int(col), int(row), C.c_double(f_threshold),
+                                 _p(st, C.c_uint8), _p(un, C.c_float))
+    return (st[:k].copy(), un[:, :n].copy()) if return_un else st[:k].copy()
+
+
+def detect_extra_points(mask, disp, box_xy, fx, fy, cx, cy, baseline):
+    """InstFeat::DetectExtraPoints: (n, 3) float64 points (x, y, depth) of one instance ROI."""
+    mask = _u8(mask)
+    rows, cols = mask.shape
+    d = np.ascontiguousarray(disp, np.float32)
+    out = np.zeros((rows * cols + 1, 3), np.float64)
+    lib().spec_detect_extra_points.restype = C.c_int
+    n = lib().spec_detect_extra_points(_p(mask, C.c_uint8), rows, cols, cols, _p(d, C.c_float), d.shape[1], int(box_xy[0]), int(box_xy[1]),
+                                       C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(baseline),
+                                       _p(out, C.c_double))
+    return out[:n].copy()
