@@ -270,7 +270,7 @@ def kernel_sources_sha() -> str:
 def run_dvfe(args):
     import torch
     import torch.distributed as dist
-    from dynamic_vins_b200 import BatchTracker, lib, make_config, synth
+    from dynamic_vins_b200 import BatchTracker, lib, make_config, shard, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,8 +297,9 @@ def run_dvfe(args):
     S, T, W, H = args.streams, args.frames, c["width"], c["height"]
     # ---- synthetic frames: S independent streams (distinct seeds per stream and rank), T unique frames each
     frames = torch.empty((T, 2, S, H, W), dtype=torch.uint8, device=dev)
-    for s in range(S):
-        st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + rank * S + s, stereo=stereo)
+    # the streams this rank owns (dynamic_vins_b200/shard.py: weak scaling, no data-path collective)
+    for s, gid in enumerate(shard.stream_ids_for_rank(S, rank)):
+        st = synth.SynthStream(W, H, seed=1000 * c["config_id"] + gid, stereo=stereo)
         frames[:, :, s] = gpu_frames(st, T, dev, args.motion_scale)
     torch.cuda.synchronize()
     order = synth.pingpong_positions(T, args.warmup + args.steps)
@@ -408,10 +409,7 @@ def run_dvfe(args):
         n_obs_e2e = sum(len(trk.features(s)) for s in range(S))
     trk.close()
 
-    t = torch.tensor([ms_value, ms_e2e, ms_probe], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_value, ms_e2e, ms_probe = float(t[0]), float(t[1]), float(t[2])
+    ms_value, ms_e2e, ms_probe = shard.reduce_max([ms_value, ms_e2e, ms_probe], dist if world > 1 else None, dev)
     total_frames = world * S * args.steps
     value = total_frames / (ms_value * 1e-3)
     e2e = total_frames / (ms_e2e * 1e-3)

@@ -215,3 +215,29 @@ def test_label_image_path_equals_mask_path_and_oracle():
             for row in r:
                 assert np.abs(row["uv"] - v["features"][int(row["id"])]["uv"]).max() <= POS_TOL
     ref.close(); lab_h.close(); lab_d.close()
+
+
+def test_cpp_feature_track_frame_and_queue(tmp_path):
+    """include/dvfe/frontend_io.hpp: FeatureTrackFrame (one iteration of FeatureTrack(), system/main.cpp:178-330) as the producer,
+    a consumer thread taking the FrontendFeature frames from the FeatureQueue and writing them with SerializePointFeature: the
+    files must be identical to those of the hand-written call sequence of test_feature_tracker.cpp (compared with the oracle in
+    test_cpp_dynamic_mode_reference_shaped_api)."""
+    name, n_frames = "c3_zed_dynamic", 5
+    cfg = write_config(tmp_path, name)
+    exe_a = build_driver(tmp_path)
+    exe_b = str(tmp_path / "test_frontend_io")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
+                           os.path.join(ROOT, "tests", "cpp", "test_frontend_io.cpp"),
+                           "-L" + os.path.join(ROOT, "dynamic_vins_b200"), "-ldvfe", "-lpthread",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe_b])
+    st = synth.make_stream(name, 43)
+    with open(tmp_path / "frames.bin", "wb") as f:
+        for k in range(n_frames):
+            write_dyn_frame(f, st.frame(k))
+    subprocess.check_call([exe_a, "dynamic", cfg, str(tmp_path / "frames.bin"), str(n_frames), str(tmp_path / "a"), "12"])
+    subprocess.check_call([exe_b, "dynamic", cfg, str(tmp_path / "frames.bin"), str(n_frames), str(tmp_path / "b"), "12"])
+    for k in range(n_frames):
+        for kind in ("point", "inst"):
+            a = open(tmp_path / f"a_{k}_{kind}.txt").read()
+            b = open(tmp_path / f"b_{k}_{kind}.txt").read()
+            assert a == b and (kind == "inst" or len(a) > 0), f"frame {k}: {kind} file"

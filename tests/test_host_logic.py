@@ -6,7 +6,7 @@ import socket
 import numpy as np
 import pytest
 
-from conftest import crc
+from conftest import ROOT, crc
 import dynamic_vins_b200 as dv
 from dynamic_vins_b200 import shard, synth
 from dynamic_vins_b200._lib import OBS_DTYPE
@@ -114,3 +114,18 @@ def test_point_feature_wire_format_round_trip():
             assert np.array_equal(a, b)          # repr() round-trips doubles exactly
     from oracle import cv_front_end as cvfe
     assert cvfe.serialize_point_features(pts) == txt
+
+
+def test_cpp_frontend_hand_off_header(tmp_path):
+    """include/dvfe/frontend_io.hpp compiled by g++ and run without a device: FeatureQueue semantics (basic/feature_queue.h:19-71),
+    the text round trip of the reference's point-feature format, and the estimator's map type instantiated with an Eigen
+    7-vector (the stand-in Eigen of oracle/shim; test code may use oracle/)."""
+    import subprocess
+    exe = str(tmp_path / "test_frontend_io")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
+                           os.path.join(ROOT, "tests", "cpp", "test_frontend_io.cpp"),
+                           "-L" + os.path.join(ROOT, "dynamic_vins_b200"), "-ldvfe", "-lpthread",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe])
+    out = subprocess.run([exe, "host", str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "frontend_io host checks ok" in out.stdout
