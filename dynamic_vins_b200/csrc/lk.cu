@@ -20,6 +20,8 @@
 //   * the Scharr derivatives are computed on the fly from a 24x24 u8 window staged in shared memory (the
 //     reference materialises a 4 B/px derivative image per level and per call);
 //   * the 2x2 sums are reduced exactly with redux.sync on 16-bit halves.
+#include <limits.h>
+
 #include "kernels.cuh"
 
 #ifndef LK_WARPS
@@ -27,6 +29,9 @@
 #endif
 #ifndef LK_MIN_BLOCKS
 #define LK_MIN_BLOCKS 6          // resident blocks per SM the register allocation targets
+#endif
+#ifndef LK_JCACHE
+#define LK_JCACHE 1            // keep the J row registers while the window origin stays on the same integer pixel
 #endif
 #define LK_RUN 7                  // pixels per run; 3 runs per window row
 #define W_BITS 14
@@ -367,6 +372,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
             // linear offset is the alignment of its column)
             const int off0 = ry0 * L.pitch + rx0, off1 = ry1 * L.pitch + rx1;
             float pdx = 0.f, pdy = 0.f;
+#if LK_JCACHE
+            // The bytes of J an iteration reads depend only on the integer part of the window origin.  Once the Gauss-Newton
+            // steps fall below a pixel, consecutive iterations mostly stay on the same integer origin and differ in the
+            // bilinear weights only: the 8 row registers are kept, the gather (12 loads + address arithmetic + funnel shifts)
+            // and its latency are skipped.  Same bytes, same arithmetic: bit-identical.
+            int c_inx = INT_MIN, c_iny = INT_MIN;
+            unsigned A0_lo = 0, A0_hi = 0, B0_lo = 0, B0_hi = 0, A1_lo = 0, A1_hi = 0, B1_lo = 0, B1_hi = 0;
+#endif
 #pragma unroll 1
             for (int it = 0; it < 30; it++) {
                 const int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
@@ -379,9 +392,21 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 lk_weights(a, b, iw00, iw01, iw10, iw11);
                 const int W01 = (iw00 & 0xffff) | (iw01 << 16);
                 const int W23 = (iw10 & 0xffff) | (iw11 << 16);
-                const int o = iny * L.pitch + inx;
                 // sum (J - I) * Ix = sum J * Ix - sum I * Ix
                 int sb1 = -c1, sb2 = -c2;
+#if LK_JCACHE
+                if (inx != c_inx || iny != c_iny) {
+                    const int o = iny * L.pitch + inx;
+                    load8o(Jpx, o + off0, A0_lo, A0_hi);
+                    load8o(Jpx, o + off0 + L.pitch, B0_lo, B0_hi);
+                    load8o(Jpx, o + off1, A1_lo, A1_hi);
+                    load8o(Jpx, o + off1 + L.pitch, B1_lo, B1_hi);
+                    c_inx = inx; c_iny = iny;
+                }
+                LK_RUN_MAC(A0_lo, A0_hi, B0_lo, B0_hi, Ix0, Iy0);
+                LK_RUN_MAC(A1_lo, A1_hi, B1_lo, B1_hi, Ix1, Iy1);
+#else
+                const int o = iny * L.pitch + inx;
                 {
                     unsigned A_lo, A_hi, B_lo, B_hi;
                     load8o(Jpx, o + off0, A_lo, A_hi);
@@ -394,6 +419,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                     load8o(Jpx, o + off1 + L.pitch, B_lo, B_hi);
                     LK_RUN_MAC(A_lo, A_hi, B_lo, B_hi, Ix1, Iy1);
                 }
+#endif
                 const bool small = !__any_sync(0xffffffffu, (lk_big(sb1) | lk_big(sb2)) != 0u);
                 const float b1 = warp_sum_f(sb1, small, FLT_SCALE);
                 const float b2 = warp_sum_f(sb2, small, FLT_SCALE);
