@@ -594,11 +594,37 @@ def _oracle_frontend(stream_id: int, workload: str = None):
     return st, fe
 
 
+def _cpu_reference(stream_id: int, workload: str = None):
+    """The CPU front-end the reference arm and `cpu_baseline` time: (stream, step(frame, time0), kind).
+    kind "reference": oracle/_ref/libdvref.so, i.e. the reference's own FeatureTracker / InstsFeatManager sources compiled
+    unmodified (oracle/ref/Makefile), their OpenCV calls served by cv2; one front end per process (the reference's id counter
+    is a static).  kind "port": the cv2-backed restatement oracle/cv_front_end.py, when that library was not built."""
+    from oracle import ref_lib
+    st, fe = _oracle_frontend(stream_id, workload)
+    if ref_lib.available() and not os.environ.get("DVFE_BENCH_FORCE_PORT"):
+        from dynamic_vins_b200 import synth
+        c = synth.CONFIGS[workload or WORKLOAD]
+        ref = ref_lib.RefFrontEnd(fe.P, c["cam0"], c["cam1"], fe.mode, c["width"], c["height"])
+
+        def step(fr, t):
+            fr.time0 = t
+            ref.step(fr)
+        return st, step, "reference"
+    if fe.mode == "dynamic":
+        def step(fr, t):
+            fr.time0 = t
+            fe.step(fr)
+    else:
+        def step(fr, t):
+            fe.tracker.track_image(fr.gray0, fr.gray1, t)
+    return st, step, "port"
+
+
 def cpu_baseline(budget_s: float) -> dict:
     """The oracle (cv2 restatement of the reference's CPU FeatureTracker::TrackImage) timed on this box's host
     cores on a bounded sample of the same workload: one stream, as many frames as fit the budget."""
     import cv2
-    st, fe = _oracle_frontend(0)
+    st, step, kind = _cpu_reference(0)
     T = 6
     ms = float(os.environ.get("DVFE_BENCH_MOTION", "1"))
     frames = [st.frame(k, pos=k * ms) for k in range(T)]
@@ -606,16 +632,16 @@ def cpu_baseline(budget_s: float) -> dict:
     order = pingpong_positions(T, 100000)
     # warm-up
     for i in range(3):
-        fr = frames[order[i]]
-        fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
+        step(frames[order[i]], 0.05 * (i + 1))
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s and n < 2000:
-        fr = frames[order[3 + n]]
-        fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (4 + n))
+        step(frames[order[3 + n]], 0.05 * (4 + n))
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "port",
-            "sample": f"1 stream x {n} frames of {WORKLOAD}, cv2 {cv2.__version__} "
+    what = ("the reference's FeatureTracker sources compiled as oracle/_ref" if kind == "reference"
+            else "the cv2 restatement oracle/cv_front_end.py")
+    return {"value": n / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": kind,
+            "sample": f"1 stream x {n} frames of {WORKLOAD}, {what}, cv2 {cv2.__version__} "
                       f"with {cv2.getNumThreads()} threads, single process"}
 
 
@@ -671,24 +697,19 @@ def _ref_worker(wid: int, T: int, conn, workload: str):
     import cv2
     cv2.setNumThreads(1)
     apply_overrides()
-    st, fe = _oracle_frontend(wid, workload)
+    st, step, kind = _cpu_reference(wid, workload)
     ms = float(os.environ.get("DVFE_BENCH_MOTION", "1"))
     frames = [st.frame(k, pos=k * ms) for k in range(T)]
     from dynamic_vins_b200.synth import pingpong_positions
     i = 0
-    conn.send("ready")
+    conn.send(kind)
     while True:
         msg = conn.recv()
         if msg == "stop":
             break
         order = pingpong_positions(T, i + msg + 1)
         for _ in range(msg):
-            fr = frames[order[i]]
-            if fe.mode == "dynamic":
-                fr.time0 = 0.05 * (i + 1)
-                fe.step(fr)
-            else:
-                fe.tracker.track_image(fr.gray0, fr.gray1, 0.05 * (i + 1))
+            step(frames[order[i]], 0.05 * (i + 1))
             i += 1
         conn.send(i)
 
@@ -710,8 +731,8 @@ def run_reference(args):
         p = ctx.Process(target=_ref_worker, args=(w, args.frames, b, WORKLOAD), daemon=True)
         p.start()
         pipes.append(a); procs.append(p)
-    for a in pipes:
-        a.recv()
+    kinds = {a.recv() for a in pipes}
+    kind = "reference" if kinds == {"reference"} else "port"
 
     def step(n):
         for a in pipes:
@@ -734,9 +755,11 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": shared_config(args),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "port",
-                            "sample": f"{n_workers} processes x {args.steps} frames, one {WORKLOAD} stream each "
-                                      f"(cv2 {cv2.__version__}, 1 thread per process)"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": kind,
+                            "sample": f"{n_workers} processes x {args.steps} frames, one {WORKLOAD} stream each; "
+                                      + ("the reference's front-end sources compiled as oracle/_ref/libdvref.so, OpenCV calls served by "
+                                         if kind == "reference" else "the restatement oracle/cv_front_end.py over ")
+                                      + f"cv2 {cv2.__version__}, 1 thread per process"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
