@@ -466,13 +466,13 @@ def run_dvfe(args):
                          "algorithmic_bytes_per_launch": ab, "launch_ms": stage_ms[dom],
                          "measured_on": "same steps, one stream group (launch = all streams), kernels serialised",
                          "ncu_sm_throughput_pct": sm_l1.get("sm_pct"), "ncu_l1tex_throughput_pct": sm_l1.get("l1tex_pct"),
-                         # warp instructions per launch (ncu, static) / live launch time, against 4 issue slots x 148 SMs x SM clock
-                         "issue_slot_frac": (sm_l1["warp_inst"] / (stage_ms[dom] * 1e-3) / (4 * 148 * (clock_info.get("sm_mhz") or 1965.0) * 1e6)
-                                             if sm_l1.get("warp_inst") and stage_ms[dom] > 0 else None),
+                         # fraction of the SM issue slots the kernel used in the committed ncu capture (sm__issue_active)
+                         "ncu_issue_active_pct": sm_l1.get("issue_active_pct"),
+                         "ncu_warp_instructions": sm_l1.get("warp_inst"),
                          "ncu_capture": ncu_note,
-                         "note": "issue-bound integer kernel: one warp per point, ~70 % of the issue slots busy (profiles/"
-                                 "ncu_r2_summary.md); traffic above the algorithmic bytes is the template cache the stereo call "
-                                 "writes for the next temporal call"},
+                         "note": "issue/latency-bound integer kernel, one warp per point (profiles/ncu_r2_summary.md): the HBM fraction "
+                                 "is small by construction; traffic above the algorithmic bytes is the template cache the stereo call "
+                                 "writes for the next temporal call (HBM bytes traded for issue slots, which bind)"},
         }
         out["run_info"]["host_placement"] = numa_note
         if world == 1 and not args.no_cpu_baseline:

@@ -25,7 +25,9 @@ def main():
     hdr = rows[0]
     col = {k: hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
                                       "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-                                      "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__time_duration.sum")}
+                                      "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__time_duration.sum",
+                                      "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+                                      "sm__warps_active.avg.pct_of_peak_sustained_active")}
     units = rows[1]
 
     def num(r, k):
@@ -33,27 +35,40 @@ def main():
         u = units[col[k]]
         return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
 
-    stages, sm_l1, n_lk = {}, {}, 0
-    for r in rows[2:]:
-        name = r[col["Kernel Name"]].split("(")[0]
-        if name == "k_lk_track":
-            stage = "lk_temporal" if n_lk == 0 else "lk_stereo"
-            n_lk += 1
-            if n_lk > 2:
-                break
-        elif name.startswith("k_pyr"):
-            stage = "pyramid"
-        elif name.startswith("k_gftt_response"):
-            stage = "gftt_response"
-        elif name.startswith("k_gftt_select"):
-            stage = "gftt_select"
-        else:
-            continue
-        stages[stage] = stages.get(stage, 0.0) + num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
-        if stage != "pyramid":
-            sm_l1[stage] = {"sm_pct": num(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
-                            "l1tex_pct": num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
-                            "warp_inst": num(r, "smsp__inst_executed.sum")}
+    # one entry per captured launch, in capture order
+    L = [(r[col["Kernel Name"]].split("(")[0], r) for r in rows[2:] if len(r) > col["gpu__time_duration.sum"]]
+    names = [n for n, _ in L]
+
+    def bytes_of(i):
+        return num(L[i][1], "dram__bytes_read.sum") + num(L[i][1], "dram__bytes_write.sum")
+
+    def info(i):
+        r = L[i][1]
+        return {"sm_pct": num(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "l1tex_pct": num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "warp_inst": num(r, "smsp__inst_executed.sum"), "time_us": num(r, "gpu__time_duration.sum"),
+                "issue_active_pct": num(r, "sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+                "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active")}
+
+    # the steady-state frame step: the temporal LK call is the k_lk_track followed by k_gftt_response (k_compact_tracked is not
+    # captured), the stereo call the one right after the right camera's k_pyr_down launches; take the last complete step
+    stages, sm_l1 = {}, {}
+    t_idx = [i for i in range(len(L) - 2) if names[i] == "k_lk_track" and names[i + 1] == "k_gftt_response" and names[i + 2] == "k_gftt_select"]
+    if not t_idx:
+        raise SystemExit("no steady-state step (k_lk_track, k_gftt_response, k_gftt_select) in the capture")
+    t = sidx = None
+    for cand in reversed(t_idx):              # the last step the capture holds completely
+        nxt = [i for i in range(cand + 3, len(L)) if names[i] == "k_lk_track"]
+        if nxt and cand >= 3 and names[cand - 3:cand] == ["k_pyr_down"] * 3 and names[nxt[0] - 3:nxt[0]] == ["k_pyr_down"] * 3:
+            t, sidx = cand, nxt[0]
+            break
+    if t is None:
+        raise SystemExit("the capture does not hold one whole steady-state step")
+    stages["lk_temporal"], sm_l1["lk_temporal"] = bytes_of(t), info(t)
+    stages["gftt_response"], sm_l1["gftt_response"] = bytes_of(t + 1), info(t + 1)
+    stages["gftt_select"], sm_l1["gftt_select"] = bytes_of(t + 2), info(t + 2)
+    stages["lk_stereo"], sm_l1["lk_stereo"] = bytes_of(sidx), info(sidx)
+    stages["pyramid"] = sum(bytes_of(i) for i in list(range(t - 3, t)) + list(range(sidx - 3, sidx)))
     stages["_sm_l1"] = sm_l1
     stages["_kernel_sources_sha"] = kernel_sources_sha()
     stages["_source"] = ("%s (ncu --set full --clock-control none, one step of bench.py --groups 1, 64 streams): "
