@@ -417,6 +417,34 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
     return DVFE_OK;
 }
 
+// Capture and instantiate the graph of the step with buffer phase `ph` and mode `flags` (bit 0 semantic, 2 stereo, 3 not the first
+// frame, 4 forward templates cached); `k` = any frame index with k % 6 == ph and (k > 0) as in the flags.  Nothing runs.
+int dvfe_tracker::capture_step(int ph, unsigned flags, long k) {
+    const unsigned long long before = g_dvfe_launches;
+    const bool keep_valid = tcache_valid;
+    tcache_valid = (flags & 16u) != 0;
+    cudaGraph_t g = nullptr;
+    DVFE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc = enqueue_compute(nullptr, nullptr, 0, 0, (flags & 1u) != 0, true, (flags & 4u) != 0, k, false);
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    tcache_valid = keep_valid;
+    const unsigned n_kernels = (unsigned)(g_dvfe_launches - before);
+    g_dvfe_launches = before;                              // nothing ran yet
+    if (rc != DVFE_OK || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        if (rc != DVFE_OK) return rc;
+        dvfe_set_error("stream capture of the frame step failed: %s", cudaGetErrorString(ce));
+        return DVFE_ERR_CUDA;
+    }
+    StepGraph sg;
+    sg.n_kernels = n_kernels;
+    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { dvfe_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return DVFE_ERR_CUDA; }
+    step_graphs.emplace(StepKey(ph, flags), sg);
+    return DVFE_OK;
+}
+
 int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch,
                          const double* time0, bool semantic, bool level0_in_place, bool has_right) {
     const long k = frames;
@@ -448,29 +476,17 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
         }
         const unsigned flags = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | (k > 0 ? 8u : 0u) | (tcache_valid ? 16u : 0u);
         const StepKey key(ph, flags);
-        auto it = step_graphs.find(key);
-        if (it == step_graphs.end()) {
-            if (step_graphs.size() >= 64) drop_graphs();          // a caller cycling through many input buffers
-            const unsigned long long before = g_dvfe_launches;
-            cudaGraph_t g = nullptr;
-            DVFE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            const int rc = enqueue_compute(nullptr, nullptr, 0, 0, semantic, true, stereo_now, k, false);
-            const cudaError_t ce = cudaStreamEndCapture(st, &g);
-            const unsigned n_kernels = (unsigned)(g_dvfe_launches - before);
-            g_dvfe_launches = before;                              // nothing ran yet
-            if (rc != DVFE_OK || ce != cudaSuccess) {
-                if (g) cudaGraphDestroy(g);
-                if (rc != DVFE_OK) return rc;
-                dvfe_set_error("stream capture of the frame step failed: %s", cudaGetErrorString(ce));
-                return DVFE_ERR_CUDA;
-            }
-            StepGraph sg;
-            sg.n_kernels = n_kernels;
-            const cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
-            cudaGraphDestroy(g);
-            if (ie != cudaSuccess) { dvfe_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return DVFE_ERR_CUDA; }
-            it = step_graphs.emplace(key, sg).first;
+        if (step_graphs.find(key) == step_graphs.end()) {
+            if (step_graphs.size() >= 64) drop_graphs();          // a caller cycling through many modes
+            DVFE_CHECK(capture_step(ph, flags, k));
+            // The first step of a mode also captures the six steady-state graphs it will replay from the next frame on (one per
+            // buffer phase), so that instantiation (host time, ~0.3 ms each) never falls into a later, possibly timed, step.
+            const bool tc_next = stereo_now && d_tcache != nullptr;
+            const unsigned steady = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | 8u | (tc_next ? 16u : 0u);
+            for (int p = 0; p < 6; p++)
+                if (step_graphs.find(StepKey(p, steady)) == step_graphs.end()) DVFE_CHECK(capture_step(p, steady, 6 + p));
         }
+        auto it = step_graphs.find(key);
         DVFE_CUDA(cudaGraphLaunch(it->second.exec, st));
         g_dvfe_launches += it->second.n_kernels;
     } else {

@@ -86,6 +86,7 @@ struct dvfe_tracker {
     bool use_graphs = true;
     bool use_reuse = true;                           // DVFE_REUSE=0: the stereo call rebuilds every forward template (A/B, debugging)
     void drop_graphs();
+    int capture_step(int ph, unsigned flags, long k);
     int enqueue_compute(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, bool semantic,
                         bool level0_in_place, bool stereo_now, long k, bool with_marks);
 
