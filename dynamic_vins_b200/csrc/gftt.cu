@@ -721,11 +721,14 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
             __syncthreads();
             // Decisions are final once written, so no barrier is needed between rounds: every thread keeps sweeping
             // its own undecided candidates until none is left (the strongest undecided candidate of the block can
-            // always be decided by its owner, so the sweep terminates).
+            // always be decided by its owner, so the sweep terminates).  The flags are single bytes that only ever go
+            // 0 -> 1 or 0 -> 2 and are read through a volatile pointer (a stale 0 means "look again next round"): the
+            // read/write overlap compute-sanitizer's racecheck reports here is this protocol (profiles/sanitizer_r2.txt).
+            volatile uint8_t* vstate = state;
             for (;;) {
                 int undecided = 0;
                 for (int i = tid; i < M; i += NMS_THREADS) {
-                    if (state[i] != 0) continue;
+                    if (vstate[i] != 0) continue;
                     const unsigned long long key = srt[i];
                     const unsigned idx = (unsigned)key;
                     const int y = idx / w, x = idx - y * w;
@@ -744,14 +747,14 @@ __global__ void __launch_bounds__(NMS_THREADS) k_gftt_select(const GfttJob* __re
                                 const int yj = ij / w, xj = ij - yj * w;
                                 const int dx = x - xj, dy = y - yj;
                                 if ((double)(dx * dx + dy * dy) < md2) {
-                                    const uint8_t sj = state[j];
+                                    const uint8_t sj = vstate[j];
                                     if (sj == 1) { rejected = true; break; }
                                     if (sj == 0) blocked = true;
                                 }
                             }
                         }
-                    if (rejected) state[i] = 2;
-                    else if (!blocked) state[i] = 1;
+                    if (rejected) vstate[i] = 2;
+                    else if (!blocked) vstate[i] = 1;
                     else undecided = 1;
                 }
                 if (!__any_sync(0xffffffffu, undecided)) break;      // warp-level: lanes of a warp sweep together

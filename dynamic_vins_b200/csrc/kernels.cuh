@@ -57,6 +57,7 @@ int launch_ingest(const IngestArgs& a, cudaStream_t st);
 int launch_build_pyramids_jobs(const PyrJob* d_jobs, int n_jobs, int max_w, int max_h, int max_levels, cudaStream_t st);
 int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cudaStream_t st);
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st);
+int launch_pyr_extract_bordered(const uint8_t* pyr, const PyrLevel& L, int border, uint8_t* out, cudaStream_t st);
 
 // lk.cu
 int launch_lk(const LkGroup* d_groups, int n_groups, int max_pts, int max_level, int flow_back, cudaStream_t st,

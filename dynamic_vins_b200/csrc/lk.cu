@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 if (level > 0) {
                     const PyrLevel Ln = G.desc.lv[level - 1];
                     float fx, fy; int wx, wy;
+                    __syncwarp();                // every lane has finished reading the buffer the copy below overwrites
                     if (level - 1 > cached_below && lk_window_origin(src, level - 1, Ln.w, Ln.h, fx, fy, wx, wy))
                         lk_stage_window_async(s_win[warp][(lmax - level + 1) & 1], pyrI + Ln.offset + (size_t)DVFE_PADY * Ln.pitch + DVFE_PADX,
                                               Ln.pitch, wx, wy, lane);

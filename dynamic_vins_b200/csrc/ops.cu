@@ -73,6 +73,32 @@ extern "C" int dvfe_op_build_pyramid(const uint8_t* img, int w, int h, int pitch
     return DVFE_OK;
 }
 
+extern "C" int dvfe_op_build_pyramid_bordered(const uint8_t* img, int w, int h, int pitch, int max_level, int level, int border,
+                                              uint8_t* out) {
+    if (!img || !out || w < 1 || h < 1 || pitch < w || max_level < 0 || max_level >= DVFE_MAX_PYR_LEVELS || level < 0 || border < 0 ||
+        border > DVFE_WIN) {
+        dvfe_set_error("op_build_pyramid_bordered: bad argument (border <= 21 = winSize)");
+        return DVFE_ERR_INVALID;
+    }
+    DVFE_CHECK(ensure_device());
+    const PyrDesc desc = make_pyr_desc(w, h, max_level);
+    if (level >= desc.n_levels) { dvfe_set_error("op_build_pyramid_bordered: level %d of %d", level, desc.n_levels); return DVFE_ERR_INVALID; }
+    DevBuf d_img, d_pyr, d_out;
+    DVFE_CHECK(upload_image(d_img, img, w, h, pitch));
+    DVFE_CHECK(d_pyr.alloc(desc.bytes));
+    const PyrLevel& L = desc.lv[level];
+    const size_t nout = (size_t)(L.w + 2 * border) * (L.h + 2 * border);
+    DVFE_CHECK(d_out.alloc(nout));
+    PyrImgSet set{};
+    set.src[0] = d_img.as<uint8_t>(); set.dst[0] = d_pyr.as<uint8_t>();
+    set.per_set = 1;
+    DVFE_CHECK(launch_build_pyramids(set, 1, desc, w, 0));
+    DVFE_CHECK(launch_pyr_extract_bordered(d_pyr.as<uint8_t>(), L, border, d_out.as<uint8_t>(), 0));
+    DVFE_CUDA(cudaDeviceSynchronize());
+    DVFE_CUDA(cudaMemcpy(out, d_out.p, nout, cudaMemcpyDeviceToHost));
+    return DVFE_OK;
+}
+
 extern "C" int dvfe_op_lk(const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch, const float* pts1, int n,
                           int flow_back, int max_level, const uint8_t* mask, int mask_pitch, float* pts2_out,
                           uint8_t* status_out, float* rev_out) {

@@ -5,6 +5,8 @@
 // Every level is written once, with a REFLECT_101 border (common.cuh), and is then reused by the
 // temporal LK of this frame, the stereo LK of this frame and the temporal LK of the next frame
 // (the reference rebuilds both pyramids inside each of its 4 LK calls per stereo frame).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 __device__ __forceinline__ void pyr_select(const PyrImgSet& set, int img, const uint8_t*& src, uint8_t*& dst) {
@@ -74,10 +76,58 @@ __device__ __forceinline__ int pyr_tap5(const uint8_t* __restrict__ p) {
     return (int)p[-2] + 4 * (int)p[-1] + 6 * (int)p[0] + 4 * (int)p[1] + (int)p[2];
 }
 
+// ---- REFLECT_101 border written by the threads that produce the interior (levels >= 1 of the batched pyramids) ----
+// Border position x' = -d (1 <= d <= PADX) holds pixel d, x' = w-1+d (1 <= d <= padR, padR = pitch - PADX - w) holds pixel
+// w-1-d; rows likewise with PADY above and below.  When w > max(PADX, padR) and h > PADY every border position is the
+// single reflection of an interior pixel, so the thread that computes a pixel can store its mirror images itself and the
+// separate k_pyr_border launch of that level disappears (pyr_border_fusable).
+__host__ __device__ __forceinline__ bool pyr_border_fusable(const PyrLevel& L) {
+    const int padR = L.pitch - DVFE_PADX - L.w;
+    return L.h > DVFE_PADY && L.w > DVFE_PADX && L.w > padR;
+}
+
+// one pixel and its mirror images (ragged edges of the interior)
+__device__ __forceinline__ void pyr_store_px_mirrored(uint8_t* __restrict__ dst, const PyrLevel& D, int x, int y, uint8_t v) {
+    const int padR = D.pitch - DVFE_PADX - D.w;
+    int xs[3], ys[3], nx = 1, ny = 1;
+    xs[0] = x; ys[0] = y;
+    if (x >= 1 && x <= DVFE_PADX) xs[nx++] = -x;
+    if (x <= D.w - 2 && x >= D.w - 1 - padR) xs[nx++] = 2 * (D.w - 1) - x;
+    if (y >= 1 && y <= DVFE_PADY) ys[ny++] = -y;
+    if (y <= D.h - 2 && y >= D.h - 1 - DVFE_PADY) ys[ny++] = 2 * (D.h - 1) - y;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) dst[(ptrdiff_t)ys[j] * D.pitch + xs[i]] = v;
+}
+
+// 8 pixels x0..x0+7 of row yy (interior or an already mirrored row): aligned store + the column mirrors of edge threads
+__device__ __forceinline__ void pyr_store8_cols(uint8_t* __restrict__ dst, const PyrLevel& D, int x0, int yy, uint2 v, bool fuse) {
+    uint8_t* __restrict__ row = dst + (ptrdiff_t)yy * D.pitch;
+    *reinterpret_cast<uint2*>(row + x0) = v;
+    if (!fuse) return;
+    const int padR = D.pitch - DVFE_PADX - D.w;
+    if (x0 <= DVFE_PADX || x0 + 7 >= D.w - 1 - padR) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int x = x0 + i;
+            const uint8_t b = (uint8_t)((i < 4 ? v.x >> (8 * i) : v.y >> (8 * (i - 4))) & 0xffu);
+            if (x >= 1 && x <= DVFE_PADX) row[-x] = b;
+            if (x <= D.w - 2 && x >= D.w - 1 - padR) row[2 * (D.w - 1) - x] = b;
+        }
+    }
+}
+
+// ... of interior row y, plus its mirrored rows
+__device__ __forceinline__ void pyr_store8(uint8_t* __restrict__ dst, const PyrLevel& D, int x0, int y, uint2 v, bool fuse) {
+    pyr_store8_cols(dst, D, x0, y, v, fuse);
+    if (!fuse) return;
+    if (y >= 1 && y <= DVFE_PADY) pyr_store8_cols(dst, D, x0, -y, v, true);
+    if (y <= D.h - 2 && y >= D.h - 1 - DVFE_PADY) pyr_store8_cols(dst, D, x0, 2 * (D.h - 1) - y, v, true);
+}
+
 // one thread = 8 consecutive outputs of two consecutive rows.  It reads 7 source rows (one 16-byte and two
 // 4-byte aligned loads each) and evaluates the separable 5x5 kernel with dp4a: the horizontal taps (1 4 6 4)
-// times the vertical weight fit int8, the fifth tap is a second dp4a.
-__device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, const PyrLevel& D, int x0, int y0) {
+// times the vertical weight fit int8, the fifth tap is a second dp4a.  fuse_border: also store the level's border (above).
+__device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, const PyrLevel& D, int x0, int y0, bool fuse_border) {
     const uint8_t* __restrict__ src = base + S.offset + (size_t)DVFE_PADY * S.pitch + DVFE_PADX;   // pixel (0,0)
     uint8_t* __restrict__ dst = base + D.offset + (size_t)DVFE_PADY * D.pitch + DVFE_PADX;
     if (x0 >= D.w || y0 >= D.h) return;
@@ -119,8 +169,8 @@ __device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, 
         o0.y = (acc0[4] >> 8) | ((acc0[5] >> 8) << 8) | ((acc0[6] >> 8) << 16) | ((acc0[7] >> 8) << 24);
         o1.x = (acc1[0] >> 8) | ((acc1[1] >> 8) << 8) | ((acc1[2] >> 8) << 16) | ((acc1[3] >> 8) << 24);
         o1.y = (acc1[4] >> 8) | ((acc1[5] >> 8) << 8) | ((acc1[6] >> 8) << 16) | ((acc1[7] >> 8) << 24);
-        *reinterpret_cast<uint2*>(dst + (size_t)y0 * D.pitch + x0) = o0;
-        *reinterpret_cast<uint2*>(dst + (size_t)(y0 + 1) * D.pitch + x0) = o1;
+        pyr_store8(dst, D, x0, y0, o0, fuse_border);
+        pyr_store8(dst, D, x0, y0 + 1, o1, fuse_border);
         return;
     }
     // the ragged right / bottom edge of the interior (w % 8, odd h)
@@ -129,21 +179,24 @@ __device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, 
             const uint8_t* c = src + (size_t)(2 * (y0 + rr)) * S.pitch + 2 * (x0 + i);
             const int s = pyr_tap5(c - 2 * S.pitch) + 4 * pyr_tap5(c - S.pitch) + 6 * pyr_tap5(c) +
                           4 * pyr_tap5(c + S.pitch) + pyr_tap5(c + 2 * S.pitch);
-            dst[(size_t)(y0 + rr) * D.pitch + x0 + i] = (uint8_t)((s + 128) >> 8);
+            const uint8_t v = (uint8_t)((s + 128) >> 8);
+            if (fuse_border) pyr_store_px_mirrored(dst, D, x0 + i, y0 + rr, v);
+            else dst[(size_t)(y0 + rr) * D.pitch + x0 + i] = v;
         }
 }
 
-__global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D) {
+// fuse_border != 0: the level's REFLECT_101 border is stored here too (no k_pyr_border launch for it)
+__global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D, int fuse_border) {
     const uint8_t* unused; uint8_t* base;
     pyr_select(set, blockIdx.z, unused, base);
-    pyr_down_body(base, S, D, (blockIdx.x * blockDim.x + threadIdx.x) * 8, (blockIdx.y * blockDim.y + threadIdx.y) * 2);
+    pyr_down_body(base, S, D, (blockIdx.x * blockDim.x + threadIdx.x) * 8, (blockIdx.y * blockDim.y + threadIdx.y) * 2, fuse_border != 0);
 }
 
 __global__ void __launch_bounds__(256) k_pyr_down_jobs(const PyrJob* __restrict__ jobs, int level) {
     const PyrJob& J = jobs[blockIdx.z];
     if (level >= J.desc.n_levels) return;
     pyr_down_body(J.dst, J.desc.lv[level - 1], J.desc.lv[level], (blockIdx.x * blockDim.x + threadIdx.x) * 8,
-                  (blockIdx.y * blockDim.y + threadIdx.y) * 2);
+                  (blockIdx.y * blockDim.y + threadIdx.y) * 2, false);
 }
 
 // level 0 of a job: the source image (sw x sh) zero-extended at the bottom/right to the level size
@@ -215,14 +268,20 @@ int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, 
         const int rc = launch_pyr_level0(set, n_img, desc, spitch, st);
         if (rc != DVFE_OK) return rc;
     }
+    static const bool fuse_enabled = []() { const char* e = getenv("DVFE_PYR_FUSE"); return e == nullptr || atoi(e) != 0; }();
     for (int l = 0; l < desc.n_levels; l++) {
         const PyrLevel& D = desc.lv[l];
+        // levels >= 1 store their own border from the down-sampling kernel; level 0 (written by DMA or the copy kernel) and
+        // levels too small for single reflections keep the border kernel
+        const bool fuse = l > 0 && fuse_enabled && pyr_border_fusable(D);
         if (l > 0) {
             dim3 grid(((D.w + 7) / 8 + 31) / 32, ((D.h + 1) / 2 + 7) / 8, n_img);
-            DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D);
+            DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D, fuse ? 1 : 0);
         }
-        dim3 bgrid((D.h + 2 * DVFE_PADY + 7) / 8, 1, n_img);
-        DVFE_LAUNCH(k_pyr_border, bgrid, blk, 0, st, set, D);
+        if (!fuse) {
+            dim3 bgrid((D.h + 2 * DVFE_PADY + 7) / 8, 1, n_img);
+            DVFE_LAUNCH(k_pyr_border, bgrid, blk, 0, st, set, D);
+        }
     }
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
@@ -234,6 +293,22 @@ __global__ void k_pyr_extract(const uint8_t* base, PyrLevel L, uint8_t* out) {
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= L.w || y >= L.h) return;
     out[(size_t)y * L.w + x] = base[L.offset + (size_t)(y + DVFE_PADY) * L.pitch + DVFE_PADX + x];
+}
+
+// one level with `border` pixels of its REFLECT_101 border on every side, dense (w + 2 border) x (h + 2 border)
+__global__ void k_pyr_extract_bordered(const uint8_t* base, PyrLevel L, int border, uint8_t* out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ow = L.w + 2 * border, oh = L.h + 2 * border;
+    if (x >= ow || y >= oh) return;
+    out[(size_t)y * ow + x] = base[L.offset + (size_t)(y - border + DVFE_PADY) * L.pitch + DVFE_PADX + x - border];
+}
+
+int launch_pyr_extract_bordered(const uint8_t* pyr, const PyrLevel& L, int border, uint8_t* out, cudaStream_t st) {
+    dim3 blk(32, 8), grid((L.w + 2 * border + 31) / 32, (L.h + 2 * border + 7) / 8);
+    DVFE_LAUNCH(k_pyr_extract_bordered, grid, blk, 0, st, pyr, L, border, out);
+    DVFE_CUDA(cudaGetLastError());
+    return DVFE_OK;
 }
 
 int launch_pyr_extract(const uint8_t* pyr, const PyrLevel& L, uint8_t* out, cudaStream_t st) {

@@ -31,6 +31,18 @@ def build_pyramid(img, max_level: int = 3):
     return [outs[i][:hs[i], :ws[i]] for i in range(n.value)]
 
 
+def build_pyramid_bordered(img, level: int, border: int = 21, max_level: int = 3):
+    """One pyramid level with `border` pixels of its REFLECT_101 border (what LK reads), dense."""
+    img = _u8(img)
+    h, w = img.shape
+    lw, lh = w, h
+    for _ in range(level):
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+    out = np.zeros((lh + 2 * border, lw + 2 * border), np.uint8)
+    L.check(L.lib().dvfe_op_build_pyramid_bordered(L.ptr(img), w, h, img.strides[0], max_level, level, border, L.ptr(out)))
+    return out
+
+
 def feature_track_by_lk(img1, img2, pts1, flow_back: bool = True, max_level: int = 3, mask=None,
                         return_rev: bool = False):
     """FeatureTrackByLK (dynamic_vins/src/front_end/feature_utils.cpp:35-69) -> (pts2, status[, rev])."""

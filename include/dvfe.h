@@ -237,6 +237,11 @@ typedef struct dvfe_state {
     float* right_prev_un;       /* [cap*2] bg.right_prev_id_pts values (valid where right_prev_valid) */
     uint8_t* right_prev_valid;  /* [cap] */
 } dvfe_state;
+/* dvfe_get_state / dvfe_set_state cover the background point arrays of one stream (what the teacher-forced parity tests
+ * exchange with the oracle), NOT the previous-frame pyramid nor the instance table / ROI buffers: set_state is valid on a tracker
+ * that has already processed the previous frame (its pyramid is the LK template image of the next step); on a fresh tracker
+ * (no frame yet) the next step has no previous image and treats the restored points as the first frame's.  set_state
+ * invalidates the LK template caches and the captured step graphs. */
 int dvfe_get_state(dvfe_tracker* t, int stream, dvfe_state* st, int cap);
 int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* st);
 
@@ -246,6 +251,11 @@ int dvfe_set_state(dvfe_tracker* t, int stream, const dvfe_state* st);
  * Writes level l (l = 0..*n_levels-1) unpadded into out_levels[l] (size ((w+1)/2.., (h+1)/2..)). */
 int dvfe_op_build_pyramid(const uint8_t* img, int w, int h, int pitch, int max_level, uint8_t* const* out_levels,
                           int* level_w, int* level_h, int* n_levels);
+/* One level of the same pyramid WITH its border, as cv::buildOpticalFlowPyramid(img, pyr, winSize, maxLevel, false,
+ * BORDER_REFLECT_101) stores it: out = dense (w_l + 2 border) x (h_l + 2 border) bytes, border <= 21 (= winSize).  The LK
+ * kernels read this border; levels >= 1 write it from the down-sampling kernel itself. */
+int dvfe_op_build_pyramid_bordered(const uint8_t* img, int w, int h, int pitch, int max_level, int level, int border,
+                                   uint8_t* out);
 
 /* FeatureTrackByLK(img1,img2,pts1,pts2,flow_back) (front_end/feature_utils.cpp:35-69):
  * forward LK (max_level) + backward LK (max level 1, initial flow) + 0.5 px check + InBorder.

@@ -33,6 +33,23 @@ def test_pyramid_bit_exact(shape):
         ref = spec.pyr_down(ref)
 
 
+@pytest.mark.parametrize("shape", [(375, 1242), (480, 752), (720, 1280), (61, 77), (50, 60), (97, 203), (1080, 1920), (188, 621)])
+def test_pyramid_border_is_reflect_101(shape):
+    """every level WITH the border LK reads (cv::buildOpticalFlowPyramid stores a winSize = 21 px REFLECT_101 border): levels >= 1
+    write it from the down-sampling kernel itself when a single reflection reaches every border pixel, small levels through the
+    border kernel; both must equal copyMakeBorder of the exact interior"""
+    import cv2
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    a = rng.integers(0, 256, shape, dtype=np.uint8)
+    ref = a
+    for l in range(spec.pyr_levels(shape[1], shape[0], 3) + 1):
+        got = ops.build_pyramid_bordered(a, l, 21)
+        want = cv2.copyMakeBorder(ref, 21, 21, 21, 21, cv2.BORDER_REFLECT_101)
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), f"level {l} of {shape}: {int((got != want).sum())} border/interior bytes differ"
+        ref = spec.pyr_down(ref)
+
+
 def test_pyramid_golden(kitti_pair):
     g = load_golden("stages_kitti.npz")
     for l, lv in enumerate(ops.build_pyramid(kitti_pair[0].gray0, 3)):
