@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, i
 }
 
 // ---- REFLECT_101 border of a level, copied from its own interior; one warp per padded row ------------------
+// Word path (w a multiple of 4, single reflections): an interior word of a band row is an aligned copy; a left border word is
+// the byte permutation (W[j+1].b0, W[j].b3, W[j].b2, W[j].b1) of two adjacent interior words of the source row, a right border
+// word (V[m].b2, V[m].b1, V[m].b0, V[m+1].b3) with V[t] = the t-th word from the right end.  Other shapes: byte by byte.
 __device__ __forceinline__ void pyr_border_body(uint8_t* base, const PyrLevel& L, int py, int lane) {
     uint8_t* lvl = base + L.offset;
     const uint8_t* __restrict__ in = lvl + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;      // pixel (0,0)
@@ -49,6 +52,21 @@ __device__ __forceinline__ void pyr_border_body(uint8_t* base, const PyrLevel& L
     const bool band = y < 0 || y >= L.h;
     // band rows: every word; side rows: the left pad words, then the words from right0 on
     const int count = band ? nwords : (DVFE_PADX / 4 + nwords - right0);
+    const int padR = L.pitch - DVFE_PADX - L.w;
+    if ((L.w & 3) == 0 && L.w > DVFE_PADX + 4 && L.w > padR + 4) {
+        const unsigned* __restrict__ sw = reinterpret_cast<const unsigned*>(srow);       // interior words of the source row
+        const int iw = L.w / 4;
+        for (int t = lane; t < count; t += 32) {
+            const int wq = band ? t : (t < DVFE_PADX / 4 ? t : right0 + (t - DVFE_PADX / 4));
+            const int k = wq - DVFE_PADX / 4;          // interior word index (negative: left border, >= iw: right border)
+            unsigned v;
+            if (k < 0) { const int j = -k - 1; v = __byte_perm(sw[j], sw[j + 1], 0x1234); }
+            else if (k >= iw) { const int m = k - iw; v = __byte_perm(sw[iw - 1 - m], sw[iw - 2 - m], 0x7012); }
+            else v = sw[k];
+            orow[wq] = v;
+        }
+        return;
+    }
     for (int t = lane; t < count; t += 32) {
         const int wq = band ? t : (t < DVFE_PADX / 4 ? t : right0 + (t - DVFE_PADX / 4));
         const int x0 = wq * 4 - DVFE_PADX;
@@ -57,6 +75,59 @@ __device__ __forceinline__ void pyr_border_body(uint8_t* base, const PyrLevel& L
         for (int i = 0; i < 4; i++) v |= (unsigned)srow[reflect101(x0 + i, L.w)] << (8 * i);
         orow[wq] = v;
     }
+}
+
+// Word-path border of one level with every thread busy: a block takes 256 border words.  Blocks [0, side_blocks) cover the side
+// rows (rows_per_block rows x (PADX/4 + padR/4) words each), the blocks after them the 2 * PADY band rows (all pitch/4 words).
+__host__ __device__ __forceinline__ bool pyr_border_words_ok(const PyrLevel& L) {
+    const int padR = L.pitch - DVFE_PADX - L.w;
+    return (L.w & 3) == 0 && L.w > DVFE_PADX + 4 && L.w > padR + 4 && L.h > DVFE_PADY;
+}
+
+__global__ void __launch_bounds__(256) k_pyr_border_words(PyrImgSet set, PyrLevel L, int side_blocks) {
+    const uint8_t* src; uint8_t* base;
+    pyr_select(set, blockIdx.z, src, base);
+    uint8_t* lvl = base + L.offset;
+    const int nwords = L.pitch / 4, iw = L.w / 4, lw = DVFE_PADX / 4;
+    const int swn = nwords - iw;                       // border words of a side row: lw on the left, the rest on the right
+    int py, wq;
+    if ((int)blockIdx.x < side_blocks) {
+        const int rpb = 256 / swn;
+        const int r = threadIdx.x / swn, t = threadIdx.x - r * swn;
+        const int y = blockIdx.x * rpb + r;
+        if (r >= rpb || y >= L.h) return;
+        py = y + DVFE_PADY;
+        wq = t < lw ? t : iw + t;                      // right border words start at lw + iw
+    } else {
+        const int t = (blockIdx.x - side_blocks) * 256 + threadIdx.x;
+        const int r = t / nwords;
+        if (r >= 2 * DVFE_PADY) return;
+        wq = t - r * nwords;
+        py = r < DVFE_PADY ? r : L.h + r;              // rows above, then rows below the image
+    }
+    const int y = py - DVFE_PADY;
+    const int ys = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);          // single reflection (h > PADY)
+    const unsigned* __restrict__ sw = reinterpret_cast<const unsigned*>(lvl + (size_t)(ys + DVFE_PADY) * L.pitch + DVFE_PADX);
+    const int k = wq - lw;
+    unsigned v;
+    if (k < 0) { const int j = -k - 1; v = __byte_perm(sw[j], sw[j + 1], 0x1234); }
+    else if (k >= iw) { const int m = k - iw; v = __byte_perm(sw[iw - 1 - m], sw[iw - 2 - m], 0x7012); }
+    else v = sw[k];
+    reinterpret_cast<unsigned*>(lvl + (size_t)py * L.pitch)[wq] = v;
+}
+
+__global__ void k_pyr_border(PyrImgSet set, PyrLevel L);
+
+static int launch_pyr_border(const PyrImgSet& set, int n_img, const PyrLevel& D, cudaStream_t st) {
+    if (pyr_border_words_ok(D)) {
+        const int nwords = D.pitch / 4, swn = nwords - D.w / 4, rpb = 256 / swn;
+        const int side_blocks = (D.h + rpb - 1) / rpb, band_blocks = (2 * DVFE_PADY * nwords + 255) / 256;
+        DVFE_LAUNCH(k_pyr_border_words, dim3(side_blocks + band_blocks, 1, n_img), 256, 0, st, set, D, side_blocks);
+    } else {
+        dim3 bgrid((D.h + 2 * DVFE_PADY + 7) / 8, 1, n_img);
+        DVFE_LAUNCH(k_pyr_border, bgrid, dim3(32, 8), 0, st, set, D);
+    }
+    return DVFE_OK;
 }
 
 __global__ void __launch_bounds__(256) k_pyr_border(PyrImgSet set, PyrLevel L) {
@@ -78,15 +149,21 @@ __device__ __forceinline__ int pyr_tap5(const uint8_t* __restrict__ p) {
 
 // ---- REFLECT_101 border written by the threads that produce the interior (levels >= 1 of the batched pyramids) ----
 // Border position x' = -d (1 <= d <= PADX) holds pixel d, x' = w-1+d (1 <= d <= padR, padR = pitch - PADX - w) holds pixel
-// w-1-d; rows likewise with PADY above and below.  When w > max(PADX, padR) and h > PADY every border position is the
-// single reflection of an interior pixel, so the thread that computes a pixel can store its mirror images itself and the
-// separate k_pyr_border launch of that level disappears (pyr_border_fusable).
+// w-1-d; rows likewise with PADY above and below.  When every border position is the single reflection of an interior pixel,
+// the thread that computes a pixel can store its mirror images itself and the separate k_pyr_border launch of that level
+// disappears.  Done with whole words: a thread holds 8 pixels = 2 words of a row; a border word is a byte permutation of two
+// adjacent row words (__byte_perm), the second of which comes from the neighbouring thread by warp shuffle.  Conditions
+// (pyr_border_fusable): w a multiple of 8 (no ragged thread column; padR is then a multiple of 8 too), w > PADX + 8 and
+// w > padR + 8 (single reflection, neighbour exists), h > PADY + 1, and no right-edge thread is lane 0 of its warp.
 __host__ __device__ __forceinline__ bool pyr_border_fusable(const PyrLevel& L) {
     const int padR = L.pitch - DVFE_PADX - L.w;
-    return L.h > DVFE_PADY && L.w > DVFE_PADX && L.w > padR;
+    if ((L.w & 7) != 0 || L.w <= DVFE_PADX + 8 || L.w <= padR + 8 || L.h <= DVFE_PADY + 1) return false;
+    for (int q = 0; q * 8 < padR; q++)
+        if (((L.w / 8 - 1 - q) & 31) == 0) return false;
+    return true;
 }
 
-// one pixel and its mirror images (ragged edges of the interior)
+// one pixel and its mirror images (ragged bottom row of the interior: odd h)
 __device__ __forceinline__ void pyr_store_px_mirrored(uint8_t* __restrict__ dst, const PyrLevel& D, int x, int y, uint8_t v) {
     const int padR = D.pitch - DVFE_PADX - D.w;
     int xs[3], ys[3], nx = 1, ny = 1;
@@ -99,29 +176,28 @@ __device__ __forceinline__ void pyr_store_px_mirrored(uint8_t* __restrict__ dst,
         for (int i = 0; i < nx; i++) dst[(ptrdiff_t)ys[j] * D.pitch + xs[i]] = v;
 }
 
-// 8 pixels x0..x0+7 of row yy (interior or an already mirrored row): aligned store + the column mirrors of edge threads
-__device__ __forceinline__ void pyr_store8_cols(uint8_t* __restrict__ dst, const PyrLevel& D, int x0, int yy, uint2 v, bool fuse) {
-    uint8_t* __restrict__ row = dst + (ptrdiff_t)yy * D.pitch;
-    *reinterpret_cast<uint2*>(row + x0) = v;
-    if (!fuse) return;
+// Row y of the fused fast path: v = pixels x0..x0+7, nxt = first word of the next thread's pixels, prv = last word of the
+// previous thread's.  Stores the interior words and, for edge threads, the border words they mirror into; the same for the
+// rows above / below the image that mirror row y.
+__device__ __forceinline__ void pyr_store8_fused(uint8_t* __restrict__ dst, const PyrLevel& D, int x0, int y, uint2 v, unsigned nxt,
+                                                 unsigned prv) {
     const int padR = D.pitch - DVFE_PADX - D.w;
-    if (x0 <= DVFE_PADX || x0 + 7 >= D.w - 1 - padR) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int x = x0 + i;
-            const uint8_t b = (uint8_t)((i < 4 ? v.x >> (8 * i) : v.y >> (8 * (i - 4))) & 0xffu);
-            if (x >= 1 && x <= DVFE_PADX) row[-x] = b;
-            if (x <= D.w - 2 && x >= D.w - 1 - padR) row[2 * (D.w - 1) - x] = b;
-        }
+    const bool left = x0 < DVFE_PADX;                         // pixels x0+1 .. x0+8 -> x' = -x0-8 .. -x0-1
+    const int q8 = D.w - 8 - x0;                              // right: pixels x0-1 .. x0+6 -> x' = w+q8 .. w+q8+7
+    const bool right = q8 < padR;
+    // border word at x' in [-4j-4, -4j-1] = bytes (W[j+1].b0, W[j].b3, W[j].b2, W[j].b1); at [w+4m, w+4m+3] = (W'[m].b2, b1, b0, W'[m+1].b3)
+    const uint2 lb = make_uint2(__byte_perm(v.y, nxt, 0x1234), __byte_perm(v.x, v.y, 0x1234));
+    const uint2 rb = make_uint2(__byte_perm(v.y, v.x, 0x7012), __byte_perm(v.x, prv, 0x7012));
+    int ys[3], ny = 1;
+    ys[0] = y;
+    if (y >= 1 && y <= DVFE_PADY) ys[ny++] = -y;
+    if (y <= D.h - 2 && y >= D.h - 1 - DVFE_PADY) ys[ny++] = 2 * (D.h - 1) - y;
+    for (int j = 0; j < ny; j++) {
+        uint8_t* __restrict__ row = dst + (ptrdiff_t)ys[j] * D.pitch;
+        *reinterpret_cast<uint2*>(row + x0) = v;
+        if (left) *reinterpret_cast<uint2*>(row - x0 - 8) = lb;
+        if (right) *reinterpret_cast<uint2*>(row + D.w + q8) = rb;
     }
-}
-
-// ... of interior row y, plus its mirrored rows
-__device__ __forceinline__ void pyr_store8(uint8_t* __restrict__ dst, const PyrLevel& D, int x0, int y, uint2 v, bool fuse) {
-    pyr_store8_cols(dst, D, x0, y, v, fuse);
-    if (!fuse) return;
-    if (y >= 1 && y <= DVFE_PADY) pyr_store8_cols(dst, D, x0, -y, v, true);
-    if (y <= D.h - 2 && y >= D.h - 1 - DVFE_PADY) pyr_store8_cols(dst, D, x0, 2 * (D.h - 1) - y, v, true);
 }
 
 // one thread = 8 consecutive outputs of two consecutive rows.  It reads 7 source rows (one 16-byte and two
@@ -169,8 +245,24 @@ __device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, 
         o0.y = (acc0[4] >> 8) | ((acc0[5] >> 8) << 8) | ((acc0[6] >> 8) << 16) | ((acc0[7] >> 8) << 24);
         o1.x = (acc1[0] >> 8) | ((acc1[1] >> 8) << 8) | ((acc1[2] >> 8) << 16) | ((acc1[3] >> 8) << 24);
         o1.y = (acc1[4] >> 8) | ((acc1[5] >> 8) << 8) | ((acc1[6] >> 8) << 16) | ((acc1[7] >> 8) << 24);
-        pyr_store8(dst, D, x0, y0, o0, fuse_border);
-        pyr_store8(dst, D, x0, y0 + 1, o1, fuse_border);
+        if (!fuse_border) {
+            *reinterpret_cast<uint2*>(dst + (size_t)y0 * D.pitch + x0) = o0;
+            *reinterpret_cast<uint2*>(dst + (size_t)(y0 + 1) * D.pitch + x0) = o1;
+            return;
+        }
+        // the neighbours' adjacent words (the lanes of a warp are consecutive x0 of one row pair; w % 8 == 0, so every lane that
+        // has pixels is here)
+        const unsigned am = __activemask();
+        const unsigned n0 = __shfl_down_sync(am, o0.x, 1), n1 = __shfl_down_sync(am, o1.x, 1);
+        const unsigned p0 = __shfl_up_sync(am, o0.y, 1), p1 = __shfl_up_sync(am, o1.y, 1);
+        const bool edge = x0 < DVFE_PADX || D.w - 8 - x0 < D.pitch - DVFE_PADX - D.w || y0 <= DVFE_PADY || y0 + 1 >= D.h - 1 - DVFE_PADY;
+        if (!edge) {
+            *reinterpret_cast<uint2*>(dst + (size_t)y0 * D.pitch + x0) = o0;
+            *reinterpret_cast<uint2*>(dst + (size_t)(y0 + 1) * D.pitch + x0) = o1;
+            return;
+        }
+        pyr_store8_fused(dst, D, x0, y0, o0, n0, p0);
+        pyr_store8_fused(dst, D, x0, y0 + 1, o1, n1, p1);
         return;
     }
     // the ragged right / bottom edge of the interior (w % 8, odd h)
@@ -186,7 +278,7 @@ __device__ __forceinline__ void pyr_down_body(uint8_t* base, const PyrLevel& S, 
 }
 
 // fuse_border != 0: the level's REFLECT_101 border is stored here too (no k_pyr_border launch for it)
-__global__ void __launch_bounds__(256) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D, int fuse_border) {
+__global__ void __launch_bounds__(256, 5) k_pyr_down(PyrImgSet set, PyrLevel S, PyrLevel D, int fuse_border) {
     const uint8_t* unused; uint8_t* base;
     pyr_select(set, blockIdx.z, unused, base);
     pyr_down_body(base, S, D, (blockIdx.x * blockDim.x + threadIdx.x) * 8, (blockIdx.y * blockDim.y + threadIdx.y) * 2, fuse_border != 0);
@@ -278,10 +370,7 @@ int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, 
             dim3 grid(((D.w + 7) / 8 + 31) / 32, ((D.h + 1) / 2 + 7) / 8, n_img);
             DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D, fuse ? 1 : 0);
         }
-        if (!fuse) {
-            dim3 bgrid((D.h + 2 * DVFE_PADY + 7) / 8, 1, n_img);
-            DVFE_LAUNCH(k_pyr_border, bgrid, blk, 0, st, set, D);
-        }
+        if (!fuse) launch_pyr_border(set, n_img, D, st);
     }
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;

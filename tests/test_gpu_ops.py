@@ -33,7 +33,7 @@ def test_pyramid_bit_exact(shape):
         ref = spec.pyr_down(ref)
 
 
-@pytest.mark.parametrize("shape", [(375, 1242), (480, 752), (720, 1280), (61, 77), (50, 60), (97, 203), (1080, 1920), (188, 621)])
+@pytest.mark.parametrize("shape", [(375, 1242), (480, 752), (720, 1280), (61, 77), (50, 60), (97, 203), (1080, 1920), (188, 621), (200, 528), (51, 96), (54, 176), (412, 2064)])
 def test_pyramid_border_is_reflect_101(shape):
     """every level WITH the border LK reads (cv::buildOpticalFlowPyramid stores a winSize = 21 px REFLECT_101 border): levels >= 1
     write it from the down-sampling kernel itself when a single reflection reaches every border pixel, small levels through the
