@@ -34,9 +34,13 @@ struct ErodeJob {
 };
 
 // pyramid.cu
+#define DVFE_L0_BUILD 0        // level 0 is copied from the source images (border included when pyr_level0_writes_border)
+#define DVFE_L0_INTERIOR 1     // level 0's interior is already in place (DMA / ingest kernel), its border is not
+#define DVFE_L0_COMPLETE 2     // level 0 is in place with its border
 int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
-                          bool level0_in_place = false);
+                          int level0_mode = DVFE_L0_BUILD);
 int launch_pyr_level0(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st);
+bool pyr_level0_writes_border(const PyrDesc& desc);
 // Frame ingest (prep.cu): optional fixed-point cv::remap (undistortion maps) + optional BGR -> gray, B images per launch,
 // written at dst_pitch (straight into level 0 of a padded pyramid, or dense).
 struct IngestArgs {

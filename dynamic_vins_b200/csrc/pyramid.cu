@@ -16,8 +16,19 @@ __device__ __forceinline__ void pyr_select(const PyrImgSet& set, int img, const 
     dst = (second ? set.dst[1] : set.dst[0]) + (size_t)idx * set.dst_stride;
 }
 
-// ---- level 0 interior: copy the u8 image into the padded level; one thread = 16 bytes ------------------
-__global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, int spitch) {
+// ---- level 0: copy the u8 image into the padded level; one thread = 16 bytes ------------------
+// fuse_border (pyr_level0_fusable: w and padR multiples of 16, single reflections, the right-edge threads not lane 0 of their
+// warp): the thread also stores the REFLECT_101 border words its pixels mirror into (byte permutations of adjacent words, the
+// neighbour's word by warp shuffle) and the rows above / below the image that mirror its row: no border launch for level 0.
+__host__ __device__ __forceinline__ bool pyr_level0_fusable(const PyrLevel& L) {
+    const int padR = L.pitch - DVFE_PADX - L.w;
+    if ((L.w & 15) != 0 || (padR & 15) != 0 || L.w <= DVFE_PADX + 16 || L.w <= padR + 16 || L.h <= DVFE_PADY + 1) return false;
+    for (int q = 0; q * 16 < padR; q++)
+        if (((L.w / 16 - 1 - q) & 31) == 0) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, int spitch, int fuse_border) {
     const uint8_t* src; uint8_t* dst;
     pyr_select(set, blockIdx.z, src, dst);
     dst += L.offset + (size_t)DVFE_PADY * L.pitch + DVFE_PADX;
@@ -26,13 +37,44 @@ __global__ void __launch_bounds__(256) k_pyr_level0(PyrImgSet set, PyrLevel L, i
     if (x0 >= L.w || y >= L.h) return;
     const uint8_t* row = src + (size_t)y * spitch + x0;
     uint8_t* out = dst + (size_t)y * L.pitch + x0;
+    uint4 q;
     if (x0 + 15 < L.w && (((uintptr_t)row) & 15) == 0) {
-        *reinterpret_cast<uint4*>(out) = __ldg(reinterpret_cast<const uint4*>(row));
+        q = __ldg(reinterpret_cast<const uint4*>(row));
     } else if (x0 + 15 < L.w && (((uintptr_t)row) & 3) == 0) {
         const unsigned* p = reinterpret_cast<const unsigned*>(row);
-        *reinterpret_cast<uint4*>(out) = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+        q = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    } else if (x0 + 15 < L.w) {
+        unsigned w4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            w4[i] = (unsigned)__ldg(row + 4 * i) | ((unsigned)__ldg(row + 4 * i + 1) << 8) | ((unsigned)__ldg(row + 4 * i + 2) << 16) |
+                    ((unsigned)__ldg(row + 4 * i + 3) << 24);
+        q = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     } else {
-        for (int i = 0; i < 16 && x0 + i < L.w; i++) out[i] = __ldg(row + i);
+        for (int i = 0; i < 16 && x0 + i < L.w; i++) out[i] = __ldg(row + i);      // ragged last column (never with fuse_border)
+        return;
+    }
+    *reinterpret_cast<uint4*>(out) = q;
+    if (!fuse_border) return;
+    const unsigned am = __activemask();
+    const unsigned nxt = __shfl_down_sync(am, q.x, 1), prv = __shfl_up_sync(am, q.w, 1);
+    const int padR = L.pitch - DVFE_PADX - L.w, q16 = L.w - 16 - x0;
+    const bool left = x0 < DVFE_PADX, right = q16 < padR;
+    int ys[3], ny = 1;
+    ys[0] = y;
+    if (y >= 1 && y <= DVFE_PADY) ys[ny++] = -y;
+    if (y <= L.h - 2 && y >= L.h - 1 - DVFE_PADY) ys[ny++] = 2 * (L.h - 1) - y;
+    if (!left && !right && ny == 1) return;
+    // pixels x0+1 .. x0+16 reversed -> x' = -x0-16 .. -x0-1 ; pixels x0-1 .. x0+14 reversed -> x' = w+q16 .. w+q16+15
+    const uint4 lb = make_uint4(__byte_perm(q.w, nxt, 0x1234), __byte_perm(q.z, q.w, 0x1234), __byte_perm(q.y, q.z, 0x1234),
+                                __byte_perm(q.x, q.y, 0x1234));
+    const uint4 rb = make_uint4(__byte_perm(q.w, q.z, 0x7012), __byte_perm(q.z, q.y, 0x7012), __byte_perm(q.y, q.x, 0x7012),
+                                __byte_perm(q.x, prv, 0x7012));
+    for (int j = 0; j < ny; j++) {
+        uint8_t* __restrict__ orow = dst + (ptrdiff_t)ys[j] * L.pitch;
+        if (j > 0) *reinterpret_cast<uint4*>(orow + x0) = q;
+        if (left) *reinterpret_cast<uint4*>(orow - x0 - 16) = lb;
+        if (right) *reinterpret_cast<uint4*>(orow + L.w + q16) = rb;
     }
 }
 
@@ -342,35 +384,42 @@ int launch_crop_jobs(const CropJob* d_jobs, int n_jobs, int max_w, int max_h, cu
     return DVFE_OK;
 }
 
-// the caller's dense images -> the interior of level 0 of the padded pyramids
+// the caller's dense images -> level 0 of the padded pyramids; *border_done (nullable) = the border was written too
+static bool pyr_fuse_enabled() {
+    static const bool on = []() { const char* e = getenv("DVFE_PYR_FUSE"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
+bool pyr_level0_writes_border(const PyrDesc& desc) { return pyr_fuse_enabled() && pyr_level0_fusable(desc.lv[0]); }
+
 int launch_pyr_level0(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st) {
     const dim3 blk(32, 8);
     const PyrLevel& L = desc.lv[0];
     dim3 grid(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, n_img);
-    DVFE_LAUNCH(k_pyr_level0, grid, blk, 0, st, set, L, spitch);
+    DVFE_LAUNCH(k_pyr_level0, grid, blk, 0, st, set, L, spitch, pyr_level0_writes_border(desc) ? 1 : 0);
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;
 }
 
-// level0_in_place: level 0's interior has already been written (H2D straight into the padded layout)
-int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st,
-                          bool level0_in_place) {
+// level0_mode: DVFE_L0_BUILD = copy level 0 from set.src; DVFE_L0_INTERIOR = its interior is in place (H2D straight into the padded
+// layout, or an ingest kernel), the border is not; DVFE_L0_COMPLETE = interior and border are in place
+int launch_build_pyramids(const PyrImgSet& set, int n_img, const PyrDesc& desc, int spitch, cudaStream_t st, int level0_mode) {
     const dim3 blk(32, 8);
-    if (!level0_in_place) {
+    bool l0_border_done = level0_mode == DVFE_L0_COMPLETE;
+    if (level0_mode == DVFE_L0_BUILD) {
         const int rc = launch_pyr_level0(set, n_img, desc, spitch, st);
         if (rc != DVFE_OK) return rc;
+        l0_border_done = pyr_level0_writes_border(desc);
     }
-    static const bool fuse_enabled = []() { const char* e = getenv("DVFE_PYR_FUSE"); return e == nullptr || atoi(e) != 0; }();
     for (int l = 0; l < desc.n_levels; l++) {
         const PyrLevel& D = desc.lv[l];
-        // levels >= 1 store their own border from the down-sampling kernel; level 0 (written by DMA or the copy kernel) and
-        // levels too small for single reflections keep the border kernel
-        const bool fuse = l > 0 && fuse_enabled && pyr_border_fusable(D);
+        // levels >= 1 store their own border from the down-sampling kernel; levels too small or too ragged for single word
+        // reflections keep a border launch
+        const bool fuse = l > 0 && pyr_fuse_enabled() && pyr_border_fusable(D);
         if (l > 0) {
             dim3 grid(((D.w + 7) / 8 + 31) / 32, ((D.h + 1) / 2 + 7) / 8, n_img);
             DVFE_LAUNCH(k_pyr_down, grid, blk, 0, st, set, desc.lv[l - 1], D, fuse ? 1 : 0);
         }
-        if (!fuse) launch_pyr_border(set, n_img, D, st);
+        if (!fuse && !(l == 0 && l0_border_done)) launch_pyr_border(set, n_img, D, st);
     }
     DVFE_CUDA(cudaGetLastError());
     return DVFE_OK;

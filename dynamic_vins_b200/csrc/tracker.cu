@@ -360,7 +360,7 @@ void dvfe_tracker::drop_graphs() {
 // No host-dependent state is read: the same call with the same arguments enqueues the same work, which is what lets
 // submit() capture it into a graph.
 int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, bool semantic,
-                                  bool level0_in_place, bool stereo_now, long k, bool with_marks) {
+                                  int level0_mode, bool stereo_now, long k, bool with_marks) {
     const int ph = (int)(k % 6), par = (int)(k % 2);
     auto mark = [&](int i) { if (with_marks) cudaEventRecord(ev[par][i], st); };
     DVFE_CUDA(cudaMemcpyAsync(d_dt, h_dt[par], B * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -374,7 +374,7 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
     set.src[0] = d_left; set.src[1] = nullptr;
     set.dst[0] = left_slot(k); set.dst[1] = nullptr;
     set.src_stride = stream_stride; set.dst_stride = desc.bytes; set.per_set = B;
-    DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_in_place));
+    DVFE_CHECK(launch_build_pyramids(set, B, desc, pitch, st, level0_mode));
     mark(ST_PYRAMID + 1);
     // The temporal call's backward templates (current left image at the tracked positions, levels <= its backward maxLevel)
     // are the stereo call's forward templates at those levels for the survivors: stored by the former, picked up through
@@ -398,7 +398,7 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
         rset.dst[0] = right_slot(k); rset.dst[1] = nullptr;
         rset.src_stride = stream_stride; rset.dst_stride = desc.bytes; rset.per_set = B;
         DVFE_CUDA(cudaStreamWaitEvent(rs, ev_resp[par], 0));        // after the response kernel of this step (and so
-        DVFE_CHECK(launch_build_pyramids(rset, B, desc, pitch, rs, level0_in_place));   // after the upload it waited for)
+        DVFE_CHECK(launch_build_pyramids(rset, B, desc, pitch, rs, level0_mode));   // after the upload it waited for)
         DVFE_CUDA(cudaEventRecord(ev_rpyr[par], rs));
     }
     mark(ST_GFTT_SELECT + 1);
@@ -418,14 +418,15 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
 }
 
 // Capture and instantiate the graph of the step with buffer phase `ph` and mode `flags` (bit 0 semantic, 2 stereo, 3 not the first
-// frame, 4 forward templates cached); `k` = any frame index with k % 6 == ph and (k > 0) as in the flags.  Nothing runs.
+// frame, 4 forward templates cached, 5 level 0 arrives with its border); `k` = any frame index with k % 6 == ph and (k > 0) as in the flags.  Nothing runs.
 int dvfe_tracker::capture_step(int ph, unsigned flags, long k) {
     const unsigned long long before = g_dvfe_launches;
     const bool keep_valid = tcache_valid;
     tcache_valid = (flags & 16u) != 0;
     cudaGraph_t g = nullptr;
     DVFE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    const int rc = enqueue_compute(nullptr, nullptr, 0, 0, (flags & 1u) != 0, true, (flags & 4u) != 0, k, false);
+    const int rc = enqueue_compute(nullptr, nullptr, 0, 0, (flags & 1u) != 0, (flags & 32u) ? DVFE_L0_COMPLETE : DVFE_L0_INTERIOR,
+                                   (flags & 4u) != 0, k, false);
     const cudaError_t ce = cudaStreamEndCapture(st, &g);
     tcache_valid = keep_valid;
     const unsigned n_kernels = (unsigned)(g_dvfe_launches - before);
@@ -474,7 +475,9 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
                 DVFE_CUDA(cudaStreamWaitEvent(st, ev_r0[par], 0));
             }
         }
-        const unsigned flags = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | (k > 0 ? 8u : 0u) | (tcache_valid ? 16u : 0u);
+        // level 0 copied by the kernel above arrives with its border; DMA / ingest kernels leave the border to the graph
+        const bool l0_complete = !level0_in_place && pyr_level0_writes_border(desc);
+        const unsigned flags = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | (k > 0 ? 8u : 0u) | (tcache_valid ? 16u : 0u) | (l0_complete ? 32u : 0u);
         const StepKey key(ph, flags);
         if (step_graphs.find(key) == step_graphs.end()) {
             if (step_graphs.size() >= 64) drop_graphs();          // a caller cycling through many modes
@@ -482,7 +485,7 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
             // The first step of a mode also captures the six steady-state graphs it will replay from the next frame on (one per
             // buffer phase), so that instantiation (host time, ~0.3 ms each) never falls into a later, possibly timed, step.
             const bool tc_next = stereo_now && d_tcache != nullptr;
-            const unsigned steady = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | 8u | (tc_next ? 16u : 0u);
+            const unsigned steady = (semantic ? 1u : 0u) | (stereo_now ? 4u : 0u) | 8u | (tc_next ? 16u : 0u) | (l0_complete ? 32u : 0u);
             for (int p = 0; p < 6; p++)
                 if (step_graphs.find(StepKey(p, steady)) == step_graphs.end()) DVFE_CHECK(capture_step(p, steady, 6 + p));
         }
@@ -490,7 +493,8 @@ int dvfe_tracker::submit(const uint8_t* d_left, const uint8_t* d_right, size_t s
         DVFE_CUDA(cudaGraphLaunch(it->second.exec, st));
         g_dvfe_launches += it->second.n_kernels;
     } else {
-        DVFE_CHECK(enqueue_compute(d_left, d_right, stream_stride, pitch, semantic, level0_in_place, stereo_now, k, prof));
+        DVFE_CHECK(enqueue_compute(d_left, d_right, stream_stride, pitch, semantic, level0_in_place ? DVFE_L0_INTERIOR : DVFE_L0_BUILD,
+                                   stereo_now, k, prof));
     }
     tcache_valid = stereo_now && d_tcache != nullptr;
     // records go home on the download stream so that the next step's kernels do not queue behind the copy

@@ -88,7 +88,7 @@ struct dvfe_tracker {
     void drop_graphs();
     int capture_step(int ph, unsigned flags, long k);
     int enqueue_compute(const uint8_t* d_left, const uint8_t* d_right, size_t stream_stride, int pitch, bool semantic,
-                        bool level0_in_place, bool stereo_now, long k, bool with_marks);
+                        int level0_mode, bool stereo_now, long k, bool with_marks);
 
     // per-stage device timers (one event set per in-flight step)
     enum { ST_PYRAMID, ST_LK_TEMPORAL, ST_COMPACT, ST_GFTT_MASK, ST_GFTT_DISCS, ST_GFTT_RESPONSE, ST_GFTT_SELECT, ST_LEFT_POST,
