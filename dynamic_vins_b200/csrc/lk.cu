@@ -162,7 +162,8 @@ __device__ __forceinline__ void lk_stage_window_async(uint8_t* __restrict__ win,
 // Scharr derivatives at the 8x2 taps the run's bilinear samples touch, computed with dp4a on 4-byte windows
 // (row filter and the vertical 3/10/3 resp. -1/+1 weights folded into the int8 tap weights), then the 14-bit
 // fixed-point bilinear samples of I, Ix, Iy.
-__device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win, int ry, int x0, int xs, bool valid, bool interior,
+template <bool INTERIOR>
+__device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win, int ry, int x0, int xs,
                                                 int ipx, int ipy, int lw, int lh, int iw00, int iw01, int iw10, int iw11,
                                                 int (&Ix)[LK_RUN], int (&Iy)[LK_RUN], int& c1, int& c2, int& sA11,
                                                 int& sA12, int& sA22) {
@@ -191,7 +192,7 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
             if (r == 3) { gx1[j] = dp4a_us(W, 0x000300FD, gx1[j]); gy1[j] = dp4a_us(W, 0x00030A03, gy1[j]); }
         }
     }
-    if (!interior) {
+    if (!INTERIOR) {
         // the derivative image has a ZERO border (cv::copyMakeBorder BORDER_CONSTANT): taps outside the image are 0
         const bool r0 = (unsigned)(ipy + ry) < (unsigned)lh, r1 = (unsigned)(ipy + ry + 1) < (unsigned)lh;
 #pragma unroll
@@ -210,7 +211,6 @@ __device__ __forceinline__ void lk_template_run(const uint8_t* __restrict__ win,
         const int ival = dp2a_hi_su(W23, T, dp2a_lo_su(W01, T, 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
         int ixv = (gx0[j] * iw00 + gx0[j + 1] * iw01 + gx1[j] * iw10 + gx1[j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
         int iyv = (gy0[j] * iw00 + gy0[j + 1] * iw01 + gy1[j] * iw10 + gy1[j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-        if (!valid) { ixv = 0; iyv = 0; }
         Ix[j] = ixv; Iy[j] = iyv;
         c1 += ival * ixv; c2 += ival * iyv;
         sA11 += ixv * ixv; sA12 += ixv * iyv; sA22 += iyv * iyv;
@@ -339,12 +339,19 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_BLOCKS) k_lk_track(const
                 const float a = prevx - (float)ipx, b = prevy - (float)ipy;
                 int iw00, iw01, iw10, iw11;
                 lk_weights(a, b, iw00, iw01, iw10, iw11);
+                // warp-uniform: the patch and its derivative taps lie inside the image (no zero-border rule to apply); the two
+                // variants are separate code so that interior patches, nearly all of them, skip the 64 border selects
                 const bool interior = ipx >= 0 && ipy >= 0 && ipx + 22 <= L.w && ipy + 22 <= L.h;
                 int sA11 = 0, sA12 = 0, sA22 = 0;
-                lk_template_run(win, ry0, rx0, rx0 + wm, true, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2,
-                                sA11, sA12, sA22);
-                lk_template_run(win, ry1, rx1, rx1 + wm, has1, interior, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix1, Iy1, c1, c2,
-                                sA11, sA12, sA22);
+                // lane 31 owns one run only: its second run is computed with zero weights, which makes I, Ix and Iy zero
+                const int v00 = has1 ? iw00 : 0, v01 = has1 ? iw01 : 0, v10 = has1 ? iw10 : 0, v11 = has1 ? iw11 : 0;
+                if (interior) {
+                    lk_template_run<true>(win, ry0, rx0, rx0 + wm, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2, sA11, sA12, sA22);
+                    lk_template_run<true>(win, ry1, rx1, rx1 + wm, ipx, ipy, L.w, L.h, v00, v01, v10, v11, Ix1, Iy1, c1, c2, sA11, sA12, sA22);
+                } else {
+                    lk_template_run<false>(win, ry0, rx0, rx0 + wm, ipx, ipy, L.w, L.h, iw00, iw01, iw10, iw11, Ix0, Iy0, c1, c2, sA11, sA12, sA22);
+                    lk_template_run<false>(win, ry1, rx1, rx1 + wm, ipx, ipy, L.w, L.h, v00, v01, v10, v11, Ix1, Iy1, c1, c2, sA11, sA12, sA22);
+                }
                 {
                     const bool small = !__any_sync(0xffffffffu, (lk_big(sA11) | lk_big(sA12) | lk_big(sA22)) != 0u);
                     A11 = warp_sum_f(sA11, small, FLT_SCALE);
