@@ -78,7 +78,7 @@ SYMBOLS = [
     "dvfe_op_build_pyramid", "dvfe_op_lk", "dvfe_op_min_eigen_val", "dvfe_op_good_features",
     "dvfe_op_disc_mask", "dvfe_op_erode_rect", "dvfe_op_lift_projective", "dvfe_op_bgr_to_gray", "dvfe_op_merge_masks",
     "dvfe_op_remap", "dvfe_set_input", "dvfe_set_undistort_maps", "dvfe_track_dynamic_async", "dvfe_op_punch_out", "dvfe_insts_table", "dvfe_track_dynamic_ex",
-    "dvfe_op_reject_with_f", "dvfe_op_detect_extra_points", "dvfe_op_build_pyramid_bordered",
+    "dvfe_op_reject_with_f", "dvfe_op_detect_extra_points", "dvfe_op_build_pyramid_bordered", "dvfe_set_detect_mode", "dvfe_op_good_features_cuda",
 ]
 
 _lib = None
@@ -123,7 +123,7 @@ def lib() -> C.CDLL:
         L.dvfe_op_lk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dvfe_op_min_eigen_val.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-        L.dvfe_op_good_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+        L.dvfe_op_good_features_cuda.argtypes = L.dvfe_op_good_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]
         L.dvfe_op_disc_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
@@ -140,6 +140,7 @@ def lib() -> C.CDLL:
         L.dvfe_set_input.argtypes = [C.c_void_p, C.c_int]
         L.dvfe_set_undistort_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.dvfe_op_merge_masks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.dvfe_set_detect_mode.argtypes = [C.c_void_p, C.c_int]
         L.dvfe_op_build_pyramid_bordered.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.dvfe_op_reject_with_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                             C.POINTER(C.c_int)]

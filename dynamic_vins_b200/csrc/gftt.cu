@@ -154,7 +154,7 @@ struct __align__(128) RespSmem {
 
 struct RespCtx {                 // per-strip constants of the marching stencil
     int w, h, y0, y1, lane, x;
-    bool owned_col, cand_col, x_border;
+    bool owned_col, cand_col, x_border, max_all;
     float* __restrict__ eig;
     int* __restrict__ counters; unsigned long long* __restrict__ cand; int cand_cap;
 };
@@ -226,7 +226,7 @@ __device__ __forceinline__ void resp_step(const RespCtx& C, RespState& S, int y,
         lam = __fsub_rn(__fadd_rn(a, cc), sqrtf(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
         if (C.owned_col && (FAST || (yl >= C.y0 && yl < C.y1))) {
             if (WRITE_EIG) C.eig[(size_t)yl * w + x] = lam;
-            if (EMIT && mk2 != 0) S.best = max(S.best, f2ord(lam));
+            if (EMIT && (mk2 != 0 || C.max_all)) S.best = max(S.best, f2ord(lam));
         }
     }
     if (!EMIT) return;
@@ -268,6 +268,7 @@ struct RespIn {
     const CUtensorMap* tmap; int tma_x, tma_y;      // non-null: the tile is box (tma_x, tma_y) of this 2-D tensor (TMA load)
     const uint8_t* __restrict__ region; int region_pitch;     // nullable
     const float2* __restrict__ pts; int n_pts, radius;        // discs (n_pts = 0: none)
+    bool max_all;                                             // the maximum is taken over every pixel (GfttJob::max_unmasked)
 };
 
 template <bool WRITE_EIG, bool EMIT>
@@ -358,6 +359,7 @@ __device__ __forceinline__ void resp_strip(RespSmem& sm, const RespIn& in, int x
         const unsigned lo = __ballot_sync(0xffffffffu, sm.bits[lane] != 0u), hi = __ballot_sync(0xffffffffu, sm.bits[lane + 32] != 0u);
         const unsigned long long occ = ((unsigned long long)hi << 32) | lo;
         need = occ | (occ << 1) | (occ << 2) | (occ << 3) | (occ << 4) | (occ << 5) | (occ << 6);
+        if (in.max_all) need = (1ull << (rows_n + 6)) - 1ull;      // the whole-image maximum needs every row (y0-3 .. y1+2)
     } else {
         need = (1ull << (rows_n + 5)) - 1ull;          // every row: y0-3 .. y1+1
     }
@@ -377,6 +379,7 @@ __device__ __forceinline__ void resp_strip(RespSmem& sm, const RespIn& in, int x
     C.owned_col = owned_col;
     C.cand_col = owned_col && x >= 1 && x < w - 1;
     C.x_border = xb < 2 || xb + 30 > w;
+    C.max_all = in.max_all;
     C.eig = eig; C.counters = counters; C.cand = cand; C.cand_cap = cand_cap;
     RespState S;
     // interior steps: rows y-3..y inside the image and owned by the strip, all 32 columns (plus the edge columns) inside
@@ -429,6 +432,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_gftt_response(
     in.tma_x = DVFE_PADX + xb - 3; in.tma_y = (int)blockIdx.z * tma_rows_per_job + DVFE_PADY + y0 - 3;
     in.region = J.region_mask; in.region_pitch = J.region_pitch;
     in.pts = J.pts; in.n_pts = *J.n; in.radius = J.disc_radius;
+    in.max_all = J.max_unmasked != 0;
     resp_strip<false, true>(s_resp[threadIdx.x >> 5], in, xb, y0, rows, nullptr, J.counters, J.cand, J.cand_cap);
 }
 
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 32 / RS_WARPS) k_min_eigen_val(
     RespIn in;
     in.img = img; in.pitch = pitch; in.w = w; in.h = h; in.bordered = false;
     in.tmap = nullptr; in.tma_x = 0; in.tma_y = 0;
-    in.region = nullptr; in.region_pitch = 0; in.pts = nullptr; in.n_pts = 0; in.radius = 0;
+    in.region = nullptr; in.region_pitch = 0; in.pts = nullptr; in.n_pts = 0; in.radius = 0; in.max_all = false;
     resp_strip<true, false>(s_resp[threadIdx.x >> 5], in, xb, y0, RS_ROWS, eig, nullptr, nullptr, 0);
 }
 
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(256) k_gftt_max_ext(const GfttJob* __restrict_
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     int best = INT_MIN;
-    if (x < J.w && y < J.h && J.mask[(size_t)y * J.mask_pitch + x] != 0) best = f2ord(J.eig_in[(size_t)y * J.w + x]);
+    if (x < J.w && y < J.h && (J.max_unmasked != 0 || J.mask[(size_t)y * J.mask_pitch + x] != 0)) best = f2ord(J.eig_in[(size_t)y * J.w + x]);
     best = __reduce_max_sync(0xffffffffu, best);
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && best != INT_MIN) atomicMax(&J.counters[1], best);
 }

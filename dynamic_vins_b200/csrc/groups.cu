@@ -138,6 +138,11 @@ int grp_set_lk_mode(dvfe_tracker* t, int site, int back_max_level, double fb) {
     return DVFE_OK;
 }
 
+int grp_set_detect_mode(dvfe_tracker* t, int mode) {
+    for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_set_detect_mode(g, mode));
+    return DVFE_OK;
+}
+
 int grp_profile(dvfe_tracker* t, int enable) {
     for (dvfe_tracker* g : t->groups) DVFE_CHECK(dvfe_profile(g, enable));
     return DVFE_OK;

@@ -101,6 +101,8 @@ struct GfttJob {                 // one detection problem (a stream's image, or 
     int disc_radius;             // radius of the discs around existing points
     float min_dist;              // NMS distance
     double quality;              // 0.01
+    int max_unmasked;            // 1: the quality threshold comes from the maximum over the WHOLE response map, not only the unmasked
+                                 //    pixels (cv::cuda::GoodFeaturesToTrackDetector: cuda::minMax(eig) without the mask)
 };
 // marks (nullable): 3 events recorded after the mask fill, the discs and the response kernel;
 // after_response (nullable): recorded between the response kernel and the (few-CTA) selection kernel

@@ -160,9 +160,9 @@ extern "C" int dvfe_op_min_eigen_val(const uint8_t* img, int w, int h, int pitch
     return DVFE_OK;
 }
 
-extern "C" int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
-                                     int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
-                                     int* n_out, int* n_candidates_out) {
+static int op_good_features(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
+                            int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
+                            int* n_out, int* n_candidates_out, int max_unmasked) {
     if ((!img && !eig) || w < 3 || h < 3 || max_corners < 1 || max_corners > 2048 || !corners_out || !n_out) {
         dvfe_set_error("op_good_features: bad argument (max_corners must be in 1..2048)");
         return DVFE_ERR_INVALID;
@@ -192,6 +192,7 @@ extern "C" int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch
         J.pts = d_pts.as<float2>(); J.n = d_n.as<int>();
         J.max_cnt = max_corners; J.min_needed = 1; J.disc_radius = 0;
         J.min_dist = (float)min_dist; J.quality = quality;
+        J.max_unmasked = max_unmasked;
         rc = d_job.alloc(sizeof(GfttJob));
         if (rc == DVFE_OK && cudaMemcpy(d_job.p, &J, sizeof(J), cudaMemcpyHostToDevice) != cudaSuccess) rc = DVFE_ERR_CUDA;
         if (rc == DVFE_OK) rc = launch_gftt(d_job.as<GfttJob>(), &J, 1, w, h, 0, 0);
@@ -210,6 +211,18 @@ extern "C" int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch
     }
     free_gftt_scratch(&sc);
     return rc;
+}
+
+extern "C" int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
+                                     int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
+                                     int* n_out, int* n_candidates_out) {
+    return op_good_features(img, w, h, pitch, eig, mask, mask_pitch, max_corners, quality, min_dist, corners_out, n_out, n_candidates_out, 0);
+}
+
+extern "C" int dvfe_op_good_features_cuda(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
+                                          int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
+                                          int* n_out, int* n_candidates_out) {
+    return op_good_features(img, w, h, pitch, eig, mask, mask_pitch, max_corners, quality, min_dist, corners_out, n_out, n_candidates_out, 1);
 }
 
 extern "C" int dvfe_op_disc_mask(uint8_t* mask, int w, int h, int pitch, const float* pts, int n, int radius) {

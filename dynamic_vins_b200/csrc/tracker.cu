@@ -41,6 +41,7 @@ int grp_track_semantic(dvfe_tracker* t, const uint8_t* left, const uint8_t* righ
                        const int* exist, const double* time0);
 int grp_route(dvfe_tracker* t, int stream, dvfe_tracker** leaf, int* local);
 int grp_set_lk_mode(dvfe_tracker* t, int site, int back_max_level, double fb);
+int grp_set_detect_mode(dvfe_tracker* t, int mode);
 int grp_profile(dvfe_tracker* t, int enable);
 int grp_profile_read(dvfe_tracker* t, const char** names, double* total_ms, long* steps);
 #define IS_GROUP(t) ((t) != nullptr && !(t)->groups.empty())
@@ -267,10 +268,10 @@ int dvfe_tracker::init() {
             DVFE_CUDA(cudaMemcpy(d_groups[ph][kind], g.data(), B * sizeof(LkGroup), cudaMemcpyHostToDevice));
         }
     }
-    // GFTT jobs: [phase][raw | semantic]
+    // GFTT jobs: [phase][raw | semantic | semantic with the cv::cuda detector's threshold (TrackImageNaive)]
     std::vector<GfttJob> jobs(B);
     for (int ph = 0; ph < 6; ph++)
-        for (int kind = 0; kind < 2; kind++) {
+        for (int kind = 0; kind < 3; kind++) {
             for (int s = 0; s < B; s++) {
                 GfttJob& J = jobs[s];
                 memset(&J, 0, sizeof(J));
@@ -279,7 +280,8 @@ int dvfe_tracker::init() {
                 J.img_pitch = L0.pitch;
                 J.w = W; J.h = H;
                 J.img_bordered = 1;
-                if (kind == 1) { J.region_mask = d_region + (size_t)s * P; J.region_pitch = W; }
+                if (kind >= 1) { J.region_mask = d_region + (size_t)s * P; J.region_pitch = W; }
+                J.max_unmasked = kind == 2 ? 1 : 0;
                 gftt_job_bind_scratch(&J, gsc, s);
                 const size_t o = (size_t)s * cap;
                 J.pts = bg.pts + o; J.ids = bg.ids + o; J.track_cnt = bg.track_cnt + o;
@@ -336,7 +338,7 @@ extern "C" void dvfe_destroy(dvfe_tracker* t) {
     free_gftt_scratch(&t->gsc);
     for (int p = 0; p < 6; p++) {
         for (int k = 0; k < 3; k++) cudaFree(t->d_groups[p][k]);
-        for (int k = 0; k < 2; k++) cudaFree(t->d_jobs[p][k]);
+        for (int k = 0; k < 3; k++) cudaFree(t->d_jobs[p][k]);
     }
     t->free_instances();
     if (t->cs) cudaStreamDestroy(t->cs);
@@ -389,7 +391,7 @@ int dvfe_tracker::enqueue_compute(const uint8_t* d_left, const uint8_t* d_right,
         DVFE_CHECK(launch_compact(bg, B, cap, st, nullptr, reuse ? d_old_idx : nullptr));
     mark(ST_COMPACT + 1);
     // discs + goodFeaturesToTrack + ids
-    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? 1 : 0], nullptr, B, W, H, cap, st, with_marks ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
+    DVFE_CHECK(launch_gftt(d_jobs[ph][semantic ? (detect_cuda ? 2 : 1) : 0], nullptr, B, W, H, cap, st, with_marks ? &ev[par][ST_GFTT_MASK + 1] : nullptr,
                            stereo_now ? ev_resp[par] : nullptr, use_tma ? tmapL[k % 3] : nullptr,
                            (int)(desc.bytes / (unsigned)desc.lv[0].pitch)));
     if (stereo_now) {
@@ -767,6 +769,14 @@ extern "C" int dvfe_set_lk_mode_site(dvfe_tracker* t, int site, int back_max_lev
 
 extern "C" int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold) {
     return dvfe_set_lk_mode_site(t, -1, back_max_level, fb_threshold);
+}
+
+extern "C" int dvfe_set_detect_mode(dvfe_tracker* t, int mode) {
+    if (!t || (mode != DVFE_DETECT_CPU && mode != DVFE_DETECT_CUDA)) { dvfe_set_error("set_detect_mode: bad argument"); return DVFE_ERR_INVALID; }
+    if (IS_GROUP(t)) return grp_set_detect_mode(t, mode);
+    t->detect_cuda = mode == DVFE_DETECT_CUDA;
+    t->drop_graphs();                 // the captured steps carry the old job table
+    return DVFE_OK;
 }
 
 int dvfe_tracker::semantic_submit(const uint8_t* left, const uint8_t* right, const uint8_t* mask,

@@ -66,7 +66,7 @@ struct dvfe_tracker {
     bool inst_pending[2] = {false, false};           // the step carried a deferred InstsTrack (dvfe_track_dynamic_async)
     GfttScratch gsc{};
     LkGroup* d_groups[6][3] = {};                    // [phase][temporal raw | temporal semantic | stereo]
-    GfttJob* d_jobs[6][2] = {};                      // [phase][raw | semantic]
+    GfttJob* d_jobs[6][3] = {};                      // [phase][raw | semantic | semantic, cv::cuda detector threshold]
     InstanceState* inst = nullptr;
     unsigned* d_tcache = nullptr;                    // LK template cache [B][cap][DVFE_MAX_PYR_LEVELS][LK_TCACHE_WORDS] (stereo only)
     bool tcache_valid = false;                       // the last step ran the stereo LK on the points `bg` holds now
@@ -83,6 +83,7 @@ struct dvfe_tracker {
     typedef std::tuple<int, unsigned> StepKey;       // buffer phase, mode flags (the caller's image pointers stay outside)
     struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned n_kernels = 0; };
     std::map<StepKey, StepGraph> step_graphs;
+    bool detect_cuda = false;                        // dvfe_set_detect_mode: semantic-path detection with the cv::cuda detector's threshold
     bool use_graphs = true;
     bool use_reuse = true;                           // DVFE_REUSE=0: the stereo call rebuilds every forward template (A/B, debugging)
     void drop_graphs();

@@ -68,16 +68,18 @@ def min_eigen_val(img):
 
 
 def good_features(img, max_corners: int, quality: float, min_dist: float, mask=None, eig=None,
-                  return_n_candidates: bool = False):
-    """cv::goodFeaturesToTrack(img, K, quality, min_dist, mask); `eig` overrides the response map."""
+                  return_n_candidates: bool = False, cuda_semantics: bool = False):
+    """cv::goodFeaturesToTrack(img, K, quality, min_dist, mask); `eig` overrides the response map.  cuda_semantics: the
+    cv::cuda detector's threshold (0.01 x the maximum of the whole response map), DetectShiTomasiCornersGpu."""
     img = _u8(img) if img is not None else None
     h, w = (img.shape if img is not None else eig.shape)
     e = np.ascontiguousarray(eig, np.float32) if eig is not None else None
     m = _u8(mask) if mask is not None else None
     out = np.zeros((max_corners, 2), np.float32)
     n, nc = C.c_int(0), C.c_int(0)
-    L.check(L.lib().dvfe_op_good_features(L.ptr(img), w, h, w, L.ptr(e), L.ptr(m), w, int(max_corners),
-                                          float(quality), float(min_dist), L.ptr(out), C.byref(n), C.byref(nc)))
+    fn = L.lib().dvfe_op_good_features_cuda if cuda_semantics else L.lib().dvfe_op_good_features
+    L.check(fn(L.ptr(img), w, h, w, L.ptr(e), L.ptr(m), w, int(max_corners), float(quality), float(min_dist), L.ptr(out), C.byref(n),
+               C.byref(nc)))
     res = out[:n.value].copy()
     return (res, nc.value) if return_n_candidates else res
 

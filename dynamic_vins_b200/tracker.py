@@ -158,6 +158,20 @@ class BatchTracker:
         CPU FeatureTrackByLK: (1, 0.5); cv::cuda call pattern of FeatureTrackByLKGpu: (3, 1.0)."""
         L.check(L.lib().dvfe_set_lk_mode_site(self._h, int(site), int(back_max_level), float(fb_threshold)))
 
+    def set_detect_mode(self, cuda_semantics: bool) -> None:
+        """Detector of the semantic path: cv::goodFeaturesToTrack (False, TrackSemanticImage) or the cv::cuda detector's
+        threshold rule (True, TrackImageNaive's DetectShiTomasiCornersGpu)."""
+        L.check(L.lib().dvfe_set_detect_mode(self._h, 1 if cuda_semantics else 0))
+
+    def track_image_naive(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
+        """FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516): the semantic step with the cv::cuda call
+        pattern at both LK sites and the cv::cuda detector's threshold."""
+        if not getattr(self, "_naive", False):
+            self.set_lk_mode(3, 1.0)
+            self.set_detect_mode(True)
+            self._naive = True
+        self.track_semantic_image(left, right, inv_merge_mask, exist_inst, time0)
+
     def track_semantic_image(self, left, right, inv_merge_mask, exist_inst, time0) -> None:
         l = self._batch(left, self.B, self.H, self.W, self.ch)
         r = self._batch(right, self.B, self.H, self.W, self.ch)

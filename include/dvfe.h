@@ -178,6 +178,19 @@ int dvfe_track_image_device_async(dvfe_tracker* t, const uint8_t* d_left, const 
 int dvfe_set_lk_mode(dvfe_tracker* t, int back_max_level, double fb_threshold);
 int dvfe_set_lk_mode_site(dvfe_tracker* t, int site, int back_max_level, double fb_threshold);
 
+/* Which detector InstFeat::DetectNewFeature (front_end/instance_feature.cpp:352-392) of the background uses in the semantic path:
+ *   DVFE_DETECT_CPU   cv::goodFeaturesToTrack (use_gpu = false: TrackSemanticImage, front_end/background_tracker.cpp:789); default
+ *   DVFE_DETECT_CUDA  DetectShiTomasiCornersGpu (use_gpu = true: TrackImageNaive, :445; front_end/feature_utils.cpp:339-348), i.e.
+ *                     cv::cuda::GoodFeaturesToTrackDetector: the quality threshold is 0.01 x the maximum of the WHOLE response
+ *                     map (cuda::minMax without the mask; the CPU detector takes the maximum over the unmasked pixels); candidates,
+ *                     ordering and the distance grid are the same.  Evaluated with this library's CPU-parity response arithmetic
+ *                     (cv::cuda's fp32 box sums are not reproduced; its candidate buffer of max(1000, 5 % of the pixels) entries
+ *                     is not modelled either).
+ * TrackImageNaive = dvfe_set_lk_mode(t, 3, 1.0) + dvfe_set_detect_mode(t, DVFE_DETECT_CUDA) + dvfe_track_semantic_image. */
+#define DVFE_DETECT_CPU 0
+#define DVFE_DETECT_CUDA 1
+int dvfe_set_detect_mode(dvfe_tracker* t, int mode);
+
 /* FeatureTracker::TrackSemanticImage(SemanticImage&) (front_end/background_tracker.cpp:757-837).
  * inv_merge_mask: HOST, same layout as left (0 = object, 255 = background), may be NULL when no stream has
  * instances; exist_inst[s] = SemanticImage::exist_inst. */
@@ -277,6 +290,10 @@ int dvfe_op_good_features(const uint8_t* img, int w, int h, int pitch, const flo
                           int* n_out, int* n_candidates_out);
 
 /* for each pt: cv::circle(mask, pt, radius, 0, -1) (front_end/background_tracker.cpp:79-80). In place. */
+/* The same with the cv::cuda detector's threshold (DVFE_DETECT_CUDA above): DetectShiTomasiCornersGpu, front_end/feature_utils.cpp:339-348. */
+int dvfe_op_good_features_cuda(const uint8_t* img, int w, int h, int pitch, const float* eig, const uint8_t* mask,
+                               int mask_pitch, int max_corners, double quality, double min_dist, float* corners_out,
+                               int* n_out, int* n_candidates_out);
 int dvfe_op_disc_mask(uint8_t* mask, int w, int h, int pitch, const float* pts, int n, int radius);
 
 /* ErodeMask(in,out,k): cv::erode with a k x k MORPH_RECT element (front_end/feature_utils.h:142-146). */

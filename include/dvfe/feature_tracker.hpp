@@ -183,11 +183,13 @@ public:
         prev_img = cur_img;
         return SetOutputFeats();
     }
-    // FeatureTracker::TrackImageNaive (:400-516): the cv::cuda call pattern at every LK site, evaluated with this library's
-    // fixed-point LK arithmetic; the dynamic regions are removed through inv_merge_mask like TrackSemanticImage does.
+    // FeatureTracker::TrackImageNaive (:400-516): the cv::cuda flow — ErodeMaskGpu, TrackLeftGPU, DetectNewFeature(use_gpu),
+    // TrackRightGPU — i.e. the cv::cuda call pattern at both LK sites and the cv::cuda detector's threshold rule, evaluated with
+    // this library's CPU-parity arithmetic; the dynamic regions are removed through inv_merge_mask like TrackSemanticImage does.
     FeatureBackground TrackImageNaive(SemanticImage& img) {
         if (!naive_mode_) {
             if (dvfe_set_lk_mode(h_, 3, 1.0) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
+            if (dvfe_set_detect_mode(h_, DVFE_DETECT_CUDA) != DVFE_OK) throw std::runtime_error(dvfe_last_error(h_));
             naive_mode_ = true;
         }
         return TrackSemanticImage(img);

@@ -209,6 +209,24 @@ def good_features(gray: np.ndarray, max_corners: int, min_dist: float, mask: Opt
     return p.reshape(-1, 2).astype(f32)
 
 
+def good_features_cuda_semantics(gray: np.ndarray, max_corners: int, min_dist: float, mask: Optional[np.ndarray]):
+    """DetectShiTomasiCornersGpu (front_end/feature_utils.cpp:339-348): cv::cuda::createGoodFeaturesToTrackDetector(CV_8UC1, n,
+    0.01, min_dist)->detect(img, pts, mask).  The detector lives in a CUDA build of OpenCV that does not exist in this image
+    (UNPINNED); its published algorithm (opencv/modules/cudaimgproc/src/gftt.cpp, cuda/gftt.cu) is restated here with the CPU
+    response arithmetic: minimum-eigenvalue map (blockSize 3, Sobel 3); maxVal = cuda::minMax over the WHOLE map (no mask, the one
+    deterministic difference from cv::goodFeaturesToTrack); candidates 1 <= x < W-1, 1 <= y < H-1 with mask != 0,
+    val > (float)(maxVal * quality) and val == max of its 3x3 neighbourhood; sorted by val descending (thrust's order among
+    equal values is unspecified: address descending here, as the CPU detector); the host-side distance grid of the CPU detector.
+    Not reproduced: fp32 box sums of the cuda kernel, and its candidate buffer of max(1000, 5 % of the pixels) entries, which
+    drops candidates in atomic order when it overflows (it does not at the candidate counts of this path)."""
+    from oracle import spec
+    if max_corners <= 0:
+        return np.zeros((0, 2), dtype=f32)
+    eig = cv2.cornerMinEigenVal(gray, 3, ksize=3)
+    pts, _ = spec.gftt_select(eig, mask, max_corners, 0.01, float(min_dist), unmasked_max=True)
+    return pts.astype(f32)
+
+
 def instance_image_padding(img1: np.ndarray, img2: np.ndarray):
     """front_end/feature_utils.cpp:406-413."""
     rows = max(img1.shape[0], img2.shape[0])
@@ -283,11 +301,13 @@ class InstFeat:
             self.right_ids, self.right_un_points, self.right_prev_id_pts, dt)
 
     # front_end/instance_feature.cpp:149-188
-    def track_left(self, curr_img, last_img, P: FrontEndParams, mask=None):
+    def track_left(self, curr_img, last_img, P: FrontEndParams, mask=None, gpu_pattern: bool = False):
         if len(self.last_points) == 0:
             return
+        # gpu_pattern: InstFeat::TrackLeftGPU (:191-225) -> FeatureTrackByLKGpu's backward level / threshold
         pts2, status = feature_track_by_lk(last_img, curr_img, self.last_points, bool(P.flow_back), P.lk_max_level,
-                                           P.lk_back_max_level, P.fb_threshold)
+                                           P.gpu_lk_back_max_level if gpu_pattern else P.lk_back_max_level,
+                                           P.gpu_fb_threshold if gpu_pattern else P.fb_threshold)
         self.curr_points = pts2
         if mask is not None:
             for i in range(len(status)):
@@ -316,13 +336,16 @@ class InstFeat:
         self.right_ids = _reduce(list(self.ids), status)
 
     # front_end/instance_feature.cpp:352-392
-    def detect_new_feature(self, gray0, P: FrontEndParams, min_dist: int, mask=None):
+    def detect_new_feature(self, gray0, P: FrontEndParams, min_dist: int, mask=None, use_gpu: bool = False):
         n_max_cnt = P.max_cnt - len(self.curr_points)
         if n_max_cnt < 10:
             return
         mask_detect = mask.copy() if mask is not None else np.full(gray0.shape, 255, np.uint8)
         draw_discs(mask_detect, self.curr_points, min_dist)
-        n_pts = good_features(gray0, n_max_cnt, P.min_dist, mask_detect)   # uses fe_para::kMinDist (:381-382)
+        if use_gpu:                                                            # :373-379 DetectShiTomasiCornersGpu(.., min_dist)
+            n_pts = good_features_cuda_semantics(gray0, n_max_cnt, min_dist, mask_detect)
+        else:
+            n_pts = good_features(gray0, n_max_cnt, P.min_dist, mask_detect)   # uses fe_para::kMinDist (:381-382)
         self.append_new(n_pts)
 
     def append_new(self, n_pts):
@@ -446,6 +469,33 @@ class FeatureTracker:
         bg.pts_velocity_(dt)
         stereo_now = bool(P.is_stereo and gray1 is not None)
         if stereo_now:                                                              # :797-803 TrackRightGPU call pattern
+            self._right(gray0, gray1, dt, gpu_pattern=True)
+        self.prev_gray0 = gray0
+        self.prev_time = self.cur_time
+        bg.post_process()
+        return self.set_output_feats(stereo_now)
+
+
+    # front_end/background_tracker.cpp:400-516 (the cv::cuda flow: ErodeMaskGpu -> TrackLeftGPU -> DetectNewFeature(use_gpu) ->
+    # TrackRightGPU), with the call pattern of the cv::cuda objects and the CPU arithmetic in their place
+    def track_image_naive(self, gray0, gray1, time0, inv_merge_mask: Optional[np.ndarray], exist_inst: bool):
+        P, bg = self.P, self.bg
+        self.cur_time = time0
+        self.stage = {}
+        if exist_inst and P.use_mask_morphology:                                    # :412-419 (erode on the device, download)
+            inv_merge_mask = erode_mask(inv_merge_mask, P.mask_morphology_size)
+        if exist_inst:                                                              # :421-424
+            mask = inv_merge_mask.copy()
+        else:
+            mask = np.full(gray0.shape, 255, np.uint8)
+        self.stage["region_mask"] = mask.copy()
+        bg.track_left(gray0, self.prev_gray0, P, mask, gpu_pattern=True)            # :437 TrackLeftGPU
+        bg.detect_new_feature(gray0, P, P.min_dist, mask, use_gpu=True)             # :445
+        bg.curr_un_points = self.cam0.undistort_points(bg.curr_points)              # :449
+        dt = self.cur_time - self.prev_time
+        bg.pts_velocity_(dt)
+        stereo_now = bool(P.is_stereo and gray1 is not None)
+        if stereo_now:                                                              # :455-462 TrackRightGPU
             self._right(gray0, gray1, dt, gpu_pattern=True)
         self.prev_gray0 = gray0
         self.prev_time = self.cur_time
@@ -591,7 +641,7 @@ class InstsFeatManager:
 # FeatureTrack() dispatcher for one frame (system/main.cpp:178-330), no ROS/queues
 # --------------------------------------------------------------------------
 class FrontEnd:
-    """mode: 'raw' (TrackImage) or 'dynamic' (TrackSemanticImage + InstsTrack)."""
+    """mode: 'raw' (TrackImage), 'naive' (TrackImageNaive) or 'dynamic' (TrackSemanticImage + InstsTrack)."""
 
     def __init__(self, params: FrontEndParams, cam0: dict, cam1: Optional[dict] = None, mode: str = "raw"):
         self.P = params
@@ -606,6 +656,9 @@ class FrontEnd:
         """frame: dynamic_vins_b200.synth.SynthFrame-shaped object; disp: optional SemanticImage::disp (dynamic mode)."""
         if self.mode == "raw":
             return {"features": self.tracker.track_image(frame.gray0, frame.gray1, frame.time0), "instances": {}}
+        if self.mode == "naive":
+            return {"features": self.tracker.track_image_naive(frame.gray0, frame.gray1, frame.time0, frame.inv_merge_mask,
+                                                               frame.exist_inst), "instances": {}}
         self.insts.begin_frame()
         self.insts.add_instances(frame.gray0, frame.boxes)
         # deterministic id order: background first, then instances (see header)

@@ -94,6 +94,10 @@ void dvref_set_hook_fundamental(void* fm) {
     auto& h = dvshim::hooks();
     h.find_fundamental_mat = reinterpret_cast<decltype(h.find_fundamental_mat)>(fm);
 }
+void dvref_set_hook_gftt_cuda(void* f) {
+    auto& h = dvshim::hooks();
+    h.good_features_cuda = reinterpret_cast<decltype(h.good_features_cuda)>(f);
+}
 
 // ---- camodocal::PinholeCamera ------------------------------------------------------------------------------------
 // cam = {k1, k2, p1, p2, fx, fy, cx, cy}
@@ -361,6 +365,25 @@ int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char
             }
         *n_iout = n;
         return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516): the all-cv::cuda flow.  The cv::cuda objects are
+// hosted (oracle/shim/dvshim_cv.hpp): GpuMat = Mat, SparsePyrLKOpticalFlow and the morphology filter forward to the CPU hooks, the
+// corner detector to the harness's restatement of cv::cuda::GoodFeaturesToTrackDetector.
+int dvref_track_image_naive(void* p, const unsigned char* gray0, const unsigned char* gray1, const unsigned char* inv_merge_mask,
+                            int exist_inst, double time0, unsigned seq, dvref_obs* out, int cap) {
+    try {
+        auto* fe = static_cast<RefFrontEnd*>(p);
+        SemanticImage img = make_image(fe, gray0, gray1, time0, seq);
+        img.gray0_gpu.upload(img.gray0);
+        if (gray1) img.gray1_gpu.upload(img.gray1);
+        img.exist_inst = exist_inst != 0;
+        if (inv_merge_mask) {
+            img.inv_merge_mask = cv::Mat(fe->rows, fe->cols, CV_8UC1, (void*)inv_merge_mask).clone();
+            img.inv_merge_mask_gpu.upload(img.inv_merge_mask);
+        }
+        return flatten(fe->tracker->TrackImageNaive(img), out, cap);
     } catch (const std::exception& e) { return fail(e); }
 }
 

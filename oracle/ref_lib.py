@@ -116,8 +116,23 @@ def _fundamental(p1, p2, n, method, param1, param2, mask):
     return 1
 
 
+def _gftt_cuda(img, rows, cols, step, corners, max_corners, quality, min_dist, mask, mask_step):
+    """cv::cuda::GoodFeaturesToTrackDetector::detect, restated from its published source over cv2 (oracle/cv_front_end.py
+    good_features_cuda_semantics: whole-image maximum for the quality threshold, CPU response arithmetic)"""
+    from oracle import cv_front_end as cvfe
+    a = np.ascontiguousarray(_view(img, rows, cols, step))
+    m = np.ascontiguousarray(_view(mask, rows, cols, mask_step)) if mask else None
+    assert abs(quality - 0.01) < 1e-12
+    pts = cvfe.good_features_cuda_semantics(a, max_corners, min_dist, m)
+    if len(pts) == 0:
+        return 0
+    np.ctypeslib.as_array(corners, (max_corners, 2))[:len(pts)] = pts
+    return len(pts)
+
+
 _CALLBACKS = (_LK_T(_lk), _GFTT_T(_gftt), _ERODE_T(_erode), _CIRCLE_T(_circle), _GRAY_T(_gray))   # keep alive
 _FM_CALLBACK = _FM_T(_fundamental)
+_GFTT_CUDA_CALLBACK = _GFTT_T(_gftt_cuda)
 _lib = None
 
 
@@ -157,6 +172,8 @@ def lib():
         L.dvref_instance_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dvref_set_hooks(*[C.cast(cb, C.c_void_p) for cb in _CALLBACKS])
         L.dvref_set_hook_fundamental(C.cast(_FM_CALLBACK, C.c_void_p))
+        L.dvref_set_hook_gftt_cuda(C.cast(_GFTT_CUDA_CALLBACK, C.c_void_p))
+        L.dvref_track_image_naive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_uint, C.POINTER(Obs), C.c_int]
         L.dvref_reject_with_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.dvref_detect_extra_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p, C.c_int]
@@ -281,7 +298,7 @@ class RefFrontEnd:
         c.min_dist, c.min_dynamic_dist = params.min_dist, params.min_dynamic_dist
         c.flow_back = int(params.flow_back)
         c.use_mask_morphology, c.mask_morphology_size = int(params.use_mask_morphology), params.mask_morphology_size
-        c.width, c.height, c.stereo, c.dynamic = width, height, int(params.is_stereo), int(mode == "dynamic")
+        c.width, c.height, c.stereo, c.dynamic = width, height, int(params.is_stereo), int(mode in ("dynamic", "naive"))
         c.cam0 = _cam8(cam0)
         c.cam1 = _cam8(cam1 if cam1 is not None else cam0)
         self.mode, self.w, self.h_img = mode, width, height
@@ -311,6 +328,15 @@ class RefFrontEnd:
         obs = (Obs * self.cap)()
         if self.mode == "raw":
             n = lib().dvref_track_image(self.h, _ptr(g0), _ptr(g1), float(frame.time0), obs, self.cap)
+            if n < 0:
+                raise RuntimeError(lib().dvref_last_error().decode())
+            assert n <= self.cap
+            return {"features": self._points(obs, n), "instances": {}}
+        if self.mode == "naive":
+            im = None if frame.inv_merge_mask is None else np.ascontiguousarray(frame.inv_merge_mask)
+            n = lib().dvref_track_image_naive(self.h, _ptr(g0), _ptr(g1), _ptr(im), int(bool(frame.exist_inst)), float(frame.time0),
+                                              self.seq, obs, self.cap)
+            self.seq += 1
             if n < 0:
                 raise RuntimeError(lib().dvref_last_error().decode())
             assert n <= self.cap

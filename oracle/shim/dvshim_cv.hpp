@@ -365,6 +365,10 @@ struct Hooks {
     // cv::findFundamentalMat(points1, points2, method, param1, param2, mask): fills mask[n], returns 1 when a matrix was found
     int (*find_fundamental_mat)(const float* pts1, const float* pts2, int n, int method, double param1, double param2,
                                 uchar* mask) = nullptr;
+    // cv::cuda::GoodFeaturesToTrackDetector::detect(image, corners, mask) of a detector created with (maxCorners, qualityLevel,
+    // minDistance, blockSize 3): returns the corner count (the harness restates the published cv::cuda algorithm over cv2)
+    int (*good_features_cuda)(const uchar* img, int rows, int cols, int step, float* corners, int max_corners, double quality,
+                              double min_dist, const uchar* mask, int mask_step) = nullptr;
 };
 Hooks& hooks();
 }  // namespace dvshim
@@ -545,8 +549,28 @@ public:
     virtual ~CornersDetector() {}
     virtual void detect(const GpuMat&, GpuMat&, const GpuMat&) = 0;
 };
-inline Ptr<CornersDetector> createGoodFeaturesToTrackDetector(int, int = 1000, double = 0.01, double = 0.0, int = 3, bool = false,
-                                                              double = 0.04) { dvshim_unreachable("cv::cuda::createGoodFeaturesToTrackDetector"); }
+class dvshim_HostedGftt : public CornersDetector {
+public:
+    dvshim_HostedGftt(int n, double q, double d) : max_corners_(n), quality_(q), min_dist_(d) {}
+    void detect(const GpuMat& image, GpuMat& corners, const GpuMat& mask) override {
+        if (!dvshim::hooks().good_features_cuda) dvshim_unreachable("cv::cuda::CornersDetector::detect (no hook registered)");
+        std::vector<float> buf((size_t)2 * (max_corners_ > 0 ? max_corners_ : 1));
+        const int n = dvshim::hooks().good_features_cuda(image.m.data, image.rows, image.cols, (int)image.m.step, buf.data(), max_corners_,
+                                                         quality_, min_dist_, mask.empty() ? nullptr : mask.m.data,
+                                                         mask.empty() ? 0 : (int)mask.m.step);
+        if (n <= 0) { corners = GpuMat(); return; }              // _corners.release()
+        corners.create(1, n, CV_32FC2);
+        std::memcpy(corners.m.data, buf.data(), sizeof(float) * 2 * (size_t)n);
+    }
+private:
+    int max_corners_;
+    double quality_, min_dist_;
+};
+inline Ptr<CornersDetector> createGoodFeaturesToTrackDetector(int, int maxCorners = 1000, double qualityLevel = 0.01, double minDistance = 0.0,
+                                                              int blockSize = 3, bool useHarris = false, double = 0.04) {
+    if (blockSize != 3 || useHarris) dvshim_unreachable("cv::cuda::createGoodFeaturesToTrackDetector (blockSize != 3 or Harris)");
+    return Ptr<CornersDetector>(std::shared_ptr<CornersDetector>(new dvshim_HostedGftt(maxCorners, qualityLevel, minDistance)));
+}
 class Filter {
 public:
     virtual ~Filter() {}

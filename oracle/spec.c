@@ -358,12 +358,15 @@ static int cand_cmp(const void* pa, const void* pb) {
 
 /* cv::goodFeaturesToTrack stages 2..6 on a given response map `eig` (h*w floats).
  * Returns number of corners written to out_xy (x,y floats, acceptance order). */
-int spec_gftt_select(const float* eig, int w, int h, const uint8_t* mask, int mstride, int max_corners,
-                     double quality, double min_dist, float* out_xy, int* n_cand_out) {
+/* unmasked_max != 0: the quality threshold comes from the maximum over the WHOLE response map (what
+ * cv::cuda::GoodFeaturesToTrackDetector::detect does: cuda::minMax(eig_, 0, &maxVal) without the mask,
+ * opencv/modules/cudaimgproc/src/gftt.cpp; candidates, ordering and the distance grid are the CPU detector's). */
+int spec_gftt_select_ex(const float* eig, int w, int h, const uint8_t* mask, int mstride, int max_corners,
+                        double quality, double min_dist, float* out_xy, int* n_cand_out, int unmasked_max) {
     float maxv = 0; int any = 0;
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
-            if (!mask || mask[(size_t)y * mstride + x]) {
+            if (unmasked_max || !mask || mask[(size_t)y * mstride + x]) {
                 float v = eig[(size_t)y * w + x];
                 if (!any || v > maxv) { maxv = v; any = 1; }
             }
@@ -430,6 +433,11 @@ int spec_gftt_select(const float* eig, int w, int h, const uint8_t* mask, int ms
     }
     free(c);
     return ncorners;
+}
+
+int spec_gftt_select(const float* eig, int w, int h, const uint8_t* mask, int mstride, int max_corners,
+                     double quality, double min_dist, float* out_xy, int* n_cand_out) {
+    return spec_gftt_select_ex(eig, w, h, mask, mstride, max_corners, quality, min_dist, out_xy, n_cand_out, 0);
 }
 
 int spec_good_features(const uint8_t* img, int w, int h, int stride, const uint8_t* mask, int mstride,

@@ -96,15 +96,17 @@ def min_eigen_val(img):
     return out
 
 
-def gftt_select(eig, mask, max_corners, quality, min_dist):
+def gftt_select(eig, mask, max_corners, quality, min_dist, unmasked_max=False):
+    """stages 2..6 of goodFeaturesToTrack on a response map; unmasked_max: cv::cuda detector's threshold (whole-image maximum)"""
     eig = np.ascontiguousarray(eig, np.float32)
     h, w = eig.shape
     out = np.zeros((max(max_corners, 1) if max_corners > 0 else h * w, 2), np.float32)
     m = _u8(mask) if mask is not None else None
     ncand = C.c_int(0)
-    n = lib().spec_gftt_select(_p(eig, C.c_float), w, h, _p(m, C.c_uint8) if m is not None else None, w,
-                               int(max_corners), C.c_double(quality), C.c_double(min_dist), _p(out, C.c_float),
-                               C.byref(ncand))
+    lib().spec_gftt_select_ex.restype = C.c_int
+    n = lib().spec_gftt_select_ex(_p(eig, C.c_float), w, h, _p(m, C.c_uint8) if m is not None else None, w,
+                                  int(max_corners), C.c_double(quality), C.c_double(min_dist), _p(out, C.c_float),
+                                  C.byref(ncand), int(bool(unmasked_max)))
     return out[:n].copy(), ncand.value
 
 

@@ -170,6 +170,30 @@ def test_nms_bit_exact_given_equal_response(kitti_pair, K, md):
         assert np.array_equal(got, cvp.reshape(-1, 2))
 
 
+def test_good_features_cuda_detector_semantics(kitti_pair):
+    """DetectShiTomasiCornersGpu's rule (quality threshold from the whole-image maximum): the op against the restatement, on a
+    given response map (bit-exact) and through the fused response kernel"""
+    import cv2
+    from oracle import cv_front_end as cvfe
+    g = kitti_pair[0].gray0
+    h, w = g.shape
+    mask = np.zeros((h, w), np.uint8)
+    mask[h // 2:, : w // 2] = 255
+    mask[: h // 3, w // 2:] = 255
+    g = g.copy()                                          # weak texture under the mask: the whole-image maximum lies outside it
+    g[mask != 0] = (128 + (g[mask != 0].astype(np.int32) - 128) // 6).astype(np.uint8)
+    eig = cv2.cornerMinEigenVal(g, 3, ksize=3)
+    for K, md in ((150, 30), (400, 10), (7, 3)):
+        want, _ = spec.gftt_select(eig, mask, K, 0.01, md, unmasked_max=True)
+        got = ops.good_features(None, K, 0.01, md, mask=mask, eig=eig, cuda_semantics=True)
+        assert np.array_equal(got, want)
+        fused = ops.good_features(g, K, 0.01, md, mask=mask, cuda_semantics=True)
+        assert np.array_equal(fused, cvfe.good_features_cuda_semantics(g, K, md, mask))
+        cpu_rule, _ = spec.gftt_select(eig, mask, K, 0.01, md)
+        assert np.array_equal(ops.good_features(None, K, 0.01, md, mask=mask, eig=eig), cpu_rule)
+    assert len(ops.good_features(g, 2000, 0.01, 3, mask=mask, cuda_semantics=True)) < len(ops.good_features(g, 2000, 0.01, 3, mask=mask))
+
+
 def test_good_features_degenerate():
     flat = np.full((64, 80), 9, np.uint8)
     assert len(ops.good_features(flat, 10, 0.01, 5)) == 0

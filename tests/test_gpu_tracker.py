@@ -501,6 +501,30 @@ def test_lk_mode_cuda_call_pattern_vs_oracle():
     trk.close()
 
 
+def test_track_image_naive_vs_oracle():
+    """FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516) against the oracle's restatement of it: eroded
+    inverse mask, cv::cuda LK call pattern for the temporal and the stereo call, cv::cuda detector threshold; two streams, the
+    second without instances on some frames"""
+    name = "c3_zed_dynamic"
+    c = synth.CONFIGS[name]
+    B = 2
+    sts = [synth.make_stream(name, 50 + s) for s in range(B)]
+    fes = [cvfe.FrontEnd(params_of(name), c["cam0"], c["cam1"], "naive") for _ in range(B)]
+    trk = BatchTracker(cfg_of(name, n_streams=B))
+    for k in range(6):
+        frs = [st.frame(k) for st in sts]
+        if k in (2, 3):
+            frs[1].exist_inst, frs[1].inv_merge_mask = False, None
+        masks = [fr.inv_merge_mask if fr.inv_merge_mask is not None else np.full(fr.gray0.shape, 255, np.uint8) for fr in frs]
+        trk.track_image_naive(np.stack([fr.gray0 for fr in frs]), np.stack([fr.gray1 for fr in frs]), np.stack(masks),
+                              [1 if fr.exist_inst else 0 for fr in frs], [fr.time0 for fr in frs])
+        for s in range(B):
+            want = fes[s].step(frs[s])["features"]
+            ids, cams, v = feature_map_arrays(want)
+            compare_records(trk.features(s), ids, cams, v, c["cam0"])
+    trk.close()
+
+
 def test_dynamic_mode_batched_streams_equal_single():
     """dvfe_insts_track_batch over B streams == per-stream dvfe_insts_track on single-stream trackers, bit for bit
     (including a stream that has no detections in one frame)"""

@@ -196,3 +196,37 @@ def test_undistort_maps_golden():
     und = ip.run(synth.colorize(gray), None, (m1, m2))[0]
     assert crc(und) == int(g["euroc_undist_gray_crc"])
     assert np.array_equal(und, spec.bgr_to_gray(spec.remap(synth.colorize(gray), m1, m2)))
+
+
+def test_cuda_detector_semantics_restatement(kitti_pair):
+    """oracle.cv_front_end.good_features_cuda_semantics (cv::cuda::GoodFeaturesToTrackDetector restated from its published source,
+    UNPINNED: no CUDA build of OpenCV here) against an independent numpy evaluation of the same rules, and against
+    cv2.goodFeaturesToTrack where the two detectors must agree (no mask: masked maximum == whole-image maximum)"""
+    g = kitti_pair[0].gray0
+    h, w = g.shape
+    no_mask = cvfe.good_features_cuda_semantics(g, 120, 20, None)
+    assert np.array_equal(no_mask, cv2.goodFeaturesToTrack(g, 120, 0.01, 20).reshape(-1, 2))
+    mask = np.zeros((h, w), np.uint8)
+    mask[h // 2:, : w // 2] = 255
+    g = g.copy()                                                           # weak texture under the mask: the strongest corners,
+    g[mask != 0] = (128 + (g[mask != 0].astype(np.int32) - 128) // 6).astype(np.uint8)   # hence the threshold, lie outside it
+    got = cvfe.good_features_cuda_semantics(g, 120, 20, mask)
+    eig = cv2.cornerMinEigenVal(g, 3, ksize=3)
+    thr = np.float32(float(eig.max()) * 0.01)                              # whole-image maximum
+    dil = cv2.dilate(eig, np.ones((3, 3), np.uint8))
+    ys, xs = np.nonzero((eig > thr) & (eig == dil) & (mask != 0))
+    keep = (ys >= 1) & (ys < h - 1) & (xs >= 1) & (xs < w - 1)
+    ys, xs = ys[keep], xs[keep]
+    order = np.lexsort((-(ys * w + xs), -eig[ys, xs].astype(np.float64)))   # value descending, then address descending
+    acc = []
+    for i in order:
+        x, y = int(xs[i]), int(ys[i])
+        if all((x - ax) ** 2 + (y - ay) ** 2 >= 400 for ax, ay in acc):
+            acc.append((x, y))
+            if len(acc) == 120:
+                break
+    assert np.array_equal(got, np.array(acc, np.float32))
+    # with no cap on the count the higher threshold of the cv::cuda rule keeps fewer corners than the CPU detector
+    n_cuda = len(cvfe.good_features_cuda_semantics(g, 100000, 3, mask))
+    n_cpu = len(cv2.goodFeaturesToTrack(g, 100000, 0.01, 3, mask=mask))
+    assert n_cuda < n_cpu, "the masked case must exercise the different threshold"

@@ -202,6 +202,25 @@ def test_dynamic_mode_oracle_equals_reference():
     ref.close()
 
 
+def test_track_image_naive_oracle_equals_reference():
+    """FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516), reference-compiled with hosted cv::cuda objects
+    (GpuMat = Mat; SparsePyrLKOpticalFlow, the morphology filter and the corner detector forward to cv2 / the restated
+    cv::cuda detector), against the restatement: mask erosion, TrackLeftGPU, DetectNewFeature(use_gpu), TrackRightGPU"""
+    name = "c3_zed_dynamic"
+    c = dict(synth.CONFIGS[name])
+    st = synth.make_stream(name, 2)
+    P = _params(c)
+    fe = cvfe.FrontEnd(P, c["cam0"], c["cam1"], "naive")
+    ref = ref_lib.RefFrontEnd(P, c["cam0"], c["cam1"], "naive", c["width"], c["height"])
+    for k in range(6):
+        fr = st.frame(k)
+        if k == 4:
+            fr.exist_inst, fr.inv_merge_mask = False, None                  # a frame without instances: the all-255 mask
+        a, b = fe.step(fr), ref.step(fr)
+        _assert_points_equal(a["features"], b["features"], f"naive frame {k}")
+    ref.close()
+
+
 def test_output_disparity_lookup_is_roi_local():
     """Output() reads prev_img.disp at inst.curr_points — ROI-local coordinates into the full-size map (dynamic_tracker.cpp:547,
     reference quirk Q8).  Non-positive disparities keep DetectExtraPoints (PCL, out of scope) empty."""
@@ -240,6 +259,31 @@ def test_cuda_lift_projective_equals_reference_compiled(cam_name):
     shifted = np.stack([pts[:, 0] + np.float32(off[0]), pts[:, 1] + np.float32(off[1])], 1).astype(np.float32)
     assert np.array_equal(np.asarray(ops.lift_projective(cam, pts, off), np.float32), ref_lib.RefCamera(cam).undistorted_pts(shifted),
                           equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_cuda_track_image_naive_vs_reference_compiled():
+    """the CUDA TrackImageNaive flow (semantic step, cv::cuda LK call pattern at both sites, cv::cuda detector threshold) against
+    the reference-compiled FeatureTracker::TrackImageNaive"""
+    from dynamic_vins_b200 import BatchTracker, make_config, obs_to_map
+    name = "c3_zed_dynamic"
+    c = dict(synth.CONFIGS[name])
+    st = synth.make_stream(name, 6)
+    P = _params(c)
+    ref = ref_lib.RefFrontEnd(P, c["cam0"], c["cam1"], "naive", c["width"], c["height"])
+    trk = BatchTracker(make_config(c["width"], c["height"], c["max_cnt"], c["min_dist"], c["cam0"], c["cam1"], stereo=True,
+                                   use_mask_morphology=c["use_mask_morphology"], mask_morphology_size=c["mask_morphology_size"]))
+    for k in range(5):
+        fr = st.frame(k)
+        want = ref.step(fr)["features"]
+        trk.track_image_naive(fr.gray0, fr.gray1, fr.inv_merge_mask, [1 if fr.exist_inst else 0], fr.time0)
+        got = obs_to_map(trk.features(0))
+        assert sorted(got) == sorted(want), f"frame {k}: ids"
+        for fid in want:
+            assert [cam for cam, _ in got[fid]] == [cam for cam, _ in want[fid]], f"frame {k}: camera list of id {fid}"
+            for (_, a), (_, b) in zip(got[fid], want[fid]):
+                assert np.abs(a[3:5] - b[3:5]).max() <= 0.02
+    trk.close(); ref.close()
 
 
 @pytest.mark.gpu
