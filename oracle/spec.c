@@ -1,7 +1,11 @@
 /* ORACLE (test infrastructure, NOT product code).
  *
- * PARITY UNPINNED against the reference binary (it ships no golden vectors for this path and cannot run here);
- * pinned against the third-party library that holds the arithmetic (cv2 4.13.0), see below.
+ * PARITY STATUS: the stages below are OpenCV's (a third-party dependency of the reference, absent from /root/reference); they are
+ * pinned against cv2 4.13.0 itself at the reference's call sites (tests/test_oracle_pinned.py, tests/test_epipolar.py) and, where
+ * the reference's own code is involved (liftProjective, FeatureTrackByLK's glue, ErodeMask, InstanceImagePadding,
+ * DetectExtraPoints, RejectWithF), against the reference's sources compiled unmodified into oracle/_ref/libdvref.so
+ * (tests/test_ref_compiled.py, tests/test_epipolar.py).  What stays unpinned is the OpenCV version: the reference pins 3.4.16,
+ * the image has 4.13.0.
  *
  * Plain-C arithmetic restatement of the OpenCV stages the reference's CPU front-end
  * calls.  The arithmetic lives in a third-party dependency that is NOT under
