@@ -8,8 +8,10 @@ Follows (reference file:line)
     cameras when is_undistort_input, then SemanticImage::SetGrayImageGpu() = cvtColor(BGR2GRAY) (basic/semantic_image.cpp:76-93).
   * basic/semantic_image.cpp:103-117  SetBackgroundMask(): merge_mask is remapped with the left maps before bitwise_not.
 
-Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.  Pinned against cv2 4.13 (the library
-the reference calls is OpenCV 3.4.16: PARITY UNPINNED against the reference binary, as for the rest of the oracle)."""
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.  PARITY UNPINNED for THIS module: it is a
+sequence of OpenCV calls (pinned against cv2 4.13 in tests/test_oracle_pinned.py; the reference pins OpenCV 3.4.16) and its
+reference sources (image_process.cpp, utils/camera_model.cpp: yaml / ROS parameter plumbing) are not among the translation units
+compiled into oracle/_ref; the front end proper (oracle/cv_front_end.py) is pinned against reference-compiled code."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
