@@ -9,7 +9,7 @@ legs of `bench.py` may import this module.  The product path
 PARITY PINNED against reference-compiled code: the reference ships no tests, golden vectors or fixtures for this
 path, and the whole ROS binary cannot be built here, but its front-end translation units can:
 oracle/ref/Makefile compiles camera_models/src/camera_models/{PinholeCamera,Camera}.cc and
-dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp UNMODIFIED (stand-in
+dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp and basic/semantic_image.cpp UNMODIFIED (stand-in
 third-party headers in oracle/shim/, OpenCV image algorithms served by cv2 through hooks) into oracle/_ref/libdvref.so.
 tests/test_ref_compiled.py asserts that every function of this module and whole-frame `FrontEnd.step` sequences (raw,
 semantic, dynamic) equal that library bit for bit.  What remains unpinned is only the OpenCV version: cv2 4.13.0 runs where
@@ -225,6 +225,18 @@ def good_features_cuda_semantics(gray: np.ndarray, max_corners: int, min_dist: f
     eig = cv2.cornerMinEigenVal(gray, 3, ksize=3)
     pts, _ = spec.gftt_select(eig, mask, max_corners, 0.01, float(min_dist), unmasked_max=True)
     return pts.astype(f32)
+
+
+def set_mask_and_roi(mask_stack: np.ndarray, rects, gray0: np.ndarray):
+    """SemanticImage::SetMaskAndRoi (basic/semantic_image.cpp:20-63): mask_tensor.to(kInt8).abs().clamp(0, 1); merge_mask = 255
+    where any instance is set, inv_merge_mask = bitwise_not; per box the ROI mask full_mask(rect) (255 = object) and gray0(rect)."""
+    # int8 arithmetic: abs(-128) wraps back to -128, which the clamp turns into 0
+    m = np.clip(np.abs(mask_stack.astype(np.int8).astype(np.int16)).astype(np.int8), 0, 1).astype(np.uint8)
+    merge = (np.clip(m.astype(np.int64).sum(0), 0, 1) * 255).astype(np.uint8)
+    inv = np.bitwise_not(merge)
+    masks = [(m[i, y:y + h, x:x + w] * 255).astype(np.uint8) for i, (x, y, w, h) in enumerate(rects)]
+    grays = [gray0[y:y + h, x:x + w].copy() for (x, y, w, h) in rects]
+    return merge, inv, masks, grays
 
 
 def instance_image_padding(img1: np.ndarray, img2: np.ndarray):

@@ -79,7 +79,8 @@ const char* dvref_last_error(void) { return g_err; }
 const char* dvref_sources(void) {
     return "camera_models/src/camera_models/PinholeCamera.cc camera_models/src/camera_models/Camera.cc "
            "dynamic_vins/src/front_end/feature_utils.cpp dynamic_vins/src/front_end/instance_feature.cpp "
-           "dynamic_vins/src/front_end/background_tracker.cpp dynamic_vins/src/front_end/dynamic_tracker.cpp";
+           "dynamic_vins/src/front_end/background_tracker.cpp dynamic_vins/src/front_end/dynamic_tracker.cpp "
+           "dynamic_vins/src/basic/semantic_image.cpp";
 }
 
 void dvref_set_hooks(void* lk, void* gftt, void* erode, void* circle, void* bgr2gray) {
@@ -365,6 +366,44 @@ int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char
             }
         *n_iout = n;
         return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// SemanticImage::SetMaskAndRoi (basic/semantic_image.cpp:20-63) on an N x rows x cols instance-mask tensor (int8 values as the
+// segmentation network leaves them) and N boxes: merge_mask, inv_merge_mask (rows x cols each), and per box the ROI mask
+// full_mask(rect) and the gray crop gray0(rect), written back to back into roi_masks / roi_grays (w*h bytes per box, in order).
+int dvref_set_mask_and_roi(const signed char* masks, int n, int rows, int cols, const unsigned char* gray0, const int* rects /* x y w h */,
+                           unsigned char* merge_mask, unsigned char* inv_merge_mask, unsigned char* roi_masks, unsigned char* roi_grays) {
+    try {
+        SemanticImage img;
+        img.gray0 = cv::Mat(rows, cols, CV_8UC1, (void*)gray0).clone();
+        img.gray0_gpu.upload(img.gray0);
+        std::vector<int64_t> vals((size_t)n * rows * cols);
+        for (size_t i = 0; i < vals.size(); i++) vals[i] = masks[i];
+        img.mask_tensor = torch::Tensor({(int64_t)n, (int64_t)rows, (int64_t)cols}, vals.data(), torch::kInt8);
+        for (int i = 0; i < n; i++) {
+            auto b = std::make_shared<Box2D>();
+            b->id = i; b->track_id = i + 1;
+            b->rect = cv::Rect2f((float)rects[4 * i], (float)rects[4 * i + 1], (float)rects[4 * i + 2], (float)rects[4 * i + 3]);
+            img.boxes2d.push_back(b);
+        }
+        img.SetMaskAndRoi();
+        if (!img.exist_inst) return 0;
+        for (int r = 0; r < rows; r++) {
+            std::memcpy(merge_mask + (size_t)r * cols, img.merge_mask.data + (size_t)r * img.merge_mask.step, (size_t)cols);
+            std::memcpy(inv_merge_mask + (size_t)r * cols, img.inv_merge_mask.data + (size_t)r * img.inv_merge_mask.step, (size_t)cols);
+        }
+        size_t off = 0;
+        for (auto& b : img.boxes2d) {
+            const cv::Mat& m = b->roi->mask_cv;
+            const cv::Mat& g = b->roi->roi_gray;
+            for (int r = 0; r < m.rows; r++) {
+                std::memcpy(roi_masks + off + (size_t)r * m.cols, m.data + (size_t)r * m.step, (size_t)m.cols);
+                std::memcpy(roi_grays + off + (size_t)r * g.cols, g.data + (size_t)r * g.step, (size_t)g.cols);
+            }
+            off += (size_t)m.rows * m.cols;
+        }
+        return n;
     } catch (const std::exception& e) { return fail(e); }
 }
 

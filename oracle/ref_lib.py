@@ -173,6 +173,8 @@ def lib():
         L.dvref_set_hooks(*[C.cast(cb, C.c_void_p) for cb in _CALLBACKS])
         L.dvref_set_hook_fundamental(C.cast(_FM_CALLBACK, C.c_void_p))
         L.dvref_set_hook_gftt_cuda(C.cast(_GFTT_CUDA_CALLBACK, C.c_void_p))
+        L.dvref_set_mask_and_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         L.dvref_track_image_naive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_uint, C.POINTER(Obs), C.c_int]
         L.dvref_reject_with_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.dvref_detect_extra_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -396,3 +398,25 @@ def detect_extra_points(mask, disp, box_xy, fx, fy, cx, cy, baseline) -> np.ndar
     if n < 0:
         raise RuntimeError(lib().dvref_last_error().decode())
     return out[:n].copy()
+
+
+def set_mask_and_roi(mask_stack, rects, gray0):
+    """SemanticImage::SetMaskAndRoi (basic/semantic_image.cpp:20-63), reference-compiled over a stand-in integer tensor:
+    mask_stack int8 [N, H, W] (the segmentation output, any non-zero value = object), rects [(x, y, w, h)] ->
+    (merge_mask, inv_merge_mask, [roi_mask], [roi_gray])"""
+    ms = np.ascontiguousarray(mask_stack, np.int8)
+    n, h, w = ms.shape
+    g = np.ascontiguousarray(gray0, np.uint8)
+    rc = np.ascontiguousarray(np.array(rects, np.int32).reshape(-1, 4))
+    merge, inv = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
+    total = int(sum(int(r[2]) * int(r[3]) for r in rc))
+    rm, rg = np.zeros(max(total, 1), np.uint8), np.zeros(max(total, 1), np.uint8)
+    k = lib().dvref_set_mask_and_roi(_ptr(ms), n, h, w, _ptr(g), _ptr(rc), _ptr(merge), _ptr(inv), _ptr(rm), _ptr(rg))
+    if k < 0:
+        raise RuntimeError(lib().dvref_last_error().decode())
+    masks, grays, off = [], [], 0
+    for x, y, bw, bh in rc:
+        masks.append(rm[off:off + bw * bh].reshape(bh, bw).copy())
+        grays.append(rg[off:off + bw * bh].reshape(bh, bw).copy())
+        off += bw * bh
+    return merge, inv, masks, grays

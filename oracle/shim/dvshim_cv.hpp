@@ -34,6 +34,7 @@ typedef unsigned short ushort;
 #define CV_64F 6
 #define CV_CN_SHIFT 3
 #define CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << CV_CN_SHIFT))
+#define CV_INTER_LINEAR 1
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_16SC2 CV_MAKETYPE(CV_16S, 2)
@@ -501,6 +502,7 @@ public:
     GpuMat() {}
     GpuMat(const Mat& host) { upload(host); }
     GpuMat(int r, int c, int type) { create(r, c, type); }
+    GpuMat(Size s, int type, void* data) : rows(s.height), cols(s.width), m(s.height, s.width, type, data) {}   // a header over the caller's bytes
     void create(int r, int c, int type) { m.create(r, c, type); rows = r; cols = c; }
     bool empty() const { return m.empty(); }
     void upload(const Mat& host) { m = host.clone(); rows = m.rows; cols = m.cols; }
@@ -592,7 +594,13 @@ inline Ptr<Filter> createMorphologyFilter(int op, int, const Mat& kernel, Point 
     return Ptr<Filter>(std::shared_ptr<Filter>(new dvshim_HostedErode(kernel)));
 }
 inline void cvtColor(const GpuMat&, GpuMat&, int, int = 0) { dvshim_unreachable("cv::cuda::cvtColor"); }
-inline void bitwise_not(const GpuMat&, GpuMat&) { dvshim_unreachable("cv::cuda::bitwise_not"); }
+inline void bitwise_not(const GpuMat& src, GpuMat& dst) {
+    if (src.m.type() != CV_8UC1) dvshim_unreachable("cv::cuda::bitwise_not (other than CV_8UC1)");
+    GpuMat out(src.rows, src.cols, src.m.type());
+    for (int r = 0; r < src.rows; r++)
+        for (int c = 0; c < src.cols; c++) out.m.data[(size_t)r * out.m.step + c] = (uchar)~src.m.data[(size_t)r * src.m.step + c];
+    dst = out;
+}
 inline void scaleAdd(const GpuMat&, double, const GpuMat&, GpuMat&) { dvshim_unreachable("cv::cuda::scaleAdd"); }
 }  // namespace cuda
 

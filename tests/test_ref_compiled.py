@@ -202,6 +202,41 @@ def test_dynamic_mode_oracle_equals_reference():
     ref.close()
 
 
+def test_set_mask_and_roi_equals_reference_and_the_label_image():
+    """SURVEY §8f N1: SemanticImage::SetMaskAndRoi (basic/semantic_image.cpp:20-63), reference-compiled over a stand-in integer
+    tensor, against (a) the restatement, (b) the masks the synthetic frames carry (what the host-mask interface is fed with) and
+    (c) the label image the device path takes (DVFE_DYN_LABELS: bit b = instance b), which must decode to the same masks —
+    tests/test_gpu_cpp_dynamic.py::test_label_image_path_equals_mask_path_and_oracle closes the loop on the GPU."""
+    st = synth.make_stream("c3_zed_dynamic", 3)
+    rng = np.random.default_rng(5)
+    for k in (0, 2, 5):
+        fr = st.frame(k)
+        H, W = fr.gray0.shape
+        stack = np.zeros((len(fr.boxes), H, W), np.int8)
+        rects = []
+        for i, b in enumerate(fr.boxes):
+            x, y, w, h = b["rect"]
+            rects.append((x, y, w, h))
+            # the network's mask values: any non-zero int8 marks the object (abs + clamp in the reference), -128 wraps to "not set"
+            val = np.int8(rng.choice([1, -1, 3, 127, -127]))
+            stack[i, y:y + h, x:x + w] = (b["mask"] != 0).astype(np.int8) * val
+        merge, inv, masks, grays = ref_lib.set_mask_and_roi(stack, rects, fr.gray0)
+        r_merge, r_inv, r_masks, r_grays = cvfe.set_mask_and_roi(stack, rects, fr.gray0)
+        assert np.array_equal(merge, r_merge) and np.array_equal(inv, r_inv)
+        assert all(np.array_equal(a, b) for a, b in zip(masks, r_masks)) and all(np.array_equal(a, b) for a, b in zip(grays, r_grays))
+        assert np.array_equal(inv, fr.inv_merge_mask) and np.array_equal(merge, fr.merge_mask)
+        assert all(np.array_equal(m, b["mask"]) for m, b in zip(masks, fr.boxes))
+        labels, lboxes = synth.label_image(fr)
+        assert np.array_equal(np.where(labels == 0, 255, 0).astype(np.uint8), inv)
+        for m, b in zip(masks, lboxes):
+            x, y, w, h = b["rect"]
+            assert np.array_equal(np.where((labels[y:y + h, x:x + w] >> b["label_bit"]) & 1, 255, 0).astype(np.uint8), m)
+    edge = np.zeros((1, 8, 8), np.int8)
+    edge[0, 2:5, 2:5] = -128
+    m2 = ref_lib.set_mask_and_roi(edge, [(0, 0, 8, 8)], np.zeros((8, 8), np.uint8))
+    assert m2[0].max() == 0 and np.array_equal(m2[0], cvfe.set_mask_and_roi(edge, [(0, 0, 8, 8)], np.zeros((8, 8), np.uint8))[0])
+
+
 def test_track_image_naive_oracle_equals_reference():
     """FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516), reference-compiled with hosted cv::cuda objects
     (GpuMat = Mat; SparsePyrLKOpticalFlow, the morphology filter and the corner detector forward to cv2 / the restated
