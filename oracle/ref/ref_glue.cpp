@@ -34,6 +34,7 @@
 #undef private
 #include "front_end/feature_utils.h"
 #include "front_end/front_end_parameters.h"
+#include "utils/io/feature_serialization.h"
 #include "camodocal/camera_models/PinholeCamera.h"
 
 // ---- shim state ----------------------------------------------------------------------------------------------------
@@ -80,7 +81,7 @@ const char* dvref_sources(void) {
     return "camera_models/src/camera_models/PinholeCamera.cc camera_models/src/camera_models/Camera.cc "
            "dynamic_vins/src/front_end/feature_utils.cpp dynamic_vins/src/front_end/instance_feature.cpp "
            "dynamic_vins/src/front_end/background_tracker.cpp dynamic_vins/src/front_end/dynamic_tracker.cpp "
-           "dynamic_vins/src/basic/semantic_image.cpp";
+           "dynamic_vins/src/basic/semantic_image.cpp dynamic_vins/src/utils/io/feature_serialization.cpp";
 }
 
 void dvref_set_hooks(void* lk, void* gftt, void* erode, void* circle, void* bgr2gray) {
@@ -366,6 +367,28 @@ int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char
             }
         *n_iout = n;
         return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// SerializePointFeature / DeserializePointFeature (utils/io/feature_serialization.cpp:26-70) on flat records (id, cam, 7 doubles),
+// sorted by (id, cam).  fmt::format is the stand-in of oracle/shim/dvshim_fmt.hpp (shortest round-trip numbers).
+int dvref_serialize_points(const char* path, const dvref_obs* obs, int n) {
+    try {
+        std::map<unsigned int, std::vector<std::pair<int, Eigen::Matrix<double, 7, 1>>>> points;
+        for (int i = 0; i < n; i++) {
+            Eigen::Matrix<double, 7, 1> v;
+            for (int k = 0; k < 7; k++) v(k, 0) = obs[i].v[k];
+            points[obs[i].id].push_back({obs[i].cam, v});
+        }
+        SerializePointFeature(path, points);
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+int dvref_deserialize_points(const char* path, dvref_obs* out, int cap) {
+    try {
+        FeatureBackground fb;
+        fb.points = DeserializePointFeature(path);
+        return flatten(fb, out, cap);
     } catch (const std::exception& e) { return fail(e); }
 }
 

@@ -173,6 +173,8 @@ def lib():
         L.dvref_set_hooks(*[C.cast(cb, C.c_void_p) for cb in _CALLBACKS])
         L.dvref_set_hook_fundamental(C.cast(_FM_CALLBACK, C.c_void_p))
         L.dvref_set_hook_gftt_cuda(C.cast(_GFTT_CUDA_CALLBACK, C.c_void_p))
+        L.dvref_serialize_points.argtypes = [C.c_char_p, C.POINTER(Obs), C.c_int]
+        L.dvref_deserialize_points.argtypes = [C.c_char_p, C.POINTER(Obs), C.c_int]
         L.dvref_set_mask_and_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
         L.dvref_track_image_naive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_uint, C.POINTER(Obs), C.c_int]
@@ -420,3 +422,26 @@ def set_mask_and_roi(mask_stack, rects, gray0):
         grays.append(rg[off:off + bw * bh].reshape(bh, bw).copy())
         off += bw * bh
     return merge, inv, masks, grays
+
+
+def serialize_point_features(path: str, points: Dict[int, List[Tuple[int, np.ndarray]]]) -> None:
+    """SerializePointFeature (utils/io/feature_serialization.cpp:26-38), reference-compiled (fmt::format is a stand-in that prints
+    the shortest round-trip form)"""
+    flat = [(fid, cam, v) for fid in sorted(points) for cam, v in points[fid]]
+    obs = (Obs * max(len(flat), 1))()
+    for i, (fid, cam, v) in enumerate(flat):
+        obs[i].id, obs[i].cam = fid, cam
+        for k in range(7):
+            obs[i].v[k] = float(v[k])
+    if lib().dvref_serialize_points(path.encode(), obs, len(flat)) < 0:
+        raise RuntimeError(lib().dvref_last_error().decode())
+
+
+def deserialize_point_features(path: str, cap: int = 65536) -> Dict[int, List[Tuple[int, np.ndarray]]]:
+    """DeserializePointFeature (utils/io/feature_serialization.cpp:45-70), reference-compiled"""
+    obs = (Obs * cap)()
+    n = lib().dvref_deserialize_points(path.encode(), obs, cap)
+    if n < 0:
+        raise RuntimeError(lib().dvref_last_error().decode())
+    assert n <= cap
+    return RefFrontEnd._points(obs, n)

@@ -18,7 +18,4 @@ public:
     void flush_on(level::level_enum) {}
 };
 }
-namespace fmt {
-template <class... A> inline std::string format(const char* f, const A&...) { return std::string(f); }
-template <class... A> inline std::string format(const std::string& f, const A&...) { return f; }
-}
+#include "../dvshim_fmt.hpp"

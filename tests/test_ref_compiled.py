@@ -7,6 +7,8 @@ the restatement in oracle/cv_front_end.py and the plain-C spec must reproduce wh
 The CPU half runs wherever the library exists (here; the GPU box gets the prebuilt file).  The `gpu` half compares the
 CUDA path with the reference-compiled library directly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -235,6 +237,53 @@ def test_set_mask_and_roi_equals_reference_and_the_label_image():
     edge[0, 2:5, 2:5] = -128
     m2 = ref_lib.set_mask_and_roi(edge, [(0, 0, 8, 8)], np.zeros((8, 8), np.uint8))
     assert m2[0].max() == 0 and np.array_equal(m2[0], cvfe.set_mask_and_roi(edge, [(0, 0, 8, 8)], np.zeros((8, 8), np.uint8))[0])
+
+
+def test_point_feature_text_format_equals_reference(tmp_path):
+    """the reference's SerializePointFeature / DeserializePointFeature (utils/io/feature_serialization.cpp:26-70,
+    reference-compiled) against the three writers / readers of this repository: the Python mirror, the C++ header
+    include/dvfe/frontend_io.hpp and the oracle.  Values must survive every combination bit for bit."""
+    import subprocess
+    from conftest import ROOT
+    from dynamic_vins_b200 import tracker as T
+    rng = np.random.default_rng(3)
+    points = {}
+    for fid in sorted(rng.choice(5000, 60, replace=False).tolist()):
+        obs = [(0, rng.normal(0, 1, 7) * 10.0 ** rng.integers(-6, 4))]
+        if fid % 3:
+            obs.append((1, rng.normal(0, 1, 7)))
+        points[int(fid)] = obs
+    points[7] = [(0, np.array([1.0, -0.0, 1e-300, 123456789.125, 0.1, 1 / 3, -2.5e-7]))]
+
+    def same(a, b):
+        assert sorted(a) == sorted(b)
+        for fid in a:
+            assert [c for c, _ in a[fid]] == [c for c, _ in b[fid]]
+            for (_, x), (_, y) in zip(a[fid], b[fid]):
+                assert np.array_equal(np.asarray(x, np.float64), np.asarray(y, np.float64)), fid
+
+    # Python mirror -> reference reader ; reference writer -> Python mirror
+    p1 = str(tmp_path / "py.txt")
+    open(p1, "w").write(T.serialize_point_features(points))
+    same(ref_lib.deserialize_point_features(p1), points)
+    p2 = str(tmp_path / "ref.txt")
+    ref_lib.serialize_point_features(p2, points)
+    same(T.deserialize_point_features(open(p2).read()), points)
+    # line layout: "<0|1> <id> <7 or 14 numbers>" in both writers
+    for a, b in zip(open(p1).read().splitlines(), open(p2).read().splitlines()):
+        ta, tb = a.split(), b.split()
+        assert ta[:2] == tb[:2] and len(ta) == len(tb) == (16 if ta[0] == "1" else 9)
+        assert [float(x) for x in ta[2:]] == [float(x) for x in tb[2:]]
+    # the C++ header's writer (tests/cpp/test_frontend_io.cpp host mode writes <dir>/3_point.txt) read by the reference, and the
+    # reference's file read by the C++ header's reader (host mode re-reads its own file; here: both parse the same bytes)
+    exe = str(tmp_path / "test_frontend_io")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
+                           os.path.join(ROOT, "tests", "cpp", "test_frontend_io.cpp"), "-L" + os.path.join(ROOT, "dynamic_vins_b200"),
+                           "-ldvfe", "-lpthread", "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe])
+    subprocess.check_call([exe, "host", str(tmp_path)], stdout=subprocess.DEVNULL)
+    cpp_file = str(tmp_path / "3_point.txt")
+    same(ref_lib.deserialize_point_features(cpp_file), T.deserialize_point_features(open(cpp_file).read()))
+    assert len(ref_lib.deserialize_point_features(cpp_file)) == 40
 
 
 def test_track_image_naive_oracle_equals_reference():
