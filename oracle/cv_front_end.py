@@ -9,7 +9,7 @@ legs of `bench.py` may import this module.  The product path
 PARITY PINNED against reference-compiled code: the reference ships no tests, golden vectors or fixtures for this
 path, and the whole ROS binary cannot be built here, but its front-end translation units can:
 oracle/ref/Makefile compiles camera_models/src/camera_models/{PinholeCamera,Camera}.cc and
-dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp and basic/semantic_image.cpp UNMODIFIED (stand-in
+dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp, basic/semantic_image.cpp and utils/io/feature_serialization.cpp UNMODIFIED (stand-in
 third-party headers in oracle/shim/, OpenCV image algorithms served by cv2 through hooks) into oracle/_ref/libdvref.so.
 tests/test_ref_compiled.py asserts that every function of this module and whole-frame `FrontEnd.step` sequences (raw,
 semantic, dynamic) equal that library bit for bit.  What remains unpinned is only the OpenCV version: cv2 4.13.0 runs where

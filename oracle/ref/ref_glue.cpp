@@ -4,6 +4,7 @@
 // into oracle/_ref/libdvref.so:
 //     camera_models/src/camera_models/{PinholeCamera,Camera}.cc
 //     dynamic_vins/src/front_end/{feature_utils,instance_feature,background_tracker,dynamic_tracker}.cpp
+//     dynamic_vins/src/basic/semantic_image.cpp, dynamic_vins/src/utils/io/feature_serialization.cpp
 // against the stand-in third-party headers in oracle/shim/ (Eigen / OpenCV containers; OpenCV image algorithms are forwarded
 // through hooks to cv2 by the Python harness, oracle/ref_lib.py).  This file only (a) defines the few out-of-scope symbols
 // those translation units reference (line detector, yaml parameter loading, camera globals), (b) converts flat C arrays to
