@@ -36,6 +36,7 @@
 #include "front_end/feature_utils.h"
 #include "front_end/front_end_parameters.h"
 #include "utils/io/feature_serialization.h"
+#include "basic/feature_queue.h"
 #include "camodocal/camera_models/PinholeCamera.h"
 
 // ---- shim state ----------------------------------------------------------------------------------------------------
@@ -369,6 +370,30 @@ int dvref_track_dynamic(void* p, const unsigned char* gray0, const unsigned char
         *n_iout = n;
         return 0;
     } catch (const std::exception& e) { return fail(e); }
+}
+
+// basic/feature_queue.h:19-71, the reference's FeatureQueue itself (header-only), one object per handle
+void* dvref_queue_new(void) { return new FeatureQueue(); }
+void dvref_queue_free(void* q) { delete static_cast<FeatureQueue*>(q); }
+void dvref_queue_push(void* q, unsigned seq, double time) {
+    FrontendFeature f;
+    f.seq_id = seq; f.time = time;
+    static_cast<FeatureQueue*>(q)->push_back(f);
+}
+int dvref_queue_request(void* q, unsigned* seq, double* time) {
+    auto f = static_cast<FeatureQueue*>(q)->request();
+    if (!f) return 0;
+    *seq = f->seq_id; *time = f->time;
+    return 1;
+}
+int dvref_queue_size(void* q) { return static_cast<FeatureQueue*>(q)->size(); }
+int dvref_queue_empty(void* q) { return static_cast<FeatureQueue*>(q)->empty() ? 1 : 0; }
+void dvref_queue_clear(void* q) { static_cast<FeatureQueue*>(q)->clear(); }
+int dvref_queue_front_time(void* q, double* time) {
+    auto t = static_cast<FeatureQueue*>(q)->front_time();
+    if (!t) return 0;
+    *time = *t;
+    return 1;
 }
 
 // SerializePointFeature / DeserializePointFeature (utils/io/feature_serialization.cpp:26-70) on flat records (id, cam, 7 doubles),

@@ -286,6 +286,21 @@ def test_point_feature_text_format_equals_reference(tmp_path):
     assert len(ref_lib.deserialize_point_features(cpp_file)) == 40
 
 
+def test_feature_queue_equals_reference(tmp_path):
+    """FeatureQueue of include/dvfe/frontend_io.hpp against the reference's own FeatureQueue
+    (basic/feature_queue.h:19-71, inside oracle/_ref/libdvref.so) under one operation script: FIFO order, the bound of
+    kImageQueueSize frames, the 30 ms timed request on an empty queue, front_time, clear"""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "test_queue_vs_reference")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_queue_vs_reference.cpp"), "-L" + os.path.join(ROOT, "dynamic_vins_b200"),
+                           "-ldvfe", "-ldl", "-lpthread", "-Wl,-rpath," + os.path.join(ROOT, "dynamic_vins_b200"), "-o", exe])
+    out = subprocess.run([exe, ref_lib.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "queue equals the reference's FeatureQueue" in out.stdout
+
+
 def test_track_image_naive_oracle_equals_reference():
     """FeatureTracker::TrackImageNaive (front_end/background_tracker.cpp:400-516), reference-compiled with hosted cv::cuda objects
     (GpuMat = Mat; SparsePyrLKOpticalFlow, the morphology filter and the corner detector forward to cv2 / the restated
