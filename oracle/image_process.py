@@ -21,12 +21,18 @@ import numpy as np
 
 
 def undistort_maps(cam: dict, width: int, height: int) -> Tuple[np.ndarray, np.ndarray, dict]:
-    """(map1 CV_16SC2, map2 CV_16UC1, camera after undistortion) as InitOneCamera() builds them"""
-    K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], np.float64)
-    D = np.array([cam.get("k1", 0), cam.get("k2", 0), cam.get("p1", 0), cam.get("p2", 0)], np.float64)
+    """(map1 CV_16SC2, map2 CV_16UC1, camera after undistortion) as InitOneCamera() builds them (utils/camera_model.cpp:441-501).
+    Followed to the letter, including two properties of the reference a clean-room version would not have:
+      * K0 and D0 are cv::Mat_<float>: the intrinsics are narrowed to float before OpenCV sees them (:446-450);
+      * D0 = (k1, k2, 0, p1, p2) (:450, commented "k1 k2 k3 p1 p2"), which OpenCV reads as (k1, k2, p1, p2, k3): the maps are
+        built with p1 = 0, p2 = the camera's p1 and k3 = the camera's p2.
+    The camera used afterwards is the distortion-free pinhole with new_K read back as float (SetCameraIntrinsicByK, :347-358)."""
+    K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], np.float32)
+    D = np.array([cam.get("k1", 0), cam.get("k2", 0), 0, cam.get("p1", 0), cam.get("p2", 0)], np.float32).reshape(5, 1)
     new_k, _ = cv2.getOptimalNewCameraMatrix(K, D, (width, height), 0, (width, height))
     map1, map2 = cv2.initUndistortRectifyMap(K, D, None, new_k, (width, height), cv2.CV_16SC2)
-    new_cam = dict(fx=float(new_k[0, 0]), fy=float(new_k[1, 1]), cx=float(new_k[0, 2]), cy=float(new_k[1, 2]),
+    nk = np.asarray(new_k, np.float32)              # cam.K0 = new_K0; fx0 = K0.at<float>(0,0) ...
+    new_cam = dict(fx=float(nk[0, 0]), fy=float(nk[1, 1]), cx=float(nk[0, 2]), cy=float(nk[1, 2]),
                    k1=0.0, k2=0.0, p1=0.0, p2=0.0)
     return map1, map2, new_cam
 
